@@ -1,0 +1,855 @@
+// rtw_api.cu — kernels + the C ABI of include/rtw.h.
+//
+// Render = ONE persistent megakernel per GPU (render_kernel): every warp pulls work units (an 8x4-pixel
+// tile x a chunk of samples) from a single atomic counter that all GPUs share, keeps its 32 lanes busy with
+// in-warp path regeneration (ballot + prefix popcount), accumulates radiance per tile in shared memory and
+// adds the finished tile straight into the framebuffer on the first GPU (peer stores over NVLink — the
+// "gather" of src/main.rs:542-547 is fused into the kernel).  Replaces src/main.rs:497-589.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rtw.h"
+#include "rtw_device.cuh"
+#include "scene_host.hpp"
+
+using namespace rtwd;
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+#define RTW_BLOCK 256
+#define RTW_WARPS (RTW_BLOCK / 32)
+
+__global__ void __launch_bounds__(RTW_BLOCK, 2)
+render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
+              unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
+    __shared__ float acc[RTW_WARPS][96];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long rays = 0, units = 0;
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= prm.n_units) break;
+        ++units;
+        const int tile = (int)(unit / (unsigned)prm.chunks), chunk = (int)(unit % (unsigned)prm.chunks);
+        const int s0 = chunk * prm.chunk_spp;
+        const int s1 = min(prm.spp, s0 + prm.chunk_spp);
+        const int n_items = 32 * (s1 - s0);
+        const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+        acc[warp][lane] = 0.f; acc[warp][lane + 32] = 0.f; acc[warp][lane + 64] = 0.f;
+        __syncwarp();
+        int next = 0, pix = 0;
+        bool alive = false;
+        PathState ps;
+        for (;;) {
+            const bool need = !alive;
+            const unsigned mask = __ballot_sync(0xffffffffu, need);
+            if (mask) {
+                if (need) {
+                    const int idx = next + __popc(mask & lt_mask);
+                    if (idx < n_items) {
+                        pix = idx & 31;
+                        const int x = tx * 8 + (pix & 7), y = ty * 4 + (pix >> 3);
+                        if (x < prm.width && y < prm.height) { path_begin(cam, prm, x, y, s0 + (idx >> 5), ps); alive = true; }
+                    }
+                }
+                next += __popc(mask);
+            }
+            if (!__any_sync(0xffffffffu, alive)) { if (next >= n_items) break; continue; }
+            if (alive) {
+                ++rays;
+                if (!path_step(sc, prm, ps)) {
+                    atomicAdd(&acc[warp][pix * 3 + 0], ps.L.x);
+                    atomicAdd(&acc[warp][pix * 3 + 1], ps.L.y);
+                    atomicAdd(&acc[warp][pix * 3 + 2], ps.L.z);
+                    alive = false;
+                }
+            }
+        }
+        __syncwarp();
+        {   // tile -> framebuffer, row 0 = top (y = H-1 of src/main.rs:591)
+            const int x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
+            if (x < prm.width && y < prm.height) {
+                float* dst = fb + ((size_t)(prm.height - 1 - y) * prm.width + x) * 3;
+                const float r = acc[warp][lane * 3], g = acc[warp][lane * 3 + 1], b = acc[warp][lane * 3 + 2];
+                if (prm.accumulate) { atomicAdd_system(dst, r); atomicAdd_system(dst + 1, g); atomicAdd_system(dst + 2, b); }
+                else { dst[0] = r; dst[1] = g; dst[2] = b; }
+            }
+        }
+        __syncwarp();
+    }
+    // ray statistics: one atomic per warp
+    for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0) { atomicAdd(stats, rays); atomicAdd(stats + 1, units); }
+}
+
+// per-path radiance with the render's Philox keys (parity hook rtw_trace_paths)
+__global__ void trace_paths_kernel(DScene sc, DCamera cam, DParams prm, int n, const int* __restrict__ px, const int* __restrict__ py,
+                                   const int* __restrict__ smp, double* __restrict__ out_rgb, int* __restrict__ out_seg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PathState ps;
+    path_begin(cam, prm, px[i], py[i], smp[i], ps);
+    while (path_step(sc, prm, ps)) {}
+    out_rgb[3 * i] = ps.L.x; out_rgb[3 * i + 1] = ps.L.y; out_rgb[3 * i + 2] = ps.L.z;
+    out_seg[i] = ps.segment;
+}
+
+__global__ void philox_kernel(int n, const uint32_t* __restrict__ ctr, const uint32_t* __restrict__ key, uint32_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i], key[2 * i + 1],
+                  out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+}
+
+__global__ void get_ray_kernel(DCamera cam, int n, const double* __restrict__ s, const double* __restrict__ t, const double* __restrict__ xi,
+                               int stride, double* __restrict__ oo, double* __restrict__ od, double* __restrict__ ot, int* __restrict__ nd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StreamRng g; g.xi = xi + (size_t)i * stride; g.n = stride; g.draw = 0;
+    Ray r = camera_get_ray(cam, (float)s[i], (float)t[i], g);
+    oo[3 * i] = r.o.x; oo[3 * i + 1] = r.o.y; oo[3 * i + 2] = r.o.z;
+    od[3 * i] = r.d.x; od[3 * i + 1] = r.d.y; od[3 * i + 2] = r.d.z;
+    ot[i] = r.time; nd[i] = g.draw > stride ? -1 : g.draw;
+}
+
+__global__ void hit_kernel(DScene sc, int n, const double* __restrict__ o, const double* __restrict__ d, const double* __restrict__ tm,
+                           float t_min, float t_max, const double* __restrict__ xi, int stride, int* __restrict__ hit,
+                           double* __restrict__ ot, double* __restrict__ op, double* __restrict__ on, int* __restrict__ front,
+                           double* __restrict__ ou, double* __restrict__ ov, int* __restrict__ mat, int* __restrict__ nd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StreamRng g; g.xi = xi + (size_t)i * stride; g.n = stride; g.draw = 0;
+    Ray r; r.o = mk((float)o[3 * i], (float)o[3 * i + 1], (float)o[3 * i + 2]);
+    r.d = mk((float)d[3 * i], (float)d[3 * i + 1], (float)d[3 * i + 2]); r.time = (float)tm[i];
+    TRay tr = make_tray(r);
+    HitRec rec; rec.t = 0; rec.p = mk(0, 0, 0); rec.normal = mk(0, 0, 0); rec.front = 0; rec.mat = -1; rec.u = 0; rec.v = 0;
+    bool h = world_hit(sc, tr, t_min, t_max, g, true, rec);
+    hit[i] = h ? 1 : 0;
+    ot[i] = rec.t; op[3 * i] = rec.p.x; op[3 * i + 1] = rec.p.y; op[3 * i + 2] = rec.p.z;
+    on[3 * i] = rec.normal.x; on[3 * i + 1] = rec.normal.y; on[3 * i + 2] = rec.normal.z;
+    front[i] = rec.front; ou[i] = rec.u; ov[i] = rec.v; mat[i] = rec.mat + 1;   // back to the 1-based handle
+    nd[i] = g.draw > stride ? -1 : g.draw;
+}
+
+__global__ void aabb_kernel(int n, const double* __restrict__ bmin, const double* __restrict__ bmax, const double* __restrict__ o,
+                            const double* __restrict__ d, float t_min, float t_max, int* __restrict__ hit) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 ro = mk((float)o[3 * i], (float)o[3 * i + 1], (float)o[3 * i + 2]);
+    V3 rd = mk((float)d[3 * i], (float)d[3 * i + 1], (float)d[3 * i + 2]);
+    V3 inv = mk(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
+    V3 oi = mk(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
+    float e;
+    hit[i] = slab((float)bmin[3 * i], (float)bmax[3 * i], (float)bmin[3 * i + 1], (float)bmax[3 * i + 1], (float)bmin[3 * i + 2],
+                  (float)bmax[3 * i + 2], inv, oi, t_min, t_max, e) ? 1 : 0;
+}
+
+__global__ void scatter_kernel(DScene sc, int mat, int n, const double* __restrict__ ro, const double* __restrict__ rd, const double* __restrict__ rt,
+                               const double* __restrict__ p, const double* __restrict__ nrm, const int* __restrict__ front,
+                               const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ xi, int stride,
+                               int* __restrict__ osc, double* __restrict__ oo, double* __restrict__ od, double* __restrict__ ot,
+                               double* __restrict__ oatt, double* __restrict__ oem, int* __restrict__ nd) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    StreamRng g; g.xi = xi + (size_t)i * stride; g.n = stride; g.draw = 0;
+    Ray r; r.o = mk((float)ro[3 * i], (float)ro[3 * i + 1], (float)ro[3 * i + 2]);
+    r.d = mk((float)rd[3 * i], (float)rd[3 * i + 1], (float)rd[3 * i + 2]); r.time = (float)rt[i];
+    HitRec rec; rec.p = mk((float)p[3 * i], (float)p[3 * i + 1], (float)p[3 * i + 2]);
+    rec.normal = mk((float)nrm[3 * i], (float)nrm[3 * i + 1], (float)nrm[3 * i + 2]);
+    rec.front = front[i]; rec.u = (float)u[i]; rec.v = (float)v[i]; rec.t = 0; rec.mat = mat;
+    DMatRec m = load_mat(sc, mat);
+    Ray s; s.o = mk(0, 0, 0); s.d = mk(0, 0, 0); s.time = 0; V3 att = mk(0, 0, 0), em = mk(0, 0, 0);
+    bool ok = scatter(sc, m, r, rec, g, s, att, em);
+    if (!ok) { s.o = mk(0, 0, 0); s.d = mk(0, 0, 0); s.time = 0; att = mk(0, 0, 0); }
+    osc[i] = ok ? 1 : 0;
+    oo[3 * i] = s.o.x; oo[3 * i + 1] = s.o.y; oo[3 * i + 2] = s.o.z;
+    od[3 * i] = s.d.x; od[3 * i + 1] = s.d.y; od[3 * i + 2] = s.d.z; ot[i] = s.time;
+    oatt[3 * i] = att.x; oatt[3 * i + 1] = att.y; oatt[3 * i + 2] = att.z;
+    oem[3 * i] = em.x; oem[3 * i + 1] = em.y; oem[3 * i + 2] = em.z;
+    nd[i] = g.draw > stride ? -1 : g.draw;
+}
+
+__global__ void texture_kernel(DScene sc, int tex, int n, const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ p,
+                               double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 c = texture_value(sc, tex, (float)u[i], (float)v[i], mk((float)p[3 * i], (float)p[3 * i + 1], (float)p[3 * i + 2]));
+    out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
+}
+
+// write_color (src/math.rs:119-132): sqrt(c/spp), clamp [0, 0.999], *256 truncated; NaN -> 0
+__global__ void write_color_kernel(const float* __restrict__ sum, int n, float inv_spp, uint8_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r = sqrtf(sum[i] * inv_spp);
+    float c = r < 0.0f ? 0.0f : (r > 0.999f ? 0.999f : r);
+    c *= 256.0f;
+    out[i] = (c == c) ? (uint8_t)(int)c : 0;
+}
+
+// =================================================================================================
+// host side
+// =================================================================================================
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& m) { g_err = m; return code; }
+#define CUDA_TRY(x)                                                                                  \
+    do {                                                                                             \
+        cudaError_t e_ = (x);                                                                        \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? RTW_ERR_OOM : RTW_ERR_CUDA, \
+                                           std::string(#x) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+struct Replica {
+    int device = -1;
+    uint8_t* blob = nullptr;
+    size_t blob_bytes = 0;
+    DScene ds{};
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long* stats = nullptr;    // [0] rays [1] units
+    int grid = 0;
+};
+
+struct SharedFb {          // framebuffer + unit counter reachable by every GPU / rank
+    uint8_t* base = nullptr;     // [counter (256 B)] [fb floats]
+    size_t bytes = 0;
+    int width = 0, height = 0;
+    bool owner = false, ipc_mapped = false;
+    unsigned int* counter() const { return reinterpret_cast<unsigned int*>(base); }
+    float* fb() const { return reinterpret_cast<float*>(base + 256); }
+};
+
+}  // namespace
+
+struct rtw_scene {
+    rtw::SceneGraph g;
+    rtw::FlatScene flat;
+    bool committed = false;
+    std::vector<Replica> reps;
+    SharedFb local;        // used by rtw_render (in-process, on reps[0].device)
+    SharedFb shared;       // used by rtw_render_shared (cross-process)
+    double ms_commit = 0;
+    uint64_t h2d_commit = 0;
+};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void free_replicas(rtw_scene* s) {
+    for (Replica& r : s->reps) {
+        cudaSetDevice(r.device);
+        if (r.blob) cudaFree(r.blob);
+        if (r.stats) cudaFree(r.stats);
+        if (r.ev0) cudaEventDestroy(r.ev0);
+        if (r.ev1) cudaEventDestroy(r.ev1);
+        if (r.stream) cudaStreamDestroy(r.stream);
+    }
+    s->reps.clear();
+    if (s->local.base) { cudaFree(s->local.base); s->local = SharedFb(); }
+}
+
+// pack FlatScene into one host blob; offsets -> DScene (device pointers filled per replica)
+struct Packed { std::vector<uint8_t> bytes; size_t o_nodes, o_prims, o_xf, o_media, o_mats, o_texs, o_perlin, o_image; };
+void pack(const rtw::FlatScene& f, Packed& p) {
+    size_t off = 0;
+    auto place = [&](size_t n) { size_t o = off; off = align_up(off + std::max<size_t>(n, 16), 256); return o; };
+    p.o_nodes = place(f.nodes.size() * sizeof(DNode));
+    p.o_prims = place(f.prims.size() * sizeof(DPrim));
+    p.o_xf = place(f.xforms.size() * sizeof(DXform));
+    p.o_media = place(f.media.size() * sizeof(DMedium));
+    p.o_mats = place(f.mats.size() * sizeof(DMat));
+    p.o_texs = place(f.texs.size() * sizeof(DTex));
+    p.o_perlin = place(f.perlin.size());
+    p.o_image = place(f.image.size());
+    p.bytes.assign(off, 0);
+    auto cp = [&](size_t o, const void* src, size_t n) { if (n) std::memcpy(p.bytes.data() + o, src, n); };
+    cp(p.o_nodes, f.nodes.data(), f.nodes.size() * sizeof(DNode));
+    cp(p.o_prims, f.prims.data(), f.prims.size() * sizeof(DPrim));
+    cp(p.o_xf, f.xforms.data(), f.xforms.size() * sizeof(DXform));
+    cp(p.o_media, f.media.data(), f.media.size() * sizeof(DMedium));
+    cp(p.o_mats, f.mats.data(), f.mats.size() * sizeof(DMat));
+    cp(p.o_texs, f.texs.data(), f.texs.size() * sizeof(DTex));
+    cp(p.o_perlin, f.perlin.data(), f.perlin.size());
+    cp(p.o_image, f.image.data(), f.image.size());
+}
+DScene bind(const rtw::FlatScene& f, const Packed& p, uint8_t* base) {
+    DScene d;
+    d.nodes = reinterpret_cast<const DNode*>(base + p.o_nodes);
+    d.prims = reinterpret_cast<const DPrim*>(base + p.o_prims);
+    d.xforms = reinterpret_cast<const DXform*>(base + p.o_xf);
+    d.media = reinterpret_cast<const DMedium*>(base + p.o_media);
+    d.mats = reinterpret_cast<const DMat*>(base + p.o_mats);
+    d.texs = reinterpret_cast<const DTex*>(base + p.o_texs);
+    d.perlin = base + p.o_perlin;
+    d.image = base + p.o_image;
+    d.n_nodes = (int)f.nodes.size(); d.n_prims = (int)f.prims.size(); d.n_bvh_prims = f.n_bvh_prims;
+    d.n_xforms = (int)f.xforms.size(); d.n_media = (int)f.media.size(); d.n_mats = (int)f.mats.size();
+    d.n_texs = (int)f.texs.size(); d.n_perlin = (int)(f.perlin.size() / RTW_PERLIN_BYTES);
+    return d;
+}
+
+DCamera to_dcamera(const rtw_camera& c) {
+    DCamera d; std::memset(&d, 0, sizeof(d));
+    d.ox = (float)c.origin[0]; d.oy = (float)c.origin[1]; d.oz = (float)c.origin[2]; d.lens_radius = (float)c.lens_radius;
+    d.lx = (float)(c.lower_left_corner[0] - c.origin[0]); d.ly = (float)(c.lower_left_corner[1] - c.origin[1]);
+    d.lz = (float)(c.lower_left_corner[2] - c.origin[2]);
+    d.hx = (float)c.horizontal[0]; d.hy = (float)c.horizontal[1]; d.hz = (float)c.horizontal[2];
+    d.vx = (float)c.vertical[0]; d.vy = (float)c.vertical[1]; d.vz = (float)c.vertical[2];
+    d.ux = (float)c.u[0]; d.uy = (float)c.u[1]; d.uz = (float)c.u[2];
+    d.wx = (float)c.v[0]; d.wy = (float)c.v[1]; d.wz = (float)c.v[2];
+    d.time0 = (float)c.time0; d.time1 = (float)c.time1;
+    return d;
+}
+
+int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
+    if (p.width < 2 || p.height < 2 || p.spp < 1 || p.max_depth < 0) return fail(RTW_ERR_INVALID_ARG, "bad render params");
+    std::memset(&d, 0, sizeof(d));
+    d.width = p.width; d.height = p.height; d.spp = p.spp; d.max_depth = p.max_depth;
+    d.bg_r = (float)p.background[0]; d.bg_g = (float)p.background[1]; d.bg_b = (float)p.background[2];
+    d.t_min = (float)p.t_min;
+    d.seed_lo = (uint32_t)p.seed; d.seed_hi = (uint32_t)(p.seed >> 32);
+    d.tiles_x = (p.width + 7) / 8; d.tiles_y = (p.height + 3) / 4;
+    long long tiles = (long long)d.tiles_x * d.tiles_y;
+    int chunk = p.samples_per_unit;
+    if (chunk <= 0) {
+        // aim for >= 16 units per resident warp, never below 32 samples per unit (in-unit regeneration tail)
+        long long want_units = 16LL * total_warps;
+        long long chunks = (want_units + tiles - 1) / tiles;
+        if (chunks < 1) chunks = 1;
+        chunk = (int)((p.spp + chunks - 1) / chunks);
+        if (chunk < 32) chunk = 32;
+    }
+    if (chunk > p.spp) chunk = p.spp;
+    d.chunk_spp = chunk;
+    d.chunks = (p.spp + chunk - 1) / chunk;
+    long long n_units = tiles * d.chunks;
+    if (n_units >= 0xffffffffLL) return fail(RTW_ERR_INVALID_ARG, "too many work units");
+    d.n_units = (uint32_t)n_units;
+    d.accumulate = 1;
+    return 0;
+}
+
+int ensure_fb(SharedFb& fb, int device, int w, int h) {
+    size_t need = 256 + (size_t)w * h * 3 * sizeof(float);
+    if (fb.base && fb.bytes >= need) { fb.width = w; fb.height = h; return 0; }
+    CUDA_TRY(cudaSetDevice(device));
+    if (fb.base) { cudaFree(fb.base); fb.base = nullptr; }
+    CUDA_TRY(cudaMalloc(&fb.base, need));
+    fb.bytes = need; fb.width = w; fb.height = h; fb.owner = true;
+    return 0;
+}
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// Launch the megakernel on replicas [0, n) against (counter, fb); sync; fill stats.
+int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp, unsigned int* counter, float* fb, rtw_stats* st) {
+    DCamera dc = to_dcamera(*cam);
+    for (int i = 0; i < n_rep; ++i) {
+        Replica& r = s->reps[i];
+        CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaMemsetAsync(r.stats, 0, 16, r.stream));
+        CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
+        render_kernel<<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
+    }
+    double ms_max = 0; uint64_t rays = 0;
+    for (int i = 0; i < n_rep; ++i) {
+        Replica& r = s->reps[i];
+        CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaStreamSynchronize(r.stream));
+        float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
+        if (ms > ms_max) ms_max = ms;
+        unsigned long long h[2];
+        CUDA_TRY(cudaMemcpy(h, r.stats, 16, cudaMemcpyDeviceToHost));
+        rays += h[0];
+        if (st && i < 8) st->units_per_device[i] = h[1];
+    }
+    if (st) { st->ms_render = ms_max; st->rays = rays; st->kernel_launches += n_rep; st->n_devices = n_rep; }
+    return 0;
+}
+
+void fill_scene_stats(rtw_scene* s, rtw_stats* st) {
+    st->n_prims = (int)s->flat.prims.size(); st->n_nodes = (int)s->flat.nodes.size();
+    st->n_materials = (int)s->flat.mats.size(); st->n_media = (int)s->flat.media.size();
+    st->ms_commit = s->ms_commit;
+}
+
+// scratch device buffers for the parity hooks
+struct Scratch {
+    std::vector<void*> ptrs;
+    ~Scratch() { for (void* p : ptrs) cudaFree(p); }
+    template <class T> int up(const T* host, size_t n, T*& dev) {
+        dev = nullptr;
+        cudaError_t e = cudaMalloc(&dev, std::max<size_t>(n, 1) * sizeof(T));
+        if (e != cudaSuccess) return fail(RTW_ERR_OOM, cudaGetErrorString(e));
+        ptrs.push_back(dev);
+        if (host && n) { e = cudaMemcpy(dev, host, n * sizeof(T), cudaMemcpyHostToDevice); if (e != cudaSuccess) return fail(RTW_ERR_CUDA, cudaGetErrorString(e)); }
+        return 0;
+    }
+    template <class T> int down(T* host, const T* dev, size_t n) {
+        cudaError_t e = cudaMemcpy(host, dev, n * sizeof(T), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return fail(RTW_ERR_CUDA, cudaGetErrorString(e));
+        return 0;
+    }
+};
+#define TRY(x) do { int rc_ = (x); if (rc_ < 0) return rc_; } while (0)
+
+int need_device() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) { cudaGetLastError(); return fail(RTW_ERR_NO_DEVICE, "no CUDA device (librtw has no CPU fallback)"); }
+    return 0;
+}
+
+bool tex_ok(rtw_scene* s, int t) { return s && t >= 0 && t < (int)s->g.textures.size(); }
+bool mat_ok(rtw_scene* s, int m) { return s && m >= 1 && m <= (int)s->g.materials.size(); }
+bool node_ok(rtw_scene* s, int id) { return s && id >= 0 && id < (int)s->g.nodes.size(); }
+int push_node(rtw_scene* s, const rtw::HNode& h) { s->g.nodes.push_back(h); s->committed = false; return (int)s->g.nodes.size() - 1; }
+int push_mat(rtw_scene* s, const rtw::HMaterial& m) { s->g.materials.push_back(m); s->committed = false; return (int)s->g.materials.size(); }
+rtw::V3d v3(const double a[3]) { rtw::V3d v; v.x = a[0]; v.y = a[1]; v.z = a[2]; return v; }
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* rtw_last_error(void) { return g_err.c_str(); }
+const char* rtw_version(void) { return "rtw-b200 0.1 (sm_100a)"; }
+int rtw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+rtw_scene* rtw_scene_new(void) { return new (std::nothrow) rtw_scene(); }
+void rtw_scene_free(rtw_scene* s) {
+    if (!s) return;
+    if (s->shared.base) rtw_shared_close(s);
+    free_replicas(s);
+    delete s;
+}
+
+int rtw_tex_solid(rtw_scene* s, const double rgb[3]) {
+    if (!s || !rgb) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    rtw::HTexture t; t.kind = TEX_SOLID; std::memcpy(t.c0, rgb, 24); s->g.textures.push_back(t); return (int)s->g.textures.size() - 1;
+}
+int rtw_tex_checker(rtw_scene* s, const double even[3], const double odd[3]) {
+    if (!s || !even || !odd) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    rtw::HTexture t; t.kind = TEX_CHECKER; std::memcpy(t.c0, even, 24); std::memcpy(t.c1, odd, 24);
+    s->g.textures.push_back(t); return (int)s->g.textures.size() - 1;
+}
+int rtw_tex_noise(rtw_scene* s, const double* ranvec, const int32_t* px, const int32_t* py, const int32_t* pz, double scale) {
+    if (!s || !ranvec || !px || !py || !pz) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    rtw::HTexture t; t.kind = TEX_NOISE; t.scale = scale;
+    t.ranvec.assign(ranvec, ranvec + 768);
+    t.perm.assign(px, px + 256); t.perm.insert(t.perm.end(), py, py + 256); t.perm.insert(t.perm.end(), pz, pz + 256);
+    for (int v : t.perm) if (v < 0 || v > 255) return fail(RTW_ERR_INVALID_ARG, "perlin permutation entry outside 0..255");
+    s->g.textures.push_back(std::move(t)); return (int)s->g.textures.size() - 1;
+}
+int rtw_tex_image(rtw_scene* s, int32_t w, int32_t h, int32_t bps, const uint8_t* data) {
+    if (!s || !data || w <= 0 || h <= 0 || bps < 3 * w) return fail(RTW_ERR_INVALID_ARG, "bad image texture");
+    rtw::HTexture t; t.kind = TEX_IMAGE; t.w = w; t.h = h; t.bps = bps; t.data.assign(data, data + (size_t)bps * h);
+    s->g.textures.push_back(std::move(t)); return (int)s->g.textures.size() - 1;
+}
+
+int rtw_mat_lambertian(rtw_scene* s, int tex) {
+    if (!tex_ok(s, tex)) return fail(RTW_ERR_INVALID_ARG, "bad texture id");
+    rtw::HMaterial m; m.kind = MAT_LAMBERTIAN; m.tex = tex; return push_mat(s, m);
+}
+int rtw_mat_metal(rtw_scene* s, const double albedo[3], double fuzz) {
+    if (!s || !albedo) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    rtw::HMaterial m; m.kind = MAT_METAL; std::memcpy(m.albedo, albedo, 24); m.fuzz = fuzz; return push_mat(s, m);
+}
+int rtw_mat_dielectric(rtw_scene* s, double ir) {
+    if (!s) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    rtw::HMaterial m; m.kind = MAT_DIELECTRIC; m.ir = ir; return push_mat(s, m);
+}
+int rtw_mat_diffuse_light(rtw_scene* s, int tex) {
+    if (!tex_ok(s, tex)) return fail(RTW_ERR_INVALID_ARG, "bad texture id");
+    rtw::HMaterial m; m.kind = MAT_DIFFUSE_LIGHT; m.tex = tex; return push_mat(s, m);
+}
+int rtw_mat_isotropic(rtw_scene* s, int tex) {
+    if (!tex_ok(s, tex)) return fail(RTW_ERR_INVALID_ARG, "bad texture id");
+    rtw::HMaterial m; m.kind = MAT_ISOTROPIC; m.tex = tex; return push_mat(s, m);
+}
+
+int rtw_sphere(rtw_scene* s, int mat, const double c[3], double r) {
+    if (!mat_ok(s, mat) || !c) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    rtw::HNode h; h.kind = rtw::H_SPHERE; h.mat = mat; h.c0 = v3(c); h.radius = r; return push_node(s, h);
+}
+int rtw_moving_sphere(rtw_scene* s, int mat, const double c0[3], const double c1[3], double t0, double t1, double r) {
+    if (!mat_ok(s, mat) || !c0 || !c1) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    rtw::HNode h; h.kind = rtw::H_MOVING_SPHERE; h.mat = mat; h.c0 = v3(c0); h.c1 = v3(c1); h.time0 = t0; h.time1 = t1; h.radius = r;
+    return push_node(s, h);
+}
+static int push_rect(rtw_scene* s, int kind, int mat, double a0, double a1, double b0, double b1, double k) {
+    if (!mat_ok(s, mat)) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    rtw::HNode h; h.kind = kind; h.mat = mat; h.a0 = a0; h.a1 = a1; h.b0 = b0; h.b1 = b1; h.k = k; return push_node(s, h);
+}
+int rtw_xy_rect(rtw_scene* s, int mat, double x0, double x1, double y0, double y1, double k) { return push_rect(s, rtw::H_XY, mat, x0, x1, y0, y1, k); }
+int rtw_xz_rect(rtw_scene* s, int mat, double x0, double x1, double z0, double z1, double k) { return push_rect(s, rtw::H_XZ, mat, x0, x1, z0, z1, k); }
+int rtw_yz_rect(rtw_scene* s, int mat, double y0, double y1, double z0, double z1, double k) { return push_rect(s, rtw::H_YZ, mat, y0, y1, z0, z1, k); }
+int rtw_box(rtw_scene* s, const double mn[3], const double mx[3], int mat) {           // new_box src/hittable.rs:132-145
+    if (!mat_ok(s, mat) || !mn || !mx) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    rtw::HNode h; h.kind = rtw::H_BOX; h.mat = mat; h.bmin = v3(mn); h.bmax = v3(mx);
+    h.children.push_back(rtw_xy_rect(s, mat, mn[0], mx[0], mn[1], mx[1], mx[2]));
+    h.children.push_back(rtw_xy_rect(s, mat, mn[0], mx[0], mn[1], mx[1], mn[2]));
+    h.children.push_back(rtw_xz_rect(s, mat, mn[0], mx[0], mn[2], mx[2], mx[1]));
+    h.children.push_back(rtw_xz_rect(s, mat, mn[0], mx[0], mn[2], mx[2], mn[1]));
+    h.children.push_back(rtw_yz_rect(s, mat, mn[1], mx[1], mn[2], mx[2], mx[0]));
+    h.children.push_back(rtw_yz_rect(s, mat, mn[1], mx[1], mn[2], mx[2], mn[0]));
+    return push_node(s, h);
+}
+int rtw_translate(rtw_scene* s, int child, const double offset[3]) {
+    if (!node_ok(s, child) || !offset) return fail(RTW_ERR_INVALID_ARG, "bad child id");
+    rtw::HNode h; h.kind = rtw::H_TRANSLATE; h.child = child; h.offset = v3(offset); return push_node(s, h);
+}
+int rtw_rotate_y(rtw_scene* s, double angle_deg, int child) {                           // new_rotate_y src/hittable.rs:147-152
+    if (!node_ok(s, child)) return fail(RTW_ERR_INVALID_ARG, "bad child id");
+    rtw::HNode h; h.kind = rtw::H_ROTATE_Y; h.child = child; h.angle_deg = angle_deg;
+    double radians = angle_deg * 3.1415926535897932385 / 180.0;
+    h.sin_theta = std::sin(radians); h.cos_theta = std::cos(radians);
+    return push_node(s, h);
+}
+int rtw_constant_medium(rtw_scene* s, int child, double density, int phase_mat) {      // src/hittable.rs:201-207
+    if (!node_ok(s, child)) return fail(RTW_ERR_INVALID_ARG, "bad child id");
+    if (!mat_ok(s, phase_mat)) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    rtw::HNode h; h.kind = rtw::H_MEDIUM; h.child = child; h.mat = phase_mat; h.density = density; return push_node(s, h);
+}
+int rtw_bvh_node(rtw_scene* s, const int32_t* children, int32_t n, double t0, double t1) {
+    if (!s || !children || n <= 0) return fail(RTW_ERR_INVALID_ARG, "empty BvhNode");
+    rtw::HNode h; h.kind = rtw::H_BVH_NODE; h.time0 = t0; h.time1 = t1;
+    for (int i = 0; i < n; ++i) { if (!node_ok(s, children[i])) return fail(RTW_ERR_INVALID_ARG, "bad child id"); h.children.push_back(children[i]); }
+    return push_node(s, h);
+}
+int rtw_world_push(rtw_scene* s, int id) {
+    if (!node_ok(s, id)) return fail(RTW_ERR_INVALID_ARG, "bad hittable id");
+    s->g.world.push_back(id); s->committed = false; return RTW_OK;
+}
+
+int rtw_camera_new(const double look_from[3], const double look_at[3], const double vup[3], double vfov, double aspect,
+                   double aperture, double focus_dist, double time0, double time1, rtw_camera* out) {   // src/camera.rs:18-56
+    if (!look_from || !look_at || !vup || !out) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    auto sub = [](const double* a, const double* b, double* r) { for (int i = 0; i < 3; ++i) r[i] = a[i] - b[i]; };
+    auto norm = [](double* v) { double inv = 1.0 / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); for (int i = 0; i < 3; ++i) v[i] = inv * v[i]; };
+    auto cross = [](const double* u, const double* v, double* r) { r[0] = u[1] * v[2] - u[2] * v[1]; r[1] = u[2] * v[0] - u[0] * v[2]; r[2] = u[0] * v[1] - u[1] * v[0]; };
+    double theta = vfov * 3.1415926535897932385 / 180.0;
+    double h = std::tan(theta / 2.0);
+    double viewport_height = 2.0 * h, viewport_width = aspect * viewport_height;
+    double w[3], u[3], v[3];
+    sub(look_from, look_at, w); norm(w);
+    cross(vup, w, u); norm(u);
+    cross(w, u, v);
+    for (int i = 0; i < 3; ++i) {
+        out->origin[i] = look_from[i];
+        out->horizontal[i] = focus_dist * viewport_width * u[i];
+        out->vertical[i] = focus_dist * viewport_height * v[i];
+        out->lower_left_corner[i] = out->origin[i] - out->horizontal[i] * 0.5 - out->vertical[i] * 0.5 - focus_dist * w[i];
+        out->u[i] = u[i]; out->v[i] = v[i]; out->w[i] = w[i];
+    }
+    out->lens_radius = aperture * 0.5; out->time0 = time0; out->time1 = time1;
+    return RTW_OK;
+}
+
+int rtw_scene_commit(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
+    if (!s) return fail(RTW_ERR_INVALID_ARG, "null scene");
+    TRY(need_device());
+    int ndev = rtw_device_count();
+    if (n_gpus <= 0) n_gpus = ndev - first_device;
+    if (first_device < 0 || n_gpus < 1 || first_device + n_gpus > ndev || n_gpus > 8) return fail(RTW_ERR_INVALID_ARG, "device range not available");
+    double t0 = now_ms();
+    std::string err;
+    int rc = rtw::flatten(s->g, s->g.world, s->flat, err);
+    if (rc) return fail(rc, err);
+    Packed pk; pack(s->flat, pk);
+    free_replicas(s);
+    s->reps.resize(n_gpus);
+    s->h2d_commit = 0;
+    for (int i = 0; i < n_gpus; ++i) {
+        Replica& r = s->reps[i];
+        r.device = first_device + i;
+        CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&r.ev0)); CUDA_TRY(cudaEventCreate(&r.ev1));
+        CUDA_TRY(cudaMalloc(&r.blob, pk.bytes.size())); r.blob_bytes = pk.bytes.size();
+        CUDA_TRY(cudaMalloc(&r.stats, 16));
+        CUDA_TRY(cudaMemcpyAsync(r.blob, pk.bytes.data(), pk.bytes.size(), cudaMemcpyHostToDevice, r.stream));
+        s->h2d_commit += pk.bytes.size();
+        r.ds = bind(s->flat, pk, r.blob);
+        cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, r.device));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, RTW_BLOCK, 0));
+        if (per_sm < 1) per_sm = 1;
+        r.grid = prop.multiProcessorCount * per_sm;
+        if (i > 0) {   // peers write the framebuffer / counter that live on the first device
+            int can = 0; CUDA_TRY(cudaDeviceCanAccessPeer(&can, r.device, first_device));
+            if (!can) return fail(RTW_ERR_CUDA, "peer access to the first device is not available");
+            cudaError_t e = cudaDeviceEnablePeerAccess(first_device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RTW_ERR_CUDA, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    for (Replica& r : s->reps) { CUDA_TRY(cudaSetDevice(r.device)); CUDA_TRY(cudaStreamSynchronize(r.stream)); }
+    s->committed = true;
+    s->ms_commit = now_ms() - t0;
+    return RTW_OK;
+}
+
+int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, float* out, rtw_stats* st) {
+    if (!s || !cam || !p || !out) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "rtw_scene_commit has not been called since the last edit");
+    double t0 = now_ms();
+    int n_rep = p->n_gpus > 0 ? p->n_gpus : (int)s->reps.size();
+    if (n_rep > (int)s->reps.size()) return fail(RTW_ERR_INVALID_ARG, "n_gpus exceeds the committed replicas");
+    int total_warps = 0;
+    for (int i = 0; i < n_rep; ++i) total_warps += s->reps[i].grid * RTW_WARPS;
+    DParams dp; TRY(make_params(*p, total_warps, dp));
+    if (st) { std::memset(st, 0, sizeof(*st)); fill_scene_stats(s, st); }
+    Replica& r0 = s->reps[0];
+    const bool dev_out = (p->flags & RTW_FLAG_DEVICE_OUT) != 0;
+    const size_t fb_bytes = (size_t)p->width * p->height * 3 * sizeof(float);
+    TRY(ensure_fb(s->local, r0.device, dev_out ? 1 : p->width, dev_out ? 1 : p->height));
+    float* fb = dev_out ? out : s->local.fb();
+    CUDA_TRY(cudaSetDevice(r0.device));
+    dp.accumulate = (n_rep > 1 || dp.chunks > 1) ? 1 : 0;
+    CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
+    if (dp.accumulate) CUDA_TRY(cudaMemsetAsync(fb, 0, fb_bytes, r0.stream));
+    if (n_rep > 1) CUDA_TRY(cudaStreamSynchronize(r0.stream));   // peers must see the zeroed buffers
+    TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, st));
+    if (!dev_out) {
+        CUDA_TRY(cudaSetDevice(r0.device));
+        CUDA_TRY(cudaMemcpy(out, fb, fb_bytes, cudaMemcpyDeviceToHost));
+        if (st) st->d2h_bytes = fb_bytes;
+    }
+    if (st) { st->paths = (uint64_t)p->width * p->height * p->spp; st->ms_total = now_ms() - t0; st->h2d_bytes = sizeof(DCamera) + sizeof(DParams) + sizeof(DScene); }
+    return RTW_OK;
+}
+
+int rtw_write_color(const float* rgb_sum, int32_t n_pixels, int32_t spp, uint8_t* out_rgb8) {
+    if (!rgb_sum || !out_rgb8 || n_pixels <= 0 || spp <= 0) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    TRY(need_device());
+    Scratch sc; float* d_in; uint8_t* d_out; size_t n = (size_t)n_pixels * 3;
+    TRY(sc.up(rgb_sum, n, d_in)); TRY(sc.up((const uint8_t*)nullptr, n, d_out));
+    write_color_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_in, (int)n, 1.0f / (float)spp, d_out);
+    CUDA_TRY(cudaGetLastError());
+    TRY(sc.down(out_rgb8, d_out, n));
+    return RTW_OK;
+}
+
+// ---- cross-process sharing (one rank per GPU): CUDA IPC ----------------------------------------
+struct IpcBlob { cudaIpcMemHandle_t h; uint64_t bytes; int32_t width, height; uint32_t magic; };
+static_assert(sizeof(IpcBlob) <= RTW_IPC_HANDLE_BYTES, "IPC blob too large");
+
+int rtw_shared_create(rtw_scene* s, int32_t w, int32_t h, uint8_t handle[RTW_IPC_HANDLE_BYTES]) {
+    if (!s || !handle || w < 2 || h < 2) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "commit first");
+    if (s->shared.base) rtw_shared_close(s);
+    CUDA_TRY(cudaSetDevice(s->reps[0].device));
+    size_t need = 256 + (size_t)w * h * 3 * sizeof(float);
+    CUDA_TRY(cudaMalloc(&s->shared.base, need));
+    s->shared.bytes = need; s->shared.width = w; s->shared.height = h; s->shared.owner = true;
+    CUDA_TRY(cudaMemset(s->shared.base, 0, need));
+    IpcBlob b; std::memset(&b, 0, sizeof(b));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.h, s->shared.base));
+    b.bytes = need; b.width = w; b.height = h; b.magic = 0x52545721u;
+    std::memset(handle, 0, RTW_IPC_HANDLE_BYTES); std::memcpy(handle, &b, sizeof(b));
+    return RTW_OK;
+}
+int rtw_shared_open(rtw_scene* s, int32_t w, int32_t h, const uint8_t handle[RTW_IPC_HANDLE_BYTES]) {
+    if (!s || !handle) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "commit first");
+    IpcBlob b; std::memcpy(&b, handle, sizeof(b));
+    if (b.magic != 0x52545721u || b.width != w || b.height != h) return fail(RTW_ERR_INVALID_ARG, "IPC handle does not match");
+    if (s->shared.base) rtw_shared_close(s);
+    CUDA_TRY(cudaSetDevice(s->reps[0].device));
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, b.h, cudaIpcMemLazyEnablePeerAccess));
+    s->shared.base = (uint8_t*)p; s->shared.bytes = b.bytes; s->shared.width = w; s->shared.height = h;
+    s->shared.owner = false; s->shared.ipc_mapped = true;
+    return RTW_OK;
+}
+int rtw_shared_reset(rtw_scene* s) {
+    if (!s || !s->shared.base || !s->shared.owner) return fail(RTW_ERR_INVALID_ARG, "not the owner of a shared framebuffer");
+    CUDA_TRY(cudaSetDevice(s->reps[0].device));
+    CUDA_TRY(cudaMemset(s->shared.base, 0, s->shared.bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return RTW_OK;
+}
+int rtw_render_shared(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, rtw_stats* st) {
+    if (!s || !cam || !p || !s->shared.base) return fail(RTW_ERR_INVALID_ARG, "no shared framebuffer");
+    if (p->width != s->shared.width || p->height != s->shared.height) return fail(RTW_ERR_INVALID_ARG, "size mismatch");
+    double t0 = now_ms();
+    int world = p->n_gpus > 0 ? p->n_gpus : 1;    // ranks taking part (sizes the work units)
+    DParams dp; TRY(make_params(*p, world * s->reps[0].grid * RTW_WARPS, dp));
+    dp.accumulate = 1;
+    if (st) { std::memset(st, 0, sizeof(*st)); fill_scene_stats(s, st); }
+    TRY(launch_all(s, 1, cam, dp, s->shared.counter(), s->shared.fb(), st));
+    if (st) { st->paths = (uint64_t)p->width * p->height * p->spp; st->ms_total = now_ms() - t0; }
+    return RTW_OK;
+}
+int rtw_shared_read(rtw_scene* s, float* out) {
+    if (!s || !out || !s->shared.base) return fail(RTW_ERR_INVALID_ARG, "no shared framebuffer");
+    CUDA_TRY(cudaSetDevice(s->reps[0].device));
+    CUDA_TRY(cudaMemcpy(out, s->shared.fb(), (size_t)s->shared.width * s->shared.height * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RTW_OK;
+}
+int rtw_shared_close(rtw_scene* s) {
+    if (!s || !s->shared.base) return RTW_OK;
+    if (!s->reps.empty()) cudaSetDevice(s->reps[0].device);
+    if (s->shared.ipc_mapped) cudaIpcCloseMemHandle(s->shared.base); else cudaFree(s->shared.base);
+    s->shared = SharedFb();
+    return RTW_OK;
+}
+
+// ---- parity hooks ---------------------------------------------------------------------------------
+int rtw_test_philox(int32_t n, const uint32_t* counter, const uint32_t* key, uint32_t* out) {
+    if (n <= 0 || !counter || !key || !out) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    TRY(need_device());
+    Scratch sc; uint32_t *dc, *dk, *dout;
+    TRY(sc.up(counter, 4 * (size_t)n, dc)); TRY(sc.up(key, 2 * (size_t)n, dk)); TRY(sc.up((uint32_t*)nullptr, 4 * (size_t)n, dout));
+    philox_kernel<<<(n + 127) / 128, 128>>>(n, dc, dk, dout);
+    CUDA_TRY(cudaGetLastError());
+    return sc.down(out, dout, 4 * (size_t)n);
+}
+
+int rtw_test_get_ray(const rtw_camera* cam, int32_t n, const double* s, const double* t, const double* xi, int32_t stride,
+                     double* oo, double* od, double* ot, int32_t* nd) {
+    if (!cam || n <= 0 || !s || !t || !xi || stride <= 0) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    TRY(need_device());
+    Scratch sc; double *ds, *dt, *dxi, *doo, *dod, *dot_; int* dnd;
+    TRY(sc.up(s, n, ds)); TRY(sc.up(t, n, dt)); TRY(sc.up(xi, (size_t)n * stride, dxi));
+    TRY(sc.up((double*)nullptr, 3 * (size_t)n, doo)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, dod));
+    TRY(sc.up((double*)nullptr, n, dot_)); TRY(sc.up((int*)nullptr, n, dnd));
+    get_ray_kernel<<<(n + 127) / 128, 128>>>(to_dcamera(*cam), n, ds, dt, dxi, stride, doo, dod, dot_, dnd);
+    CUDA_TRY(cudaGetLastError());
+    TRY(sc.down(oo, doo, 3 * (size_t)n)); TRY(sc.down(od, dod, 3 * (size_t)n)); TRY(sc.down(ot, dot_, n)); TRY(sc.down(nd, dnd, n));
+    return RTW_OK;
+}
+
+// scene view for the hooks: the committed world, or one hittable flattened on the fly
+struct View {
+    uint8_t* blob = nullptr; DScene ds{}; bool owned = false;
+    ~View() { if (owned && blob) cudaFree(blob); }
+};
+static int make_view(rtw_scene* s, int target, View& v) {
+    if (target < 0) {
+        if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "commit first");
+        CUDA_TRY(cudaSetDevice(s->reps[0].device));
+        v.ds = s->reps[0].ds; return 0;
+    }
+    if (!node_ok(s, target)) return fail(RTW_ERR_INVALID_ARG, "bad target");
+    rtw::FlatScene f; std::string err;
+    int rc = rtw::flatten(s->g, std::vector<int>{target}, f, err);
+    if (rc) return fail(rc, err);
+    Packed pk; pack(f, pk);
+    CUDA_TRY(cudaMalloc(&v.blob, pk.bytes.size())); v.owned = true;
+    CUDA_TRY(cudaMemcpy(v.blob, pk.bytes.data(), pk.bytes.size(), cudaMemcpyHostToDevice));
+    v.ds = bind(f, pk, v.blob);
+    return 0;
+}
+
+int rtw_test_hit(rtw_scene* s, int32_t target, int32_t n, const double* o, const double* d, const double* tm, double t_min,
+                 double t_max, const double* xi, int32_t stride, int32_t* hit, double* ot, double* op, double* on,
+                 int32_t* front, double* ou, double* ov, int32_t* mat, int32_t* nd) {
+    if (!s || n <= 0 || !o || !d || !tm || !xi || stride <= 0) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    TRY(need_device());
+    View v; TRY(make_view(s, target, v));
+    Scratch sc; double *d_o, *d_d, *d_tm, *d_xi, *d_t, *d_p, *d_n, *d_u, *d_v; int *d_hit, *d_front, *d_mat, *d_nd;
+    TRY(sc.up(o, 3 * (size_t)n, d_o)); TRY(sc.up(d, 3 * (size_t)n, d_d)); TRY(sc.up(tm, n, d_tm)); TRY(sc.up(xi, (size_t)n * stride, d_xi));
+    TRY(sc.up((double*)nullptr, n, d_t)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_p)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_n));
+    TRY(sc.up((double*)nullptr, n, d_u)); TRY(sc.up((double*)nullptr, n, d_v));
+    TRY(sc.up((int*)nullptr, n, d_hit)); TRY(sc.up((int*)nullptr, n, d_front)); TRY(sc.up((int*)nullptr, n, d_mat)); TRY(sc.up((int*)nullptr, n, d_nd));
+    hit_kernel<<<(n + 127) / 128, 128>>>(v.ds, n, d_o, d_d, d_tm, (float)t_min, (float)t_max, d_xi, stride, d_hit, d_t, d_p, d_n, d_front, d_u, d_v, d_mat, d_nd);
+    CUDA_TRY(cudaGetLastError());
+    TRY(sc.down(hit, d_hit, n)); TRY(sc.down(ot, d_t, n)); TRY(sc.down(op, d_p, 3 * (size_t)n)); TRY(sc.down(on, d_n, 3 * (size_t)n));
+    TRY(sc.down(front, d_front, n)); TRY(sc.down(ou, d_u, n)); TRY(sc.down(ov, d_v, n)); TRY(sc.down(mat, d_mat, n)); TRY(sc.down(nd, d_nd, n));
+    return RTW_OK;
+}
+
+int rtw_test_aabb(int32_t n, const double* bmin, const double* bmax, const double* o, const double* d, double t_min, double t_max, int32_t* hit) {
+    if (n <= 0 || !bmin || !bmax || !o || !d || !hit) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    TRY(need_device());
+    Scratch sc; double *d_mn, *d_mx, *d_o, *d_d; int* d_hit;
+    TRY(sc.up(bmin, 3 * (size_t)n, d_mn)); TRY(sc.up(bmax, 3 * (size_t)n, d_mx)); TRY(sc.up(o, 3 * (size_t)n, d_o)); TRY(sc.up(d, 3 * (size_t)n, d_d));
+    TRY(sc.up((int*)nullptr, n, d_hit));
+    aabb_kernel<<<(n + 127) / 128, 128>>>(n, d_mn, d_mx, d_o, d_d, (float)t_min, (float)t_max, d_hit);
+    CUDA_TRY(cudaGetLastError());
+    return sc.down(hit, d_hit, n);
+}
+
+int rtw_test_scatter(rtw_scene* s, int32_t mat, int32_t n, const double* ro, const double* rd, const double* rt, const double* p,
+                     const double* nrm, const int32_t* front, const double* u, const double* v, const double* xi, int32_t stride,
+                     int32_t* osc, double* oo, double* od, double* ot, double* oatt, double* oem, int32_t* nd) {
+    if (!s || n <= 0 || !ro || !rd || !rt || !p || !nrm || !front || !u || !v || !xi || stride <= 0) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    if (!mat_ok(s, mat)) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    TRY(need_device());
+    View vw; TRY(make_view(s, -1, vw));
+    Scratch sc; double *d_ro, *d_rd, *d_rt, *d_p, *d_n, *d_u, *d_v, *d_xi, *d_oo, *d_od, *d_ot, *d_att, *d_em; int *d_front, *d_sc, *d_nd;
+    TRY(sc.up(ro, 3 * (size_t)n, d_ro)); TRY(sc.up(rd, 3 * (size_t)n, d_rd)); TRY(sc.up(rt, n, d_rt)); TRY(sc.up(p, 3 * (size_t)n, d_p));
+    TRY(sc.up(nrm, 3 * (size_t)n, d_n)); TRY(sc.up(front, n, d_front)); TRY(sc.up(u, n, d_u)); TRY(sc.up(v, n, d_v)); TRY(sc.up(xi, (size_t)n * stride, d_xi));
+    TRY(sc.up((int*)nullptr, n, d_sc)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_oo)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_od));
+    TRY(sc.up((double*)nullptr, n, d_ot)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_att)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_em));
+    TRY(sc.up((int*)nullptr, n, d_nd));
+    scatter_kernel<<<(n + 127) / 128, 128>>>(vw.ds, mat - 1, n, d_ro, d_rd, d_rt, d_p, d_n, d_front, d_u, d_v, d_xi, stride, d_sc, d_oo, d_od, d_ot, d_att, d_em, d_nd);
+    CUDA_TRY(cudaGetLastError());
+    TRY(sc.down(osc, d_sc, n)); TRY(sc.down(oo, d_oo, 3 * (size_t)n)); TRY(sc.down(od, d_od, 3 * (size_t)n)); TRY(sc.down(ot, d_ot, n));
+    TRY(sc.down(oatt, d_att, 3 * (size_t)n)); TRY(sc.down(oem, d_em, 3 * (size_t)n)); TRY(sc.down(nd, d_nd, n));
+    return RTW_OK;
+}
+
+int rtw_test_texture(rtw_scene* s, int32_t tex, int32_t n, const double* u, const double* v, const double* p, double* out) {
+    if (!s || n <= 0 || !u || !v || !p || !out) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    if (!tex_ok(s, tex)) return fail(RTW_ERR_INVALID_ARG, "bad texture id");
+    TRY(need_device());
+    View vw; TRY(make_view(s, -1, vw));
+    Scratch sc; double *d_u, *d_v, *d_p, *d_out;
+    TRY(sc.up(u, n, d_u)); TRY(sc.up(v, n, d_v)); TRY(sc.up(p, 3 * (size_t)n, d_p)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_out));
+    texture_kernel<<<(n + 127) / 128, 128>>>(vw.ds, tex, n, d_u, d_v, d_p, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return sc.down(out, d_out, 3 * (size_t)n);
+}
+
+int rtw_trace_paths(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, int32_t n, const int32_t* px, const int32_t* py,
+                    const int32_t* smp, double* out_rgb, int32_t* out_seg) {
+    if (!s || !cam || !p || n <= 0 || !px || !py || !smp || !out_rgb || !out_seg) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    TRY(need_device());
+    View vw; TRY(make_view(s, -1, vw));
+    DParams dp; TRY(make_params(*p, 1, dp));
+    Scratch sc; int *d_x, *d_y, *d_s, *d_seg; double* d_rgb;
+    TRY(sc.up(px, n, d_x)); TRY(sc.up(py, n, d_y)); TRY(sc.up(smp, n, d_s)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_rgb)); TRY(sc.up((int*)nullptr, n, d_seg));
+    trace_paths_kernel<<<(n + 127) / 128, 128>>>(vw.ds, to_dcamera(*cam), dp, n, d_x, d_y, d_s, d_rgb, d_seg);
+    CUDA_TRY(cudaGetLastError());
+    TRY(sc.down(out_rgb, d_rgb, 3 * (size_t)n)); TRY(sc.down(out_seg, d_seg, n));
+    return RTW_OK;
+}
+
+// host-only introspection used by the CPU tests (no device needed): flatten + structural BVH check
+int rtw_debug_flatten(rtw_scene* s, int32_t* out_counts /* prims, bvh_prims, nodes, xforms, media, mats, texs, depth */, double* out_sah) {
+    if (!s) return fail(RTW_ERR_INVALID_ARG, "null scene");
+    rtw::FlatScene f; std::string err;
+    int rc = rtw::flatten(s->g, s->g.world, f, err);
+    if (rc) return fail(rc, err);
+    if (!rtw::validate_bvh(f, err)) return fail(RTW_ERR_INVALID_ARG, "invalid BVH: " + err);
+    if (out_counts) {
+        out_counts[0] = (int)f.prims.size(); out_counts[1] = f.n_bvh_prims; out_counts[2] = (int)f.nodes.size(); out_counts[3] = (int)f.xforms.size();
+        out_counts[4] = (int)f.media.size(); out_counts[5] = (int)f.mats.size(); out_counts[6] = (int)f.texs.size(); out_counts[7] = f.max_depth;
+    }
+    if (out_sah) *out_sah = f.sah_cost;
+    return RTW_OK;
+}
+
+}  // extern "C"

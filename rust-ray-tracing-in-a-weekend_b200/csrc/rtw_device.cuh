@@ -1,0 +1,560 @@
+// rtw_device.cuh — device functions of the render hot path (sm_100a).
+//
+// One section per reference module; every function cites the reference lines it restates
+// (paths relative to /root/reference).  Arithmetic is f32 except where the reference's f64 is needed for
+// conditioning: the sphere discriminant (sphere_hit) runs in f64 — B200 executes FP64 at half FP32 rate.
+#ifndef RTW_DEVICE_CUH
+#define RTW_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "rtw_types.h"
+
+namespace rtwd {
+
+#define RTW_DEV __device__ __forceinline__
+#define RTW_PI_F 3.14159265358979323846f
+
+// ------------------------------------------------------------------------------------------------
+// src/math.rs — Vector3 (:12-20) and its operators (:147-266) in f32
+// ------------------------------------------------------------------------------------------------
+struct V3 { float x, y, z; };
+RTW_DEV V3 mk(float x, float y, float z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+RTW_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+RTW_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+RTW_DEV V3 operator-(V3 a) { return mk(-a.x, -a.y, -a.z); }
+RTW_DEV V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+RTW_DEV V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
+RTW_DEV V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
+RTW_DEV float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }       // :82-84
+RTW_DEV float length_squared(V3 a) { return dot(a, a); }                                    // :86-88
+RTW_DEV V3 normalize(V3 v) { float inv = 1.0f / sqrtf(length_squared(v)); return inv * v; } // :102-104 ((1/len)*v, :260-266)
+RTW_DEV V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }                       // :106-108
+RTW_DEV V3 refract(V3 uv, V3 n, float etai_over_etat) {                                      // :110-117
+    float cos_theta = fminf(dot(-uv, n), 1.0f);
+    V3 r_out_perp = etai_over_etat * (uv + cos_theta * n);
+    V3 r_out_parallel = (-sqrtf(fabsf(1.0f - length_squared(r_out_perp)))) * n;
+    return r_out_perp + r_out_parallel;
+}
+RTW_DEV bool near_zero(V3 v) { const float S = 1e-8f; return fabsf(v.x) < S && fabsf(v.y) < S && fabsf(v.z) < S; }  // :134-137
+RTW_DEV void sphere_uv(V3 p, float& u, float& v) {                                           // :288-300
+    float theta = acosf(-p.y);
+    float phi = atan2f(-p.z, p.x) + RTW_PI_F;
+    u = phi * (1.0f / (2.0f * RTW_PI_F));
+    v = theta * (1.0f / RTW_PI_F);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RNG — replaces rand::thread_rng (src/math.rs:268-280).  Philox4x32-10, key = seed,
+// counter = (draw block, bounce, pixel, sample); a draw is (word >> 8) * 2^-24 (identical in the oracle).
+// ------------------------------------------------------------------------------------------------
+RTW_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                           uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+struct PhiloxRng {
+    uint32_t k0, k1, pixel, sample, bounce, draw;
+    uint32_t w0, w1, w2, w3;
+    RTW_DEV void init(uint32_t seed_lo, uint32_t seed_hi, uint32_t px, uint32_t s) {
+        k0 = seed_lo; k1 = seed_hi; pixel = px; sample = s; bounce = 0; draw = 0;
+    }
+    RTW_DEV void set_bounce(uint32_t b) { bounce = b; draw = 0; }
+    RTW_DEV float next() {                               // random_double()
+        uint32_t i = draw & 3u;
+        if (i == 0) philox4x32_10(draw >> 2, bounce, pixel, sample, k0, k1, w0, w1, w2, w3);
+        ++draw;
+        uint32_t w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
+        return (float)(w >> 8) * (1.0f / 16777216.0f);
+    }
+};
+
+// explicit stream (parity hooks): `stride` f64 draws per item, consumed in order
+struct StreamRng {
+    const double* xi; int n; int draw;
+    RTW_DEV void set_bounce(uint32_t) {}
+    RTW_DEV float next() { float v = draw < n ? (float)xi[draw] : 0.5f; ++draw; return v; }
+};
+
+template <class R> RTW_DEV float rng_range(R& g, float a, float b) { return a + (b - a) * g.next(); }   // :273-276
+template <class R> RTW_DEV V3 random_in_unit_sphere(R& g) {                                               // :51-58, draw order x,y,z :43-49
+    for (;;) {
+        float x = rng_range(g, -1.0f, 1.0f), y = rng_range(g, -1.0f, 1.0f), z = rng_range(g, -1.0f, 1.0f);
+        V3 p = mk(x, y, z);
+        if (length_squared(p) < 1.0f) return p;
+    }
+}
+template <class R> RTW_DEV V3 random_unit_vector(R& g) { return normalize(random_in_unit_sphere(g)); }   // :78-80
+
+// ------------------------------------------------------------------------------------------------
+// src/ray.rs (:3-7, :19-21) — directions are never normalised
+// ------------------------------------------------------------------------------------------------
+struct Ray { V3 o, d; float time; };
+RTW_DEV V3 ray_at(const Ray& r, float t) { return mk(fmaf(t, r.d.x, r.o.x), fmaf(t, r.d.y, r.o.y), fmaf(t, r.d.z, r.o.z)); }
+
+// ------------------------------------------------------------------------------------------------
+// src/camera.rs:58-66 — get_ray.  Draw order: disk loop (x, y per iteration, src/math.rs:69-76), then time.
+// ------------------------------------------------------------------------------------------------
+template <class R> RTW_DEV Ray camera_get_ray(const DCamera& c, float s, float t, R& g) {
+    float rx, ry;
+    for (;;) {
+        rx = rng_range(g, -1.0f, 1.0f); ry = rng_range(g, -1.0f, 1.0f);
+        if (rx * rx + ry * ry < 1.0f) break;
+    }
+    rx *= c.lens_radius; ry *= c.lens_radius;
+    V3 offset = mk(c.ux * rx + c.wx * ry, c.uy * rx + c.wy * ry, c.uz * rx + c.wz * ry);
+    Ray r;
+    r.o = mk(c.ox + offset.x, c.oy + offset.y, c.oz + offset.z);
+    r.d = mk(c.lx + s * c.hx + t * c.vx - offset.x, c.ly + s * c.hy + t * c.vy - offset.y, c.lz + s * c.hz + t * c.vz - offset.z);
+    r.time = rng_range(g, c.time0, c.time1);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// src/perlin.rs — noise (:32-68), perlin_interp (:70-94), turb (:96-108).  Smoothstep is applied twice and the
+// weight vector uses the once-smoothed fraction, exactly like the reference.
+// ------------------------------------------------------------------------------------------------
+RTW_DEV float perlin_noise(const uint8_t* __restrict__ tbl, V3 p) {
+    const float4* ranvec = reinterpret_cast<const float4*>(tbl);
+    const uint8_t* perm = tbl + 256 * 16;
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    u = u * u * (3.0f - 2.0f * u); v = v * v * (3.0f - 2.0f * v); w = w * w * (3.0f - 2.0f * w);
+    int i = __float2int_rz(fx), j = __float2int_rz(fy), k = __float2int_rz(fz);   // saturating like Rust `as i32`
+    float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                int h = __ldg(perm + ((i + di) & 255)) ^ __ldg(perm + 256 + ((j + dj) & 255)) ^ __ldg(perm + 512 + ((k + dk) & 255));
+                float4 g = __ldg(ranvec + h);
+                float fi = (float)di, fj = (float)dj, fk = (float)dk;
+                float wt = (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww);
+                accum += wt * (g.x * (u - fi) + g.y * (v - fj) + g.z * (w - fk));
+            }
+    return accum;
+}
+RTW_DEV float perlin_turb(const uint8_t* __restrict__ tbl, V3 p, int depth) {
+    float accum = 0.0f, weight = 1.0f;
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * perlin_noise(tbl, p);
+        weight *= 0.5f;
+        p = p * 2.0f;
+    }
+    return fabsf(accum);
+}
+
+// ------------------------------------------------------------------------------------------------
+// src/texture.rs:30-75 — get_color_value
+// ------------------------------------------------------------------------------------------------
+RTW_DEV V3 texture_value(const DScene& sc, int tex, float u, float v, V3 p) {
+    const float4* tp = reinterpret_cast<const float4*>(sc.texs + tex);
+    float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
+    int kind = __float_as_int(t1.w);
+    if (kind == TEX_SOLID) return mk(t0.x, t0.y, t0.z);
+    if (kind == TEX_CHECKER) {                                                             // :35-42
+        float sines = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
+        return sines < 0.0f ? mk(t1.x, t1.y, t1.z) : mk(t0.x, t0.y, t0.z);
+    }
+    int4 ti = __ldg(reinterpret_cast<const int4*>(tp + 2));
+    if (kind == TEX_NOISE) {                                                               // :43-45
+        float c = 0.5f * (1.0f + sinf(t0.w * p.z + 10.0f * perlin_turb(sc.perlin + (size_t)ti.x * RTW_PERLIN_BYTES, p, 7)));
+        return mk(c, c, c);
+    }
+    // TEX_IMAGE                                                                           // :46-73
+    float uu = fminf(fmaxf(u, 0.0f), 1.0f);
+    float vv = 1.0f - fminf(fmaxf(v, 0.0f), 1.0f);
+    int i = (int)(uu * (float)ti.y), j = (int)(vv * (float)ti.z);
+    if (i >= ti.y) i = ti.y - 1;
+    if (j >= ti.z) j = ti.z - 1;
+    if (i < 0) i = 0;
+    if (j < 0) j = 0;
+    const uint8_t* px = sc.image + (size_t)ti.x + (size_t)j * ti.w + (size_t)i * 3;
+    const float s = 1.0f / 255.0f;
+    return mk(s * (float)__ldg(px), s * (float)__ldg(px + 1), s * (float)__ldg(px + 2));
+}
+
+// ------------------------------------------------------------------------------------------------
+// src/hittable.rs — primitive intersection
+// ------------------------------------------------------------------------------------------------
+struct HitRec {               // HitRecord :6-15
+    V3 p, normal; float t; int front; int mat; float u, v;
+};
+
+// Per-segment ray data kept in registers during traversal.
+struct TRay {
+    V3 o, d; float time;
+    double ox, oy, oz, dx, dy, dz, a;      // f64 copies for the sphere discriminant; a = |d|^2
+};
+RTW_DEV TRay make_tray(const Ray& r) {
+    TRay t; t.o = r.o; t.d = r.d; t.time = r.time;
+    t.ox = r.o.x; t.oy = r.o.y; t.oz = r.o.z; t.dx = r.d.x; t.dy = r.d.y; t.dz = r.d.z;
+    t.a = t.dx * t.dx + t.dy * t.dy + t.dz * t.dz;
+    return t;
+}
+
+RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float time, double& cx, double& cy, double& cz, double& r) {
+    const double2* q = reinterpret_cast<const double2*>(pp);
+    double2 c01 = __ldg(q), c23 = __ldg(q + 1);
+    cx = c01.x; cy = c01.y; cz = c23.x; r = c23.y;
+    if (type == PRIM_MOVING_SPHERE) {                                                      // get_center_at_time :556-558
+        double2 d01 = __ldg(q + 2), d2t = __ldg(q + 3);
+        float2 tt = *reinterpret_cast<const float2*>(&d2t.y);
+        double s = (double)((time - tt.x) * tt.y);
+        cx = fma(s, d01.x, cx); cy = fma(s, d01.y, cy); cz = fma(s, d2t.x, cz);
+    }
+}
+
+// sphere_hit :254-288 — roots only.  oc, half_b, c and the discriminant in f64 (the reference's precision),
+// then the numerically stable root pair in f32.  Returns the accepted root or NaN.
+RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi) {
+    double cx, cy, cz, rad;
+    load_prim_center(pp, type, r.time, cx, cy, cz, rad);
+    double ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
+    double half_b = ocx * r.dx + ocy * r.dy + ocz * r.dz;
+    double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
+    double disc = half_b * half_b - r.a * c;
+    if (disc < 0.0) return CUDART_NAN_F;
+    float sq = sqrtf((float)disc), hb = (float)half_b, a = (float)r.a, cf = (float)c;
+    float t_near, t_far;
+    if (hb < 0.0f) { float q = sq - hb; t_far = q / a; t_near = cf / q; }
+    else { float q = -hb - sq; t_near = q / a; t_far = cf / q; }
+    float root = t_near;                                                                   // :266-273
+    if (!(root >= t_lo && root <= t_hi)) {
+        root = t_far;
+        if (!(root >= t_lo && root <= t_hi)) return CUDART_NAN_F;
+    }
+    return root;
+}
+
+RTW_DEV void xform_ray(const DScene& sc, int xf, V3& o, V3& d) {                            // Translate :233, RotateY :390-394 (composed)
+    const float4* xp = reinterpret_cast<const float4*>(sc.xforms + xf);
+    float4 m = __ldg(xp); float bz = __ldg(reinterpret_cast<const float*>(xp + 1));
+    float ox = m.x * o.x - m.y * o.z + m.z, oz = m.y * o.x + m.x * o.z + bz;
+    float dx = m.x * d.x - m.y * d.z, dz = m.y * d.x + m.x * d.z;
+    o = mk(ox, o.y + m.w, oz); d = mk(dx, d.y, dz);
+}
+
+// xy/xz/yz_rect_hit :308-384 — t only.  The ray is in the rect's object space.
+RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, float t_lo, float t_hi) {
+    const float4* q = reinterpret_cast<const float4*>(pp);
+    float4 ab = __ldg(q); float k = __ldg(reinterpret_cast<const float*>(q + 1));
+    float ok, dk, oa, da, ob, db;
+    if (type == PRIM_XY) { ok = o.z; dk = d.z; oa = o.x; da = d.x; ob = o.y; db = d.y; }
+    else if (type == PRIM_XZ) { ok = o.y; dk = d.y; oa = o.x; da = d.x; ob = o.z; db = d.z; }
+    else { ok = o.x; dk = d.x; oa = o.y; da = d.y; ob = o.z; db = d.z; }
+    float t = (k - ok) / dk;
+    if (!(t >= t_lo && t <= t_hi)) return CUDART_NAN_F;
+    float a = oa + t * da, b = ob + t * db;
+    if (a < ab.x || a > ab.y || b < ab.z || b > ab.w) return CUDART_NAN_F;
+    return t;
+}
+
+// Any primitive: accepted root in [t_lo, t_hi] or NaN.
+RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi) {
+    const DPrim* pp = sc.prims + pi;
+    int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
+    if (meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi);
+    V3 o = r.o, d = r.d;
+    if (meta.z) xform_ray(sc, meta.z, o, d);
+    return rect_root(pp, meta.x, o, d, t_lo, t_hi);
+}
+
+// AABB::hit (src/aabb.rs:77-103) for the two children of a node, with precomputed 1/d and o/d.  Conservative
+// (closed interval, upper bound padded by 2 ulp — Ize, "Robust BVH ray traversal") so that the f32 slab test can
+// never cull a primitive the f64 reference would hit; the primitive tests decide.
+RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float t_lo, float t_hi, float& t_enter) {
+    float x0 = fmaf(mnx, inv.x, -oi.x), x1 = fmaf(mxx, inv.x, -oi.x);
+    float y0 = fmaf(mny, inv.y, -oi.y), y1 = fmaf(mxy, inv.y, -oi.y);
+    float z0 = fmaf(mnz, inv.z, -oi.z), z1 = fmaf(mxz, inv.z, -oi.z);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)) * 1.0000004f;
+    t_enter = tn;
+    return tn <= tf;
+}
+
+#define RTW_STACK 64
+
+// Closest surface hit over the BVH (replaces hit_hittables :43-55 + bvh_node_hit :290-306 over the whole world).
+RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best) {
+    V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    V3 oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
+    int stack[RTW_STACK];
+    int sp = 0;
+    int node = 0;
+    if (sc.n_bvh_prims == 0) return;
+    for (;;) {
+        if (node >= 0) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+            float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+            float e0, e1;
+            bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, t_min, t_best, e0);
+            bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, t_min, t_best, e1);
+            if (h0 && h1) {
+                int nearc = n3.x, farc = n3.y;
+                if (e1 < e0) { nearc = n3.y; farc = n3.x; }
+                stack[sp++] = farc;
+                node = nearc;
+                continue;
+            }
+            if (h0) { node = n3.x; continue; }
+            if (h1) { node = n3.y; continue; }
+        } else {
+            int code = ~node, first = code >> 3, count = (code & 7) + 1;
+            for (int i = 0; i < count; ++i) {
+                float t = prim_root(sc, first + i, r, t_min, t_best);
+                if (t == t) { t_best = t; prim_best = first + i; }       // not NaN: accepted, t <= t_best
+            }
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+}
+
+// set_face_normal :23-26
+RTW_DEV void set_face_normal(V3 dir, V3 outward, V3& normal, int& front) {
+    front = dot(dir, outward) < 0.0f;
+    normal = front ? outward : -outward;
+}
+
+// Fill the HitRecord for the accepted (prim, t): sphere_hit :275-287, rect_hit :322-329, then the wrapper chain
+// (Translate :236-239, hit_rotate_y :398-410) with the reference's nested set_face_normal calls replayed literally.
+RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool want_uv, HitRec& rec) {
+    const DPrim* pp = sc.prims + pi;
+    int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);
+    rec.t = t; rec.mat = meta.y; rec.u = 0.0f; rec.v = 0.0f;
+    Ray wr; wr.o = r.o; wr.d = r.d;
+    rec.p = ray_at(wr, t);
+    V3 outward_obj, d_obj = r.d;
+    const int xf = meta.z;
+    float mc = 1.0f, ms = 0.0f;
+    if (xf) { float4 m = __ldg(reinterpret_cast<const float4*>(sc.xforms + xf)); mc = m.x; ms = m.y; d_obj = mk(mc * r.d.x - ms * r.d.z, r.d.y, ms * r.d.x + mc * r.d.z); }
+    if (meta.x <= PRIM_MOVING_SPHERE) {
+        double cx, cy, cz, rad;
+        load_prim_center(pp, meta.x, r.time, cx, cy, cz, rad);
+        float inv_r = 1.0f / (float)rad;
+        // (p - c) / r in f64 for the subtraction (|c| can be 1000x the offset), f32 after
+        V3 ow = mk((float)((double)rec.p.x - cx) * inv_r, (float)((double)rec.p.y - cy) * inv_r, (float)((double)rec.p.z - cz) * inv_r);
+        outward_obj = xf ? mk(mc * ow.x - ms * ow.z, ow.y, ms * ow.x + mc * ow.z) : ow;
+        if (want_uv) sphere_uv(outward_obj, rec.u, rec.v);
+    } else {
+        V3 o = r.o, d = r.d;
+        if (xf) xform_ray(sc, xf, o, d);
+        const float4* q = reinterpret_cast<const float4*>(pp);
+        float4 ab = __ldg(q);
+        float a, b;
+        if (meta.x == PRIM_XY) { a = o.x + t * d.x; b = o.y + t * d.y; outward_obj = mk(0.f, 0.f, 1.f); }
+        else if (meta.x == PRIM_XZ) { a = o.x + t * d.x; b = o.z + t * d.z; outward_obj = mk(0.f, 1.f, 0.f); }
+        else { a = o.y + t * d.y; b = o.z + t * d.z; outward_obj = mk(1.f, 0.f, 0.f); }
+        rec.u = (a - ab.x) / (ab.y - ab.x);
+        rec.v = (b - ab.z) / (ab.w - ab.z);
+    }
+    set_face_normal(d_obj, outward_obj, rec.normal, rec.front);
+    if (xf) {
+        const DXform* x = sc.xforms + xf;
+        int n_ops = __ldg(&x->n_ops);
+        V3 nrm = rec.normal; int front = rec.front;
+        for (int j = n_ops - 1; j >= 0; --j) {
+            float4 op = __ldg(reinterpret_cast<const float4*>(&x->ops[j]));
+            // normal into the space outside op j (inverse rotation; identity for Translate)
+            nrm = mk(op.x * nrm.x + op.y * nrm.z, nrm.y, -op.y * nrm.x + op.x * nrm.z);
+            // direction on the INSIDE of op j (object-space ray of hit_rotate_y :409; moved_ray of Translate :238)
+            V3 dj = mk(op.z * r.d.x - op.w * r.d.z, r.d.y, op.w * r.d.x + op.z * r.d.z);
+            V3 outn = nrm;
+            set_face_normal(dj, outn, nrm, front);
+        }
+        rec.normal = nrm; rec.front = front;
+    }
+}
+
+// hit_constant_medium :417-473 for medium m, with the current closest surface hit as t_max.
+template <class R>
+RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, float t_max, R& g, float& t_out, int& mat_out) {
+    int4 md = __ldg(reinterpret_cast<const int4*>(sc.media + mi));
+    const float inf = CUDART_INF_F;
+    float t1 = CUDART_NAN_F;
+    {   // boundary.hit(ray, -inf, inf) :422 — closest-so-far scan over the boundary prims (hit_hittables :43-55)
+        float hi = inf;
+        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, -inf, hi); if (t == t) { hi = t; t1 = t; } }
+    }
+    if (!(t1 == t1)) return false;
+    float t2 = CUDART_NAN_F;
+    {   // boundary.hit(ray, rec1.t + 0.0001, inf) :423
+        float hi = inf, lo = t1 + 0.0001f;
+        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi); if (t == t) { hi = t; t2 = t; } }
+    }
+    if (!(t2 == t2)) return false;
+    if (t1 < t_min) t1 = t_min;
+    if (t2 > t_max) t2 = t_max;
+    if (t1 >= t2) return false;
+    if (t1 < 0.0f) t1 = 0.0f;
+    float ray_length = sqrtf(length_squared(r.d));
+    float distance_inside_boundary = (t2 - t1) * ray_length;
+    float hit_distance = __int_as_float(md.z) * logf(g.next());                            // :446 — the draw
+    if (hit_distance > distance_inside_boundary) return false;
+    t_out = t1 + hit_distance / ray_length;
+    mat_out = md.w;
+    return true;
+}
+
+// World closest hit = surfaces through the BVH, then the media in list order (media_deferred order of the oracle).
+template <class R>
+RTW_DEV bool world_hit(const DScene& sc, const TRay& r, float t_min, float t_max, R& g, bool want_uv, HitRec& rec) {
+    float t_best = t_max; int prim_best = -1;
+    bvh_closest(sc, r, t_min, t_best, prim_best);
+    int med_mat = -1; float med_t = 0.0f;
+    for (int m = 0; m < sc.n_media; ++m) {
+        float t; int mat;
+        if (medium_hit(sc, m, r, t_min, t_best, g, t, mat)) { t_best = t; med_t = t; med_mat = mat; prim_best = -2; }
+    }
+    if (prim_best == -1) return false;
+    if (prim_best == -2) {                                                                 // :460-464
+        Ray wr; wr.o = r.o; wr.d = r.d;
+        rec.t = med_t; rec.p = ray_at(wr, med_t); rec.normal = mk(1.f, 0.f, 0.f); rec.front = 1; rec.mat = med_mat;
+        rec.u = 0.f; rec.v = 0.f;
+        return true;
+    }
+    finalize_hit(sc, prim_best, t_best, r, want_uv, rec);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// src/material.rs — emitted (:25-34), scatter (:15-23, :36-94)
+// ------------------------------------------------------------------------------------------------
+RTW_DEV float reflectance(float cosine, float ref_idx) {                                    // :89-94
+    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    r0 = r0 * r0;
+    float x = 1.0f - cosine, x2 = x * x;
+    return r0 + (1.0f - r0) * (x2 * x2 * x);                                               // powf(5.0)
+}
+
+struct DMatRec { float r, g, b, param; int kind, tex; };
+RTW_DEV DMatRec load_mat(const DScene& sc, int mat) {
+    const float4* mp = reinterpret_cast<const float4*>(sc.mats + mat);
+    float4 a = __ldg(mp); int4 b = __ldg(reinterpret_cast<const int4*>(mp + 1));
+    DMatRec m; m.r = a.x; m.g = a.y; m.b = a.z; m.param = a.w; m.kind = b.x; m.tex = b.y;
+    return m;
+}
+RTW_DEV bool mat_needs_uv(const DScene& sc, const DMatRec& m) {
+    if (m.tex < 0) return false;
+    return __float_as_int(__ldg(&reinterpret_cast<const float4*>(sc.texs + m.tex)[1].w)) == TEX_IMAGE;
+}
+RTW_DEV V3 mat_color(const DScene& sc, const DMatRec& m, const HitRec& rec) {
+    if (m.tex < 0) return mk(m.r, m.g, m.b);
+    return texture_value(sc, m.tex, rec.u, rec.v, rec.p);
+}
+
+// Returns true when a scattered ray exists.  `emitted` is always written.
+template <class R>
+RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const HitRec& rec, R& g, Ray& scattered, V3& attenuation, V3& emitted) {
+    emitted = mk(0.f, 0.f, 0.f);
+    scattered.o = rec.p; scattered.time = ray.time;
+    switch (m.kind) {
+    case MAT_LAMBERTIAN: {                                                                 // :36-48
+        V3 dir = rec.normal + random_unit_vector(g);
+        if (near_zero(dir)) dir = rec.normal;
+        scattered.d = dir;
+        attenuation = mat_color(sc, m, rec);
+        return true;
+    }
+    case MAT_METAL: {                                                                      // :50-60
+        V3 reflected = reflect(normalize(ray.d), rec.normal);
+        scattered.d = reflected + m.param * random_in_unit_sphere(g);
+        attenuation = mk(m.r, m.g, m.b);
+        return dot(scattered.d, rec.normal) > 0.0f;
+    }
+    case MAT_DIELECTRIC: {                                                                 // :62-82
+        attenuation = mk(1.f, 1.f, 1.f);
+        float ratio = rec.front ? 1.0f / m.param : m.param;
+        V3 unit_direction = normalize(ray.d);
+        float cos_theta = fminf(dot(-unit_direction, rec.normal), 1.0f);
+        float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+        bool cannot_refract = ratio * sin_theta > 1.0f;
+        if (cannot_refract || reflectance(cos_theta, ratio) > g.next())                   // short-circuit draw :72
+            scattered.d = reflect(unit_direction, rec.normal);
+        else
+            scattered.d = refract(unit_direction, rec.normal, ratio);
+        return true;
+    }
+    case MAT_DIFFUSE_LIGHT:                                                                // :20, :25-34 (both faces emit)
+        emitted = mat_color(sc, m, rec);
+        attenuation = mk(0.f, 0.f, 0.f);
+        return false;
+    default:                                                                               // Isotropic :84-87
+        scattered.d = random_in_unit_sphere(g);
+        attenuation = mat_color(sc, m, rec);
+        return true;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// src/main.rs:19-38 — ray_color, unrolled into an iterative throughput/radiance pair:
+//   L += T * emitted;  T *= attenuation;  miss: L += T * background;  depth exhausted: nothing added (:21-23)
+// ------------------------------------------------------------------------------------------------
+struct PathState {
+    Ray ray;
+    V3 T, L;
+    int segment;            // segments traced so far (bounce id of the next one = segment + 1)
+    PhiloxRng rng;
+};
+
+RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, int s, PathState& ps) {   // :517-520
+    ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)(y * prm.width + x), (uint32_t)s);
+    float u = ((float)x + ps.rng.next()) / ((float)prm.width - 1.0f);
+    float v = ((float)y + ps.rng.next()) / ((float)prm.height - 1.0f);
+    ps.ray = camera_get_ray(cam, u, v, ps.rng);
+    ps.T = mk(1.f, 1.f, 1.f); ps.L = mk(0.f, 0.f, 0.f);
+    ps.segment = 0;
+}
+
+// One level of ray_color.  Returns true while the path continues.
+RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps) {
+    if (ps.segment >= prm.max_depth) return false;                                         // :21-23
+    ps.segment++;
+    ps.rng.set_bounce((uint32_t)ps.segment);
+    TRay tr = make_tray(ps.ray);
+    float t_best = CUDART_INF_F; int prim_best = -1;
+    bvh_closest(sc, tr, prm.t_min, t_best, prim_best);                                     // :25
+    int med_mat = -1; float med_t = 0.f;
+    for (int m = 0; m < sc.n_media; ++m) {
+        float t; int mat;
+        if (medium_hit(sc, m, tr, prm.t_min, t_best, ps.rng, t, mat)) { t_best = t; med_t = t; med_mat = mat; prim_best = -2; }
+    }
+    if (prim_best == -1) {                                                                 // :37
+        ps.L = ps.L + ps.T * mk(prm.bg_r, prm.bg_g, prm.bg_b);
+        return false;
+    }
+    HitRec rec; DMatRec m;
+    if (prim_best == -2) {
+        rec.t = med_t; rec.p = ray_at(ps.ray, med_t); rec.normal = mk(1.f, 0.f, 0.f); rec.front = 1; rec.mat = med_mat; rec.u = 0.f; rec.v = 0.f;
+        m = load_mat(sc, med_mat);
+    } else {
+        int mat = __ldg(&sc.prims[prim_best].mat);
+        m = load_mat(sc, mat);                                                             // :26
+        finalize_hit(sc, prim_best, t_best, tr, mat_needs_uv(sc, m), rec);
+    }
+    Ray scattered; V3 att, em;
+    bool cont = scatter(sc, m, ps.ray, rec, ps.rng, scattered, att, em);                  // :28-33
+    ps.L = ps.L + ps.T * em;
+    if (!cont) return false;
+    ps.T = ps.T * att;
+    ps.ray = scattered;
+    return true;
+}
+
+}  // namespace rtwd
+
+#endif

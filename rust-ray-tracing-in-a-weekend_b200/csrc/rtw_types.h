@@ -1,0 +1,125 @@
+// rtw_types.h — device-resident scene layout (shared by the host flattener and the CUDA kernels).
+//
+// The reference keeps the scene as a tree of tagged unions with Box<Hittable> children and by-value
+// textures inside materials (src/hittable.rs:29-41, src/material.rs:6-12, src/texture.rs:4-9).  Here the
+// scene is flattened once per commit into index-linked 16-byte-aligned records in ONE device blob:
+//
+//   nodes   : 64 B  binary BVH nodes holding BOTH children's boxes (4 x LDG.128 per visit)
+//   prims   : 80 B  records (5 x 16 B).  BVH-referenced prims first (leaf order), medium boundaries after
+//   xforms  : composed Translate/RotateY chains (src/hittable.rs:232-247, :386-415)
+//   media   : ConstantMedium table (src/hittable.rs:417-473)
+//   mats    : 32 B  materials, solid-colour textures inlined
+//   texs    : 48 B  textures; perlin tables (float4 gradients + u8 perms); image texels (RGB8)
+#ifndef RTW_TYPES_H
+#define RTW_TYPES_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define RTW_ALIGN(n) __align__(n)
+#else
+#define RTW_ALIGN(n) alignas(n)
+#endif
+
+enum : int32_t {
+    PRIM_SPHERE = 0,         // Hittable::Sphere        src/hittable.rs:31
+    PRIM_MOVING_SPHERE = 1,  // Hittable::MovingSphere  src/hittable.rs:32
+    PRIM_XY = 2,             // XYRect :34  (normal +z; a = x, b = y)
+    PRIM_XZ = 3,             // XZRect :35  (normal +y; a = x, b = z)
+    PRIM_YZ = 4              // YZRect :36  (normal +x; a = y, b = z)
+};
+
+enum : int32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
+enum : int32_t { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3 };
+
+// 80 B.  Spheres keep centre/radius in f64: the discriminant is evaluated in f64 on the device (B200 runs
+// FP64 at half the FP32 rate), which removes the |oc|^2 - r^2 cancellation of the r = 1000 ground sphere.
+struct RTW_ALIGN(16) DPrim {
+    union {
+        struct { double cx, cy, cz, r; } s;       // sphere: centre at time0 (world space, xform baked), radius
+        struct { float a0, a1, b0, b1, k, pad0, pad1, pad2; } q;   // rect (object space)
+    };
+    double dcx, dcy, dcz;                         // moving sphere: centre1 - centre0
+    float t0, inv_dt;                             // moving sphere: time0, 1/(time1-time0)
+    int32_t type;                                 // PRIM_*
+    int32_t mat;                                  // 0-based material index (reference handle - 1)
+    int32_t xform;                                // 0 = identity, else index into xforms
+    int32_t pad;
+};
+
+// Aila–Laine style node: both children's slabs live in the parent.
+struct RTW_ALIGN(16) DNode {
+    float c0minx, c0maxx, c0miny, c0maxy;
+    float c1minx, c1maxx, c1miny, c1maxy;
+    float c0minz, c0maxz, c1minz, c1maxz;
+    int32_t child0, child1;     // >= 0: inner node index.  < 0: leaf, ~code, code = first << 3 | (count - 1)
+    int32_t pad0, pad1;
+};
+
+#define RTW_MAX_CHAIN 4
+// One Translate/RotateY chain.  World -> object: o_obj = R(m_cos, m_sin) * o_w + b, d_obj = R * d_w, with
+// R(c, s) (x, z) = (c x - s z, s x + c z)  (src/hittable.rs:390-394).  ops[] (innermost LAST) replay the
+// reference's nested set_face_normal calls (src/hittable.rs:238, :409): `cum` rotates d_w into the space
+// inside op j.
+struct RTW_ALIGN(16) DXform {
+    float m_cos, m_sin, bx, by;
+    float bz; int32_t n_ops; int32_t pad0, pad1;
+    struct { float op_cos, op_sin, cum_cos, cum_sin; } ops[RTW_MAX_CHAIN];   // op_sin = 0 & op_cos = 1: Translate
+    int32_t is_rot[RTW_MAX_CHAIN];
+};
+
+struct RTW_ALIGN(16) DMedium {
+    int32_t first, count;       // boundary prims [first, first+count)
+    float neg_inv_density;      // src/hittable.rs:205
+    int32_t mat;                // phase function, 0-based
+};
+
+struct RTW_ALIGN(16) DMat {
+    float r, g, b, param;       // albedo / inline solid colour; param = fuzz (Metal) or ir (Dielectric)
+    int32_t kind;               // MAT_*
+    int32_t tex;                // -1: solid colour inlined in rgb; else texture index
+    int32_t pad0, pad1;
+};
+
+struct RTW_ALIGN(16) DTex {
+    float r0, g0, b0, scale;    // Solid: rgb0; Checker: even; Noise: scale
+    float r1, g1, b1; int32_t kind;   // Checker: odd
+    int32_t a, w, h, bps;       // Noise: a = perlin table index; Image: a = byte offset into image blob
+};
+
+#define RTW_PERLIN_BYTES (256 * 16 + 768)   // float4 ranvec[256] + u8 perm_x/y/z[256]
+
+struct DScene {
+    const DNode* nodes;
+    const DPrim* prims;
+    const DXform* xforms;
+    const DMedium* media;
+    const DMat* mats;
+    const DTex* texs;
+    const uint8_t* perlin;      // n_perlin tables of RTW_PERLIN_BYTES
+    const uint8_t* image;       // image texel blob
+    int32_t n_nodes, n_prims, n_bvh_prims, n_xforms, n_media, n_mats, n_texs, n_perlin;
+};
+
+// Camera in device precision.  llc_rel = lower_left_corner - origin is folded on the host in f64
+// (src/camera.rs:63 evaluates it per ray; folding avoids an f32 cancellation at |origin| ~ 800).
+struct DCamera {
+    float ox, oy, oz, lens_radius;
+    float lx, ly, lz, time0;     // llc_rel
+    float hx, hy, hz, time1;     // horizontal
+    float vx, vy, vz, pad0;      // vertical
+    float ux, uy, uz, pad1;      // u
+    float wx, wy, wz, pad2;      // v (camera "v" basis vector)
+};
+
+struct DParams {
+    int32_t width, height, spp, max_depth;
+    float bg_r, bg_g, bg_b, t_min;
+    uint32_t seed_lo, seed_hi;
+    int32_t tiles_x, tiles_y;          // 8x4-pixel tiles
+    int32_t chunks, chunk_spp;         // samples split into `chunks` units of `chunk_spp` per tile
+    uint32_t n_units;
+    int32_t accumulate;                // 1: atomicAdd into the framebuffer (several units or GPUs per pixel)
+};
+
+#endif

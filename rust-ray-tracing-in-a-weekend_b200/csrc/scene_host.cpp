@@ -1,0 +1,412 @@
+// scene_host.cpp — flatten the reference-shaped scene graph into SoA device records + a linearised BVH.
+//
+// What is mirrored (semantics) and what is deliberately not (structure):
+//  * Box = its 6 rects in new_box order (src/hittable.rs:132-145); closest-of-six == six rects in the BVH.
+//  * Translate / RotateY wrap a subtree (src/hittable.rs:232-247, :386-415): the chain of wrappers above a
+//    primitive is composed into one DXform; spheres are baked to world space (a rigid motion of a sphere is a
+//    sphere), rects keep object coordinates and the ray is moved into object space at test time.
+//  * BvhNode (src/hittable.rs:77-130): membership only.  The reference builder clones the list at every node
+//    (:78, O(N^2)) and leaves the world list itself un-accelerated (src/main.rs:25); any valid BVH returns the
+//    same closest hit, so ONE binned-SAH BVH is built over every surface primitive of the world.
+//  * ConstantMedium (src/hittable.rs:417-473): boundary subtree flattened into a private prim range scanned
+//    linearly; media are evaluated after the surface closest hit (same distribution).
+#include "scene_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "../../include/rtw.h"
+
+namespace rtw {
+namespace {
+
+const double PI = 3.1415926535897932385;   // src/math.rs:5
+
+struct Op { bool rot; double s, c; V3d off; };
+typedef std::vector<Op> Chain;
+
+struct Box3 {
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    void grow(const double p[3]) { for (int i = 0; i < 3; ++i) { mn[i] = std::min(mn[i], p[i]); mx[i] = std::max(mx[i], p[i]); } }
+    void grow(const Box3& b) { for (int i = 0; i < 3; ++i) { mn[i] = std::min(mn[i], b.mn[i]); mx[i] = std::max(mx[i], b.mx[i]); } }
+    double area() const {
+        double dx = mx[0] - mn[0], dy = mx[1] - mn[1], dz = mx[2] - mn[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0;
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct Composed { double C = 1, S = 0, b[3] = {0, 0, 0}; };
+
+Composed compose(const Chain& ch, std::vector<Composed>* prefix = nullptr) {
+    Composed m;
+    for (const Op& op : ch) {
+        if (!op.rot) { m.b[0] -= op.off.x; m.b[1] -= op.off.y; m.b[2] -= op.off.z; }
+        else {
+            double C = op.c * m.C - op.s * m.S, S = op.s * m.C + op.c * m.S;
+            double bx = op.c * m.b[0] - op.s * m.b[2], bz = op.s * m.b[0] + op.c * m.b[2];
+            m.C = C; m.S = S; m.b[0] = bx; m.b[2] = bz;
+        }
+        if (prefix) prefix->push_back(m);
+    }
+    return m;
+}
+// object -> world point / vector
+inline void to_world_point(const Composed& m, const double p[3], double out[3]) {
+    double x = p[0] - m.b[0], y = p[1] - m.b[1], z = p[2] - m.b[2];
+    out[0] = m.C * x + m.S * z; out[1] = y; out[2] = -m.S * x + m.C * z;
+}
+inline void to_world_vec(const Composed& m, const double v[3], double out[3]) {
+    out[0] = m.C * v[0] + m.S * v[2]; out[1] = v[1]; out[2] = -m.S * v[0] + m.C * v[2];
+}
+
+struct Flattener {
+    const SceneGraph& g;
+    FlatScene& out;
+    std::string& err;
+    std::vector<DPrim> bvh_prims;
+    std::vector<Box3> bvh_boxes;
+    std::vector<DPrim> boundary_prims;
+    std::vector<Chain> chains;      // index = xform id - 1
+
+    Flattener(const SceneGraph& g_, FlatScene& o, std::string& e) : g(g_), out(o), err(e) {}
+
+    int fail(int code, const std::string& m) { err = m; return code; }
+
+    static bool same(const Chain& a, const Chain& b) {
+        if (a.size() != b.size()) return false;
+        for (size_t i = 0; i < a.size(); ++i)
+            if (a[i].rot != b[i].rot || a[i].s != b[i].s || a[i].c != b[i].c || a[i].off.x != b[i].off.x ||
+                a[i].off.y != b[i].off.y || a[i].off.z != b[i].off.z) return false;
+        return true;
+    }
+
+    int intern(const Chain& ch) {
+        if (ch.empty()) return 0;
+        for (size_t i = 0; i < chains.size(); ++i) if (same(chains[i], ch)) return (int)i + 1;
+        chains.push_back(ch);
+        std::vector<Composed> prefix;
+        Composed m = compose(ch, &prefix);
+        DXform x; std::memset(&x, 0, sizeof(x));
+        x.m_cos = (float)m.C; x.m_sin = (float)m.S; x.bx = (float)m.b[0]; x.by = (float)m.b[1]; x.bz = (float)m.b[2];
+        x.n_ops = (int)ch.size();
+        for (size_t j = 0; j < ch.size(); ++j) {
+            x.ops[j].op_cos = (float)(ch[j].rot ? ch[j].c : 1.0);
+            x.ops[j].op_sin = (float)(ch[j].rot ? ch[j].s : 0.0);
+            x.ops[j].cum_cos = (float)prefix[j].C; x.ops[j].cum_sin = (float)prefix[j].S;
+            x.is_rot[j] = ch[j].rot ? 1 : 0;
+        }
+        out.xforms.push_back(x);
+        return (int)chains.size();
+    }
+
+    void push_prim(const DPrim& p, const Box3& b, bool boundary) {
+        if (boundary) boundary_prims.push_back(p);
+        else { bvh_prims.push_back(p); bvh_boxes.push_back(b); }
+    }
+
+    int emit_sphere(const HNode& h, const Chain& ch, bool boundary) {
+        DPrim p; std::memset(&p, 0, sizeof(p));
+        Composed m = compose(ch);
+        double c0[3] = {h.c0.x, h.c0.y, h.c0.z}, c0w[3];
+        to_world_point(m, c0, c0w);
+        p.s.cx = c0w[0]; p.s.cy = c0w[1]; p.s.cz = c0w[2]; p.s.r = h.radius;
+        double ar = std::fabs(h.radius);
+        Box3 b;
+        double lo[3] = {c0w[0] - ar, c0w[1] - ar, c0w[2] - ar}, hi[3] = {c0w[0] + ar, c0w[1] + ar, c0w[2] + ar};
+        b.grow(lo); b.grow(hi);
+        if (h.kind == H_MOVING_SPHERE) {
+            double dc[3] = {h.c1.x - h.c0.x, h.c1.y - h.c0.y, h.c1.z - h.c0.z}, dcw[3];
+            to_world_vec(m, dc, dcw);
+            p.dcx = dcw[0]; p.dcy = dcw[1]; p.dcz = dcw[2];
+            p.t0 = (float)h.time0; p.inv_dt = (float)(1.0 / (h.time1 - h.time0));
+            p.type = PRIM_MOVING_SPHERE;
+            // box over the sphere's own [time0, time1] (the MovingSphere arm shadows the arguments, hittable.rs:480-482)
+            double lo1[3] = {lo[0] + dcw[0], lo[1] + dcw[1], lo[2] + dcw[2]}, hi1[3] = {hi[0] + dcw[0], hi[1] + dcw[1], hi[2] + dcw[2]};
+            b.grow(lo1); b.grow(hi1);
+        } else p.type = PRIM_SPHERE;
+        p.mat = h.mat - 1;
+        p.xform = intern(ch);
+        push_prim(p, b, boundary);
+        return 0;
+    }
+
+    int emit_rect(const HNode& h, const Chain& ch, bool boundary) {
+        DPrim p; std::memset(&p, 0, sizeof(p));
+        p.q.a0 = (float)h.a0; p.q.a1 = (float)h.a1; p.q.b0 = (float)h.b0; p.q.b1 = (float)h.b1; p.q.k = (float)h.k;
+        p.type = h.kind == H_XY ? PRIM_XY : (h.kind == H_XZ ? PRIM_XZ : PRIM_YZ);
+        p.mat = h.mat - 1;
+        p.xform = intern(ch);
+        Composed m = compose(ch);
+        Box3 b;
+        const double pad = 0.0001;    // hittable.rs:486-503
+        for (int i = 0; i < 8; ++i) {
+            double a = (i & 1) ? h.a1 : h.a0, bb = (i & 2) ? h.b1 : h.b0, kk = (i & 4) ? h.k + pad : h.k - pad;
+            double q[3], w[3];
+            if (h.kind == H_XY) { q[0] = a; q[1] = bb; q[2] = kk; }
+            else if (h.kind == H_XZ) { q[0] = a; q[1] = kk; q[2] = bb; }
+            else { q[0] = kk; q[1] = a; q[2] = bb; }
+            to_world_point(m, q, w);
+            b.grow(w);
+        }
+        push_prim(p, b, boundary);
+        return 0;
+    }
+
+    int emit(int id, Chain& ch, bool boundary, int depth) {
+        if (id < 0 || id >= (int)g.nodes.size()) return fail(RTW_ERR_INVALID_ARG, "hittable id out of range");
+        if (depth > 64) return fail(RTW_ERR_UNSUPPORTED_NESTING, "hittable nesting deeper than 64");
+        const HNode& h = g.nodes[id];
+        switch (h.kind) {
+        case H_SPHERE: case H_MOVING_SPHERE: return emit_sphere(h, ch, boundary);
+        case H_XY: case H_XZ: case H_YZ: return emit_rect(h, ch, boundary);
+        case H_BOX: case H_BVH_NODE:
+            for (int c : h.children) { int rc = emit(c, ch, boundary, depth + 1); if (rc) return rc; }
+            return 0;
+        case H_TRANSLATE: case H_ROTATE_Y: {
+            if ((int)ch.size() >= RTW_MAX_CHAIN)
+                return fail(RTW_ERR_UNSUPPORTED_NESTING, "more than 4 nested Translate/RotateY wrappers");
+            Op op; op.rot = h.kind == H_ROTATE_Y; op.s = h.sin_theta; op.c = h.cos_theta; op.off = h.offset;
+            ch.push_back(op);
+            int rc = emit(h.child, ch, boundary, depth + 1);
+            ch.pop_back();
+            return rc;
+        }
+        default: {   // H_MEDIUM
+            if (boundary) return fail(RTW_ERR_UNSUPPORTED_NESTING, "ConstantMedium used as the boundary of a ConstantMedium");
+            if (!ch.empty()) return fail(RTW_ERR_UNSUPPORTED_NESTING, "ConstantMedium inside Translate/RotateY");
+            DMedium m; m.first = (int)boundary_prims.size();
+            int rc = emit(h.child, ch, true, depth + 1);
+            if (rc) return rc;
+            m.count = (int)boundary_prims.size() - m.first;
+            if (m.count == 0) return fail(RTW_ERR_INVALID_ARG, "ConstantMedium with an empty boundary");
+            m.neg_inv_density = (float)(-1.0 / h.density);
+            m.mat = h.mat - 1;
+            out.media.push_back(m);
+            return 0;
+        }
+        }
+    }
+};
+
+// ---- binned-SAH BVH ----------------------------------------------------------------------------
+struct BuildNode { Box3 box; int left = -1, right = -1; int first = 0, count = 0; };
+
+struct Builder {
+    const std::vector<Box3>& boxes;
+    std::vector<double> cen;          // 3 per prim
+    std::vector<int> idx;
+    std::vector<BuildNode> nodes;
+    int max_depth = 0;
+    static constexpr int NBINS = 16, MAX_LEAF = 4;
+    static constexpr double C_TRAV = 1.0, C_ISECT = 1.5;
+
+    explicit Builder(const std::vector<Box3>& b) : boxes(b) {
+        size_t n = b.size();
+        cen.resize(3 * n); idx.resize(n);
+        for (size_t i = 0; i < n; ++i) {
+            idx[i] = (int)i;
+            for (int a = 0; a < 3; ++a) cen[3 * i + a] = 0.5 * (b[i].mn[a] + b[i].mx[a]);
+        }
+    }
+
+    int build(int first, int count, int depth) {
+        max_depth = std::max(max_depth, depth);
+        int me = (int)nodes.size();
+        nodes.emplace_back();
+        Box3 box, cbox;
+        for (int i = first; i < first + count; ++i) {
+            box.grow(boxes[idx[i]]);
+            cbox.grow(&cen[3 * idx[i]]);
+        }
+        nodes[me].box = box; nodes[me].first = first; nodes[me].count = count;
+        if (count <= 1) return me;
+        // pick split
+        double best_cost = 1e300; int best_axis = -1, best_bin = -1;
+        double parent_area = std::max(box.area(), 1e-300);
+        for (int a = 0; a < 3; ++a) {
+            double lo = cbox.mn[a], hi = cbox.mx[a];
+            if (!(hi > lo)) continue;
+            double scale = NBINS / (hi - lo);
+            Box3 bb[NBINS]; int bc[NBINS] = {0};
+            for (int i = first; i < first + count; ++i) {
+                int k = std::min(NBINS - 1, std::max(0, (int)((cen[3 * idx[i] + a] - lo) * scale)));
+                bb[k].grow(boxes[idx[i]]); bc[k]++;
+            }
+            double la[NBINS], ra[NBINS]; int lc[NBINS], rc[NBINS];
+            Box3 acc; int n = 0;
+            for (int k = 0; k < NBINS; ++k) { if (bc[k]) acc.grow(bb[k]); n += bc[k]; la[k] = acc.area(); lc[k] = n; }
+            acc = Box3(); n = 0;
+            for (int k = NBINS - 1; k >= 0; --k) { if (bc[k]) acc.grow(bb[k]); n += bc[k]; ra[k] = acc.area(); rc[k] = n; }
+            for (int k = 0; k < NBINS - 1; ++k) {
+                if (lc[k] == 0 || rc[k + 1] == 0) continue;
+                double cost = C_TRAV + C_ISECT * (la[k] * lc[k] + ra[k + 1] * rc[k + 1]) / parent_area;
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
+            }
+        }
+        double leaf_cost = C_ISECT * count;
+        if (count <= MAX_LEAF && (best_axis < 0 || leaf_cost <= best_cost)) return me;
+        int mid;
+        if (best_axis < 0) {
+            mid = first + count / 2;       // coincident centroids: split by index
+        } else {
+            double lo = cbox.mn[best_axis], hi = cbox.mx[best_axis], scale = NBINS / (hi - lo);
+            auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](int p) {
+                int k = std::min(NBINS - 1, std::max(0, (int)((cen[3 * p + best_axis] - lo) * scale)));
+                return k <= best_bin;
+            });
+            mid = (int)(it - idx.begin());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        }
+        int l = build(first, mid - first, depth + 1);
+        int r = build(mid, first + count - mid, depth + 1);
+        nodes[me].left = l; nodes[me].right = r;
+        return me;
+    }
+};
+
+inline float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
+inline float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
+
+void set_child_box(DNode& n, int which, const Box3* b) {
+    const float inf = std::numeric_limits<float>::infinity();
+    float mnx = inf, mxx = -inf, mny = inf, mxy = -inf, mnz = inf, mxz = -inf;
+    if (b) { mnx = down(b->mn[0]); mxx = up(b->mx[0]); mny = down(b->mn[1]); mxy = up(b->mx[1]); mnz = down(b->mn[2]); mxz = up(b->mx[2]); }
+    if (which == 0) { n.c0minx = mnx; n.c0maxx = mxx; n.c0miny = mny; n.c0maxy = mxy; n.c0minz = mnz; n.c0maxz = mxz; }
+    else { n.c1minx = mnx; n.c1maxx = mxx; n.c1miny = mny; n.c1maxy = mxy; n.c1minz = mnz; n.c1maxz = mxz; }
+}
+inline int leaf_code(int first, int count) { return ~((first << 3) | (count - 1)); }
+
+void pack_materials(const SceneGraph& g, FlatScene& out) {
+    for (const HTexture& t : g.textures) {
+        DTex d; std::memset(&d, 0, sizeof(d));
+        d.kind = t.kind; d.r0 = (float)t.c0[0]; d.g0 = (float)t.c0[1]; d.b0 = (float)t.c0[2];
+        d.r1 = (float)t.c1[0]; d.g1 = (float)t.c1[1]; d.b1 = (float)t.c1[2]; d.scale = (float)t.scale;
+        if (t.kind == TEX_NOISE) {
+            d.a = (int)(out.perlin.size() / RTW_PERLIN_BYTES);
+            size_t base = out.perlin.size();
+            out.perlin.resize(base + RTW_PERLIN_BYTES);
+            float* rv = reinterpret_cast<float*>(out.perlin.data() + base);
+            for (int i = 0; i < 256; ++i) {
+                rv[4 * i] = (float)t.ranvec[3 * i]; rv[4 * i + 1] = (float)t.ranvec[3 * i + 1];
+                rv[4 * i + 2] = (float)t.ranvec[3 * i + 2]; rv[4 * i + 3] = 0.f;
+            }
+            uint8_t* pm = out.perlin.data() + base + 256 * 16;
+            for (int i = 0; i < 768; ++i) pm[i] = (uint8_t)(t.perm[i] & 255);
+        } else if (t.kind == TEX_IMAGE) {
+            size_t base = (out.image.size() + 15) & ~(size_t)15;
+            out.image.resize(base + t.data.size());
+            std::memcpy(out.image.data() + base, t.data.data(), t.data.size());
+            d.a = (int)base; d.w = t.w; d.h = t.h; d.bps = t.bps;
+        }
+        out.texs.push_back(d);
+    }
+    for (const HMaterial& m : g.materials) {
+        DMat d; std::memset(&d, 0, sizeof(d));
+        d.kind = m.kind; d.tex = -1;
+        if (m.kind == MAT_METAL) { d.r = (float)m.albedo[0]; d.g = (float)m.albedo[1]; d.b = (float)m.albedo[2]; d.param = (float)m.fuzz; }
+        else if (m.kind == MAT_DIELECTRIC) { d.r = d.g = d.b = 1.f; d.param = (float)m.ir; }
+        else {
+            const HTexture& t = g.textures[m.tex];
+            if (t.kind == TEX_SOLID) { d.r = (float)t.c0[0]; d.g = (float)t.c0[1]; d.b = (float)t.c0[2]; }
+            else d.tex = m.tex;
+        }
+        out.mats.push_back(d);
+    }
+}
+
+}  // namespace
+
+int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, std::string& err) {
+    out = FlatScene();
+    DXform ident; std::memset(&ident, 0, sizeof(ident)); ident.m_cos = 1.f;
+    out.xforms.push_back(ident);
+    Flattener fl(g, out, err);
+    Chain ch;
+    for (int id : roots) {
+        int rc = fl.emit(id, ch, false, 0);
+        if (rc) return rc;
+    }
+    pack_materials(g, out);
+    for (const DPrim& p : fl.bvh_prims) if (p.mat < 0 || p.mat >= (int)out.mats.size()) { err = "material handle out of range"; return RTW_ERR_INVALID_ARG; }
+    for (const DMedium& m : out.media) if (m.mat < 0 || m.mat >= (int)out.mats.size()) { err = "phase material handle out of range"; return RTW_ERR_INVALID_ARG; }
+    const int n = (int)fl.bvh_prims.size();
+    if (n >= (1 << 28)) { err = "too many primitives"; return RTW_ERR_INVALID_ARG; }
+    // BVH
+    Builder b(fl.bvh_boxes);
+    DNode root; std::memset(&root, 0, sizeof(root));
+    if (n == 0) {
+        set_child_box(root, 0, nullptr); set_child_box(root, 1, nullptr);
+        root.child0 = root.child1 = leaf_code(0, 1);
+        out.nodes.push_back(root);
+    } else {
+        b.nodes.reserve(2 * (size_t)n);
+        b.build(0, n, 0);
+        // leaf order
+        out.prims.resize(n);
+        for (int i = 0; i < n; ++i) out.prims[i] = fl.bvh_prims[b.idx[i]];
+        if (b.nodes[0].left < 0) {     // the whole scene is one leaf
+            // one leaf: both slots point at it (tested twice, like the reference's duplicated single-object
+            // leaves, src/hittable.rs:96-98); an "empty" slot cannot be encoded with min/max slabs
+            set_child_box(root, 0, &b.nodes[0].box); set_child_box(root, 1, &b.nodes[0].box);
+            root.child0 = leaf_code(0, n); root.child1 = leaf_code(0, n);
+            out.nodes.push_back(root);
+        } else {
+            // inner build nodes -> DNode indices (pre-order)
+            std::vector<int> dn(b.nodes.size(), -1);
+            int cnt = 0;
+            for (size_t i = 0; i < b.nodes.size(); ++i) if (b.nodes[i].left >= 0) dn[i] = cnt++;
+            out.nodes.resize(cnt);
+            double sah = 0, root_area = std::max(b.nodes[0].box.area(), 1e-300);
+            for (size_t i = 0; i < b.nodes.size(); ++i) {
+                const BuildNode& bn = b.nodes[i];
+                if (bn.left < 0) { sah += Builder::C_ISECT * bn.count * bn.box.area() / root_area; continue; }
+                sah += Builder::C_TRAV * bn.box.area() / root_area;
+                DNode d; std::memset(&d, 0, sizeof(d));
+                const BuildNode& l = b.nodes[bn.left]; const BuildNode& r = b.nodes[bn.right];
+                set_child_box(d, 0, &l.box); set_child_box(d, 1, &r.box);
+                d.child0 = l.left >= 0 ? dn[bn.left] : leaf_code(l.first, l.count);
+                d.child1 = r.left >= 0 ? dn[bn.right] : leaf_code(r.first, r.count);
+                out.nodes[dn[i]] = d;
+            }
+            out.sah_cost = sah;
+        }
+    }
+    out.max_depth = b.max_depth;
+    out.n_bvh_prims = n;
+    // boundary prims follow; shift media ranges
+    for (DMedium& m : out.media) m.first += n;
+    out.prims.insert(out.prims.end(), fl.boundary_prims.begin(), fl.boundary_prims.end());
+    if (out.max_depth > 60) { err = "BVH deeper than the traversal stack"; return RTW_ERR_UNSUPPORTED_NESTING; }
+    return 0;
+}
+
+bool validate_bvh(const FlatScene& f, std::string& err) {
+    std::vector<int> seen(f.n_bvh_prims, 0);
+    struct Item { int node; };
+    if (f.nodes.empty()) { err = "no nodes"; return false; }
+    std::vector<int> stack{0};
+    size_t visited = 0;
+    while (!stack.empty()) {
+        int ni = stack.back(); stack.pop_back();
+        if (ni < 0 || ni >= (int)f.nodes.size()) { err = "node index out of range"; return false; }
+        if (++visited > f.nodes.size()) { err = "cycle"; return false; }
+        const DNode& n = f.nodes[ni];
+        for (int c = 0; c < 2; ++c) {
+            int ch = c ? n.child1 : n.child0;
+            float mnx = c ? n.c1minx : n.c0minx, mxx = c ? n.c1maxx : n.c0maxx;
+            if (ch >= 0) { stack.push_back(ch); continue; }
+            if (mnx > mxx) continue;   // empty slot
+            int code = ~ch, first = code >> 3, count = (code & 7) + 1;
+            if (first < 0 || first + count > f.n_bvh_prims) { err = "leaf range out of bounds"; return false; }
+            for (int i = first; i < first + count; ++i) seen[i]++;
+        }
+    }
+    const int want = (f.nodes.size() == 1 && f.nodes[0].child0 == f.nodes[0].child1 && f.nodes[0].child0 < 0) ? 2 : 1;
+    for (int i = 0; i < f.n_bvh_prims; ++i) if (seen[i] != want) { err = "prim not referenced exactly once"; return false; }
+    return true;
+}
+
+}  // namespace rtw
