@@ -186,13 +186,14 @@ __global__ void texture_kernel(DScene sc, int tex, int n, const double* __restri
     out[3 * i] = c.x; out[3 * i + 1] = c.y; out[3 * i + 2] = c.z;
 }
 
-// write_color (src/math.rs:119-132): sqrt(c/spp), clamp [0, 0.999], *256 truncated; NaN -> 0
-__global__ void write_color_kernel(const float* __restrict__ sum, int n, float inv_spp, uint8_t* __restrict__ out) {
+// write_color (src/math.rs:119-132): sqrt(c * (1/spp)), clamp [0, 0.999], *256 truncated; NaN -> 0.
+// Evaluated in f64 like the reference so the bytes are bit-exact for identical sums.
+__global__ void write_color_kernel(const float* __restrict__ sum, int n, double scale, uint8_t* __restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float r = sqrtf(sum[i] * inv_spp);
-    float c = r < 0.0f ? 0.0f : (r > 0.999f ? 0.999f : r);
-    c *= 256.0f;
+    double r = sqrt((double)sum[i] * scale);
+    double c = r < 0.0 ? 0.0 : (r > 0.999 ? 0.999 : r);
+    c *= 256.0;
     out[i] = (c == c) ? (uint8_t)(int)c : 0;
 }
 
@@ -644,7 +645,7 @@ int rtw_write_color(const float* rgb_sum, int32_t n_pixels, int32_t spp, uint8_t
     TRY(need_device());
     Scratch sc; float* d_in; uint8_t* d_out; size_t n = (size_t)n_pixels * 3;
     TRY(sc.up(rgb_sum, n, d_in)); TRY(sc.up((const uint8_t*)nullptr, n, d_out));
-    write_color_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_in, (int)n, 1.0f / (float)spp, d_out);
+    write_color_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_in, (int)n, 1.0 / (double)spp, d_out);
     CUDA_TRY(cudaGetLastError());
     TRY(sc.down(out_rgb8, d_out, n));
     return RTW_OK;

@@ -393,7 +393,9 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     if (!(t1 == t1)) return false;
     float t2 = CUDART_NAN_F;
     {   // boundary.hit(ray, rec1.t + 0.0001, inf) :423
+        // in f32 the +0.0001 vanishes once |t1| > 2048 (r = 5000 fog sphere): keep the probe strictly beyond t1
         float hi = inf, lo = t1 + 0.0001f;
+        if (!(lo > t1)) lo = nextafterf(t1, inf);
         for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi); if (t == t) { hi = t; t2 = t; } }
     }
     if (!(t2 == t2)) return false;

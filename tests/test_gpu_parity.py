@@ -1,0 +1,514 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (BASELINE.json north_star): kernel-level outputs within 1e-5 relative of the f64 reference arithmetic on
+identical (f32-representable) inputs; discrete outputs equal except on rays the oracle itself flips under a 1e-6
+relative input perturbation ("ill-conditioned"); full renders within the Monte-Carlo bound (3 sigma per pixel,
+PSNR >= 40 dB at 4096 spp).  Integer/byte work (Philox words, write_color bytes, draw counts) is bit-exact.
+"""
+import math
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import f32, q24
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REL = 1e-5
+
+
+def rel_err(got, ref, scale):
+    return np.abs(got - ref) / np.maximum(np.abs(ref), scale)
+
+
+def build_both(pkg, gpu, orc, name, wrap=None, **kw):
+    if wrap is None:
+        wrap = name not in ("cornell_box_smoke", "final_scene")
+    a, spec = pkg.scenes.build(gpu, name, **kw)
+    b, _ = pkg.scenes.build(orc, name, wrap_bvh=wrap, **kw)
+    b.set_media_deferred(True)
+    a.commit(1, 0)
+    return a, b, spec
+
+
+def camera_rays(pkg, lib, spec, n, rs, W=96, H=64):
+    cam = spec.camera(lib, W, H)
+    g = lib.test_get_ray(cam, f32(rs.rand(n)), f32(rs.rand(n)), q24(rs, (n, 24)))
+    return g
+
+
+def stable(oracle_hit, o, d, tm, scale, **kw):
+    """Mask of rays whose ORACLE answer (hit flag, and t within 1e-5) survives 1e-6-relative input perturbations."""
+    base = oracle_hit(o, d, tm, **kw)
+    ok = np.ones(len(o), bool)
+    rs = np.random.RandomState(99)
+    for _ in range(2):
+        dd = d * (1 + 1e-6 * rs.uniform(-1, 1, d.shape))
+        oo = o + 1e-6 * scale * rs.uniform(-1, 1, o.shape)
+        h = oracle_hit(oo, dd, tm, **kw)
+        ok &= h["hit"] == base["hit"]
+        ok &= (h["mat"] == base["mat"])
+        both = (h["hit"] == 1) & (base["hit"] == 1)
+        ok &= ~both | (np.abs(h["t"] - base["t"]) <= 20 * REL * np.maximum(np.abs(base["t"]), 1e-3))
+        ok &= ~both | (np.abs(h["normal"] - base["normal"]).max(1) < 1e-3)
+    return base, ok
+
+
+def compare_hits(ha, hb, ok, pos_scale, min_stable=0.9, check_uv=True):
+    assert ok.mean() >= min_stable, ok.mean()
+    assert np.array_equal(ha["hit"][ok], hb["hit"][ok])
+    # over ALL rays (ill-conditioned included) the flags may differ only rarely
+    assert np.mean(ha["hit"] != hb["hit"]) < 5e-3
+    m = ok & (hb["hit"] == 1)
+    assert m.sum() > 0
+    assert np.array_equal(ha["mat"][m], hb["mat"][m])
+    assert np.array_equal(ha["front"][m], hb["front"][m])
+    assert rel_err(ha["t"][m], hb["t"][m], 1e-3).max() <= REL
+    assert rel_err(ha["p"][m], hb["p"][m], pos_scale).max() <= REL
+    assert np.abs(ha["normal"][m] - hb["normal"][m]).max() <= REL
+    if check_uv:
+        # u wraps at the sphere seam: compare on the circle
+        du = np.abs(ha["u"][m] - hb["u"][m])
+        du = np.minimum(du, 1 - du)
+        polar = (hb["v"][m] < 1e-3) | (hb["v"][m] > 1 - 1e-3)
+        assert du[~polar].max() <= 2 * REL and np.abs(ha["v"][m] - hb["v"][m]).max() <= 5 * REL
+    assert np.array_equal(ha["ndraw"][ok], hb["ndraw"][ok])
+
+
+# --------------------------------------------------------------------------------------------- RNG / camera
+def test_philox_bit_exact(gpu, orc):
+    rs = np.random.RandomState(0)
+    ctr = rs.randint(0, 2 ** 32, (100000, 4), dtype=np.uint64).astype(np.uint32)
+    key = rs.randint(0, 2 ** 32, (100000, 2), dtype=np.uint64).astype(np.uint32)
+    assert np.array_equal(gpu.philox(ctr, key), orc.philox(ctr, key))
+    assert list(gpu.philox([0, 0, 0, 0], [0, 0])[0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+@pytest.mark.parametrize("name", ["random_scene", "cornell_box", "final_scene", "simple_light"])
+def test_get_ray(pkg, gpu, orc, name):
+    sc, spec = pkg.scenes.build(orc, name)
+    rs = np.random.RandomState(1)
+    n = 200000
+    s, t, xi = f32(rs.rand(n)), f32(rs.rand(n)), q24(rs, (n, 24))
+    ga = gpu.test_get_ray(spec.camera(gpu, 1200, 800), s, t, xi)
+    gb = orc.test_get_ray(spec.camera(orc, 1200, 800), s, t, xi)
+    assert np.array_equal(ga["ndraw"], gb["ndraw"]) and (gb["ndraw"] >= 3).all()
+    assert np.array_equal(ga["time"], gb["time"])
+    scale = np.abs(np.array(spec.look_from)).max()
+    assert rel_err(ga["origin"], gb["origin"], scale).max() <= REL
+    dn = np.linalg.norm(gb["dir"], axis=1, keepdims=True)
+    assert (np.abs(ga["dir"] - gb["dir"]) / dn).max() <= REL
+
+
+def test_aabb_is_conservative_and_agrees(gpu, orc):
+    rs = np.random.RandomState(2)
+    n = 300000
+    c = f32(rs.uniform(-50, 50, (n, 3))); h = f32(rs.uniform(0.01, 20, (n, 3)))
+    mn, mx = f32(c - h), f32(c + h)
+    o = f32(rs.uniform(-100, 100, (n, 3)))
+    d = f32((c + rs.uniform(-1.5, 1.5, (n, 3)) * h - o) * rs.uniform(0.1, 3, (n, 1)))
+    ga = gpu.test_aabb(mn, mx, o, d, 0.001, 1e30)
+    gb = orc.test_aabb(mn, mx, o, d, 0.001, 1e30)
+    assert (ga >= gb).all()                      # the f32 slab test never culls what the f64 reference hits
+    # disagreements only where the interval is degenerate at the 1e-5 level
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t0, t1 = (mn - o) / d, (mx - o) / d
+    lo, hi = np.minimum(t0, t1).max(1), np.maximum(t0, t1).min(1)
+    lo = np.maximum(lo, 0.001)
+    degenerate = np.abs(hi - lo) <= 1e-4 * np.maximum(np.abs(hi), 1.0)
+    assert not (ga != gb)[~degenerate].any()
+    assert 0.2 < gb.mean() < 0.95
+
+
+# --------------------------------------------------------------------------------------------- primitives
+def _prim_cases(pkg, sc):
+    m = sc.lambertian(sc.tex_solid((0.5, 0.5, 0.5)))
+    m2 = sc.metal((0.5, 0.5, 0.5), 0.1)
+    cases = {}
+    cases["sphere"] = (sc.sphere(m, (1.5, -0.5, 2.0), 1.25), (1.5, -0.5, 2.0), 1.25)
+    cases["small_sphere"] = (sc.sphere(m2, (3.7, 0.2, -4.1), 0.2), (3.7, 0.2, -4.1), 0.2)
+    cases["ground_sphere"] = (sc.sphere(m, (0.0, -1000.0, 0.0), 1000.0), (0.0, 0.0, 0.0), 12.0)
+    cases["moving_sphere"] = (sc.moving_sphere(m, (0.3, 0.2, -1.0), (0.3, 0.65, -1.0), 0.0, 1.0, 0.2), (0.3, 0.4, -1.0), 0.45)
+    cases["xy_rect"] = (sc.xy_rect(m, 3, 5, 1, 3, -2), (4, 2, -2), 1.6)
+    cases["xz_rect"] = (sc.xz_rect(m, 213, 343, 227, 332, 554), (278, 554, 280), 90)
+    cases["yz_rect"] = (sc.yz_rect(m2, 0, 555, 0, 555, 555), (555, 278, 278), 400)
+    cases["box"] = (sc.box((0, 0, 0), (165, 330, 165), m), (82, 165, 82), 200)
+    box = sc.box((0, 0, 0), (165, 330, 165), m)
+    cases["translate_rotate_box"] = (sc.translate(sc.rotate_y(15.0, box), (265, 0, 295)), (347, 165, 377), 220)
+    cases["rotate_box"] = (sc.rotate_y(-18.0, sc.box((0, 0, 0), (165, 165, 165), m2)), (80, 82, 80), 160)
+    cases["translate_sphere"] = (sc.translate(sc.sphere(m, (0, 0, 0), 10.0), (100, 20, -30)), (100, 20, -30), 10)
+    cases["rotate_translate_rotate_sphere"] = (
+        sc.rotate_y(30.0, sc.translate(sc.rotate_y(45.0, sc.moving_sphere(m, (5, 0, 0), (5, 3, 0), 0.0, 1.0, 2.0)), (10, 0, 0))),
+        (12.0, 1.5, -9.0), 6.0)
+    bvh = sc.bvh_node([sc.sphere(m, (x * 3.0, 0.0, z * 3.0), 1.0) for x in range(4) for z in range(4)])
+    cases["bvh_node_of_spheres"] = (bvh, (4.5, 0, 4.5), 8)
+    cases["translate_rotate_bvh"] = (sc.translate(sc.rotate_y(15.0, bvh), (-100, 270, 395)), (-94, 270, 398), 9)
+    return cases
+
+
+CASE_NAMES = ["sphere", "small_sphere", "ground_sphere", "moving_sphere", "xy_rect", "xz_rect", "yz_rect", "box",
+              "translate_rotate_box", "rotate_box", "translate_sphere", "rotate_translate_rotate_sphere",
+              "bvh_node_of_spheres", "translate_rotate_bvh"]
+
+
+@pytest.mark.parametrize("case", CASE_NAMES)
+def test_hittable_hit(pkg, gpu, orc, case):
+    """Hittable::hit (src/hittable.rs:209-252) per variant / composition, fixed rays."""
+    a, b = pkg.Scene(gpu), pkg.Scene(orc)
+    ta, center, radius = _prim_cases(pkg, a)[case]
+    tb, _, _ = _prim_cases(pkg, b)[case]
+    assert ta == tb
+    rs = np.random.RandomState(zlib.crc32(case.encode()) % 1000)
+    n = 120000
+    center = np.array(center, float)
+    # origins on a shell around the target (some inside), directions towards a jittered point of it, un-normalised
+    dirs = rs.randn(n, 3); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    o = f32(center + dirs * radius * rs.uniform(0.2, 6.0, (n, 1)))
+    tgt = center + rs.uniform(-1.2, 1.2, (n, 3)) * radius
+    d = f32((tgt - o) * rs.uniform(0.05, 2.0, (n, 1)))
+    tm = f32(rs.rand(n))
+    hb, ok = stable(lambda oo, dd, tt: b.test_hit(tb, oo, dd, tt), o, d, tm, radius)
+    ha = a.test_hit(ta, o, d, tm)
+    assert 0.15 < hb["hit"].mean() < 0.999
+    compare_hits(ha, hb, ok, pos_scale=np.abs(center).max() + radius)
+
+
+def test_hit_range_edges(pkg, gpu, orc):
+    """t_min / t_max handling: rays starting ON the surface (t_min = 0.001 self-intersection guard), finite t_max."""
+    a, b = pkg.Scene(gpu), pkg.Scene(orc)
+    for sc in (a, b):
+        m = sc.dielectric(1.5)
+        sc.target = sc.sphere(m, (0.0, 1.0, 0.0), 1.0)
+    rs = np.random.RandomState(8)
+    n = 100000
+    nrm = rs.randn(n, 3); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    o = f32(np.array([0, 1.0, 0]) + nrm)                     # on the sphere (to f32 rounding)
+    d = f32(rs.randn(n, 3))
+    hb, ok = stable(lambda oo, dd, tt: b.test_hit(b.target, oo, dd, tt), o, d, np.zeros(n), 1.0)
+    ha = a.test_hit(a.target, o, d, np.zeros(n))
+    compare_hits(ha, hb, ok, pos_scale=2.0, min_stable=0.8)
+    inward = np.einsum("ij,ij->i", d, o - np.array([0, 1.0, 0])) < -0.2 * np.linalg.norm(d, axis=1)
+    assert (ha["hit"][inward] == 1).all() and (ha["front"][inward] == 0).all()      # exits through the far side
+    # finite t_max clips
+    ha2 = a.test_hit(a.target, o, d, np.zeros(n), t_max=0.5); hb2 = b.test_hit(b.target, o, d, np.zeros(n), t_max=0.5)
+    agree = ha2["hit"] == hb2["hit"]
+    assert agree[ok].mean() > 0.9995 and (hb2["t"][hb2["hit"] == 1] <= 0.5).all()
+
+
+@pytest.mark.parametrize("name", ["cornell_box_smoke", "final_scene"])
+def test_constant_medium_hit(pkg, gpu, orc, name):
+    """hit_constant_medium (src/hittable.rs:417-473) inside the world scan: draw gating, free-flight distance."""
+    a, b, spec = build_both(pkg, gpu, orc, name)
+    rs = np.random.RandomState(3)
+    g = camera_rays(pkg, orc, spec, 150000, rs)
+    xi = q24(rs, (150000, 4))
+    xi[xi == 0] = 0.5
+    o, d, tm = f32(g["origin"]), f32(g["dir"]), f32(g["time"])
+    hb, ok = stable(lambda oo, dd, tt, xi=xi: b.test_hit(-1, oo, dd, tt, xi=xi), o, d, tm, 1000.0)
+    ha = a.test_hit(-1, o, d, tm, xi=xi)
+    n_media = 2
+    assert hb["ndraw"].max() == n_media and (hb["ndraw"] >= (1 if name == "final_scene" else 0)).all()
+    compare_hits(ha, hb, ok, pos_scale=1000.0, check_uv=False)
+    med = ok & (hb["hit"] == 1) & np.all(hb["normal"] == [1, 0, 0], axis=1) & (hb["u"] == 0)
+    assert med.sum() > 100            # some rays really scatter inside the media
+
+
+@pytest.mark.parametrize("name", ["random_scene", "two_spheres", "two_perlin_spheres", "earth", "simple_light", "cornell_box", "final_scene"])
+def test_world_bvh_hit(pkg, gpu, orc, name):
+    """World closest hit through OUR flattened SAH BVH vs the oracle's hit_hittables over the reference tree:
+    primary rays, then secondary rays leaving the primary hit points."""
+    a, b, spec = build_both(pkg, gpu, orc, name)
+    rs = np.random.RandomState(4)
+    n = 150000
+    g = camera_rays(pkg, orc, spec, n, rs)
+    xi = q24(rs, (n, 4)); xi[xi == 0] = 0.5
+    o, d, tm = f32(g["origin"]), f32(g["dir"]), f32(g["time"])
+    scale = max(np.abs(np.array(spec.look_from)).max(), 10.0)
+    hb, ok = stable(lambda oo, dd, tt: b.test_hit(-1, oo, dd, tt, xi=xi), o, d, tm, scale)
+    ha = a.test_hit(-1, o, d, tm, xi=xi)
+    compare_hits(ha, hb, ok, pos_scale=scale, check_uv=name in ("earth", "final_scene"))
+    # secondary rays: origin = hit point (f32), direction = normal + unit vector (Lambertian-like, un-normalised)
+    hit = hb["hit"] == 1
+    o2 = f32(hb["p"][hit]); nn = hb["normal"][hit]
+    v = rs.randn(hit.sum(), 3); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    d2 = f32(nn + v); tm2 = tm[hit]; xi2 = xi[hit]
+    keep = np.linalg.norm(d2, axis=1) > 0.05
+    o2, d2, tm2, xi2 = o2[keep], d2[keep], tm2[keep], xi2[keep]
+    hb2, ok2 = stable(lambda oo, dd, tt: b.test_hit(-1, oo, dd, tt, xi=xi2), o2, d2, tm2, scale)
+    ha2 = a.test_hit(-1, o2, d2, tm2, xi=xi2)
+    compare_hits(ha2, hb2, ok2, pos_scale=scale, min_stable=0.8, check_uv=name in ("earth", "final_scene"))
+
+
+# --------------------------------------------------------------------------------------------- materials / textures
+def _scatter_inputs(rs, n):
+    nrm = rs.randn(n, 3); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    d = rs.randn(n, 3) * rs.uniform(0.05, 12, (n, 1))
+    flip = np.einsum("ij,ij->i", d, nrm) > 0
+    d[flip] -= 2 * np.einsum("ij,ij->i", d, nrm)[flip, None] * nrm[flip]      # face-forward: dot(d, n) < 0
+    p = rs.uniform(-20, 20, (n, 3))
+    return f32(p - d), f32(d), f32(rs.rand(n)), f32(p), f32(nrm), rs.randint(0, 2, n).astype(np.int32), f32(rs.rand(n)), f32(rs.rand(n))
+
+
+@pytest.mark.parametrize("kind", ["lambertian_solid", "lambertian_checker", "metal", "metal_fuzz1", "dielectric", "diffuse_light", "isotropic"])
+def test_material_scatter(pkg, gpu, orc, kind):
+    """Material::scatter / emitted (src/material.rs:15-94) with fixed random inputs."""
+    scenes = []
+    for lib in (gpu, orc):
+        sc = pkg.Scene(lib)
+        mats = dict(lambertian_solid=lambda: sc.lambertian(sc.tex_solid((0.4, 0.2, 0.1))),
+                    lambertian_checker=lambda: sc.lambertian(sc.tex_checker((0.2, 0.5, 0.5), (0.9, 0.9, 0.9))),
+                    metal=lambda: sc.metal((0.7, 0.6, 0.5), 0.3), metal_fuzz1=lambda: sc.metal((0.8, 0.8, 0.9), 1.0),
+                    dielectric=lambda: sc.dielectric(1.5), diffuse_light=lambda: sc.diffuse_light(sc.tex_solid((15, 15, 15))),
+                    isotropic=lambda: sc.isotropic(sc.tex_solid((0.2, 0.4, 0.9))))
+        mat = mats[kind]()
+        sc.push(sc.sphere(mat, (0, 0, 0), 1.0))
+        scenes.append((sc, mat))
+    scenes[0][0].commit(1, 0)
+    rs = np.random.RandomState(6)
+    n = 200000
+    ro, rd, rt, p, nrm, front, u, v = _scatter_inputs(rs, n)
+    xi = q24(rs, (n, 48))
+    ra = scenes[0][0].test_scatter(scenes[0][1], ro, rd, rt, p, nrm, front, u, v, xi)
+    rb = scenes[1][0].test_scatter(scenes[1][1], ro, rd, rt, p, nrm, front, u, v, xi)
+    assert (rb["ndraw"] >= 0).all()
+    same = (ra["scattered"] == rb["scattered"]) & (ra["ndraw"] == rb["ndraw"])
+    if kind == "dielectric":    # reflect/refract branch: side of the surface the new ray leaves on
+        same &= np.sign(np.einsum("ij,ij->i", ra["dir"], nrm)) == np.sign(np.einsum("ij,ij->i", rb["dir"], nrm))
+    if kind == "lambertian_checker":
+        same &= np.all(ra["attenuation"] == f32(rb["attenuation"]), axis=1)
+    assert same.mean() > 0.9995, same.mean()
+    m = same & (rb["scattered"] == 1)
+    if kind != "diffuse_light":
+        assert m.sum() > 0.4 * n
+        dn = np.maximum(np.linalg.norm(rb["dir"][m], axis=1, keepdims=True), 1e-2)
+        assert (np.abs(ra["dir"][m] - rb["dir"][m]) / dn).max() <= REL
+        assert np.array_equal(ra["origin"][m], rb["origin"][m]) and np.array_equal(ra["time"][m], rb["time"][m])
+        assert np.abs(ra["attenuation"][m] - rb["attenuation"][m]).max() <= REL
+    assert rel_err(ra["emitted"], rb["emitted"], 1.0).max() <= REL
+    if kind == "diffuse_light":
+        assert (ra["scattered"] == 0).all() and np.allclose(ra["emitted"], 15.0)
+
+
+@pytest.mark.parametrize("kind", ["checker", "noise4", "noise0.1", "image"])
+def test_texture_value(pkg, gpu, orc, kind):
+    """Texture::get_color_value (src/texture.rs:30-75) + Perlin::turb/noise (src/perlin.rs:32-108)."""
+    out = []
+    rs = np.random.RandomState(7)
+    n = 200000
+    span = dict(checker=30.0, noise4=40.0, image=1.0)["noise4" if kind.startswith("noise") else kind]
+    if kind == "noise0.1":
+        span = 400.0
+    p = f32(rs.uniform(-span, span, (n, 3)))
+    u, v = f32(rs.uniform(-0.1, 1.1, n)), f32(rs.uniform(-0.1, 1.1, n))
+    for lib in (gpu, orc):
+        sc = pkg.Scene(lib)
+        if kind == "checker":
+            t = sc.tex_checker((0.2, 0.5, 0.5), (0.9, 0.9, 0.9))
+        elif kind.startswith("noise"):
+            t = sc.tex_noise(*pkg.scenes.perlin_tables(pkg.scenes.HostRng(3)), float(kind[5:]))
+        else:
+            t = sc.tex_image(pkg.scenes.earth_texels())
+        sc.push(sc.sphere(sc.lambertian(t), (0, 0, 0), 1.0))
+        if lib is gpu:
+            sc.commit(1, 0)
+        out.append(sc.test_texture(t, u, v, p))
+    ga, gb = out
+    if kind == "checker":
+        sines = np.sin(10 * p[:, 0]) * np.sin(10 * p[:, 1]) * np.sin(10 * p[:, 2])
+        ok = np.abs(sines) > 1e-4
+        assert np.array_equal(ga[ok], f32(gb[ok])) and np.mean(np.any(ga != f32(gb), axis=1)) < 1e-4
+    elif kind == "image":
+        uu, vv = np.clip(u, 0, 1) * 1024, (1 - np.clip(v, 0, 1)) * 512
+        ok = (np.abs(uu - np.round(uu)) > 1e-3) & (np.abs(vv - np.round(vv)) > 1e-3)
+        assert np.abs(ga[ok] - gb[ok]).max() <= 1e-7 and np.mean(np.any(np.abs(ga - gb) > 1e-7, axis=1)) < 1e-3
+    else:
+        # marble = 0.5 (1 + sin(scale z + 10 turb)): f32 evaluation of a 7-octave sum feeding a sine of slope 10
+        err = np.abs(ga - gb).max(1)
+        assert np.percentile(err, 99.9) <= 2 * REL and err.max() <= 1e-4, (np.percentile(err, 99.9), err.max())
+
+
+# --------------------------------------------------------------------------------------------- whole paths
+PATH_BARS = dict(random_scene=0.995, two_spheres=0.995, two_perlin_spheres=0.995, earth=0.999, simple_light=0.995,
+                 cornell_box=0.98, cornell_box_smoke=0.97, final_scene=0.90)
+
+
+@pytest.mark.parametrize("name", list(PATH_BARS))
+def test_paths_match_oracle_and_golden(pkg, gpu, orc, name):
+    """ray_color (src/main.rs:19-38) end to end, path by path with shared Philox keys: same number of segments and
+    radiance within 1e-3 relative for at least PATH_BARS of the paths (f32 vs f64 can only diverge at discrete
+    decisions: rejection-loop acceptance, Schlick test, grazing hits, checker cell), equal means."""
+    a, b, spec = build_both(pkg, gpu, orc, name)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_paths_v1.npz"))
+    W, H = int(g["size"][0]), int(g["size"][1])
+    p = pkg.make_params(W, H, 64, background=spec.background, seed=int(g["seed"]))
+    ra, sa = a.trace_paths(spec.camera(gpu, W, H), p, g["px"], g["py"], g["sample"])
+    rb, sb = g[name + "_rgb"], g[name + "_seg"]
+    good = (sa == sb) & (np.abs(ra - rb).max(1) <= 1e-3 * np.maximum(1.0, np.abs(rb).max(1)))
+    assert good.mean() >= PATH_BARS[name], good.mean()
+    # a bigger live sample
+    rs = np.random.RandomState(12)
+    n = 60000
+    px, py, sm = rs.randint(0, W, n), rs.randint(0, H, n), rs.randint(0, 4096, n)
+    ra, sa = a.trace_paths(spec.camera(gpu, W, H), p, px, py, sm)
+    rb, sb = b.trace_paths(spec.camera(orc, W, H), p, px, py, sm)
+    good = (sa == sb) & (np.abs(ra - rb).max(1) <= 1e-3 * np.maximum(1.0, np.abs(rb).max(1)))
+    assert good.mean() >= PATH_BARS[name], good.mean()
+    assert np.isfinite(ra).all()
+    se = rb.std(0) / math.sqrt(n) * math.sqrt(2 * (1 - good.mean()) + 1e-6)   # only unmatched paths contribute noise
+    assert (np.abs(ra.mean(0) - rb.mean(0)) <= 5 * se + 1e-5).all(), (ra.mean(0), rb.mean(0), se)
+    assert abs(sa.mean() - sb.mean()) < 0.02 * sb.mean()
+
+
+# --------------------------------------------------------------------------------------------- full renders
+def _psnr(a, b):
+    mse = np.mean((a - b) ** 2)
+    return 99.0 if mse == 0 else 10 * math.log10(1.0 / mse)
+
+
+def _display(sum_, spp):
+    return np.clip(np.sqrt(np.clip(sum_ / spp, 0, None)), 0, 0.999)      # write_color without the quantisation
+
+
+@pytest.mark.parametrize("name,W,H", [("random_scene", 48, 32), ("two_perlin_spheres", 48, 27), ("earth", 48, 27),
+                                      ("simple_light", 32, 32), ("cornell_box", 32, 32), ("cornell_box_smoke", 24, 24),
+                                      ("final_scene", 32, 32)])
+def test_render_psnr_4096spp(pkg, gpu, orc, name, W, H):
+    """North-star render bar: at 4096 spp and equal Philox keys the megakernel's image is within PSNR >= 40 dB of the
+    oracle's, and per-pixel means within 3 sigma (sigma^2 = (s_ref^2 + s_gpu^2)/n, s_gpu ~ s_ref)."""
+    spp = 4096
+    a, b, spec = build_both(pkg, gpu, orc, name)
+    p = pkg.make_params(W, H, spp, background=spec.background, seed=5)
+    img, st = a.render(spec.camera(gpu, W, H), p)
+    ref = b.render_oracle(spec.camera(orc, W, H), p, threads=0, sumsq=True)
+    assert st["paths"] == W * H * spp and np.isfinite(img).all()
+    psnr = _psnr(_display(img.astype(np.float64), spp), _display(ref["sum"], spp))
+    assert psnr >= 40.0, psnr
+    mean_ref = ref["sum"] / spp
+    var = np.maximum(ref["sumsq"] / spp - mean_ref ** 2, 0)
+    sigma = np.sqrt(2 * var / spp)
+    out = np.abs(img / spp - mean_ref) > 3 * sigma + 1e-6
+    assert out.mean() <= 0.005, out.mean()
+
+
+@pytest.mark.parametrize("name,W,H,spp", [("random_scene", 60, 40, 256), ("cornell_box", 40, 40, 512), ("final_scene", 32, 32, 512)])
+def test_render_unbiased_vs_independent_oracle(pkg, gpu, orc, name, W, H, spp):
+    """Same test with INDEPENDENT noise (different seeds): catches a bias that common random numbers would hide."""
+    a, b, spec = build_both(pkg, gpu, orc, name)
+    img, _ = a.render(spec.camera(gpu, W, H), pkg.make_params(W, H, spp, background=spec.background, seed=101))
+    ref = b.render_oracle(spec.camera(orc, W, H), pkg.make_params(W, H, spp, background=spec.background, seed=202), threads=0, sumsq=True)
+    mean_ref = ref["sum"] / spp
+    var = np.maximum(ref["sumsq"] / spp - mean_ref ** 2, 0)
+    sigma = np.sqrt(2 * var / spp)
+    z = (img / spp - mean_ref) / (sigma + 1e-4)
+    assert np.mean(np.abs(z) > 3) <= 0.02, np.mean(np.abs(z) > 3)       # heavy-tailed pixels (fireflies) inflate 0.27 %
+    tot_sigma = math.sqrt((2 * var / spp).sum()) / var.size
+    assert abs((img / spp).mean() - mean_ref.mean()) <= 4 * tot_sigma + 1e-4
+
+
+def test_render_is_partition_invariant_full_size(pkg, gpu):
+    """BASELINE config 1 at full size (1200x800, 500 spp, depth 50).  Size-independent property: the per-pixel sum
+    is the sum of deterministic per-(pixel, sample) path values, so ANY split of the samples into work units —
+    direct stores (one unit per tile) or atomically accumulated chunks — gives the same image up to f32 summation
+    order; and a second seed gives a statistically equal but different image."""
+    sc, spec = pkg.scenes.build(gpu, "random_scene")
+    sc.commit(1, 0)
+    cam = spec.camera(gpu, 1200, 800)
+    imgs = []
+    for spu in (500, 0, 64):
+        img, st = sc.render(cam, pkg.make_params(1200, 800, 500, background=spec.background, seed=1, samples_per_unit=spu))
+        assert st["paths"] == 480_000_000 and st["rays"] > st["paths"] and np.isfinite(img).all()
+        if spu:
+            assert sum(st["units_per_device"]) == 150 * 200 * math.ceil(500 / spu)
+        imgs.append(img)
+    for other in imgs[1:]:
+        assert np.abs(other - imgs[0]).max() <= 2e-4 * np.abs(imgs[0]).max()
+    assert imgs[0].min() >= 0 and imgs[0].max() <= 500.0 + 1e-3           # radiance <= 1 in this scene
+    sky = imgs[0][:40].reshape(-1, 3) / 500                               # top rows: mostly sky (0.7, 0.8, 1.0)
+    assert np.allclose(np.median(sky, 0), [0.7, 0.8, 1.0], atol=1e-3)
+    img2, _ = sc.render(cam, pkg.make_params(1200, 800, 500, background=spec.background, seed=2))
+    assert not np.array_equal(img2, imgs[0]) and abs(img2.mean() - imgs[0].mean()) < 2e-3 * imgs[0].mean()
+
+
+@pytest.mark.parametrize("name,W,H,spp", [("two_spheres", 800, 450, 200), ("two_perlin_spheres", 800, 450, 200), ("earth", 800, 450, 200),
+                                          ("simple_light", 600, 600, 200), ("cornell_box", 600, 600, 200), ("final_scene", 800, 800, 64)])
+def test_full_resolution_configs(pkg, gpu, orc, name, W, H, spp):
+    """BASELINE configs 2-4 at full resolution (reduced spp for C3/C4 to bound the test): finite, partition-invariant,
+    and the box-downsampled image agrees with an oracle render of the same scene at 1/10 resolution within MC noise."""
+    a, b, spec = build_both(pkg, gpu, orc, name)
+    cam = spec.camera(gpu, W, H)
+    img, st = a.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=3))
+    img2, _ = a.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=3, samples_per_unit=spp))
+    assert np.isfinite(img).all() and st["paths"] == W * H * spp
+    assert np.abs(img - img2).max() <= 2e-4 * max(np.abs(img).max(), 1.0)
+    f = 10
+    w, h = W // f, H // f
+    small = img[:h * f, :w * f].reshape(h, f, w, f, 3).mean((1, 3)) / spp
+    ospp = 256
+    ref = b.render_oracle(spec.camera(orc, w, h), pkg.make_params(w, h, ospp, background=spec.background, seed=9), threads=0)
+    refm = ref["sum"] / ospp
+    # same radiance field sampled on two pixel grids: compare the image means and a coarse 4x4 block average
+    assert abs(small.mean() - refm.mean()) <= 0.03 * refm.mean() + 2e-3
+    bh, bw = h // 4, w // 4
+    blk = lambda x: x[:bh * 4, :bw * 4].reshape(4, bh, 4, bw, 3).mean((1, 3))
+    assert np.abs(blk(small) - blk(refm)).max() <= 0.12 * max(blk(refm).max(), 0.05)
+
+
+def test_render_edge_cases(pkg, gpu, orc):
+    # empty world: every sample returns the background (src/main.rs:37)
+    sc = pkg.Scene(gpu)
+    sc.commit(1, 0)
+    cam = gpu.camera_new((0, 0, 5), (0, 0, 0), (0, 1, 0), 40.0, 37 / 23, 0.1, 5.0)
+    img, st = sc.render(cam, pkg.make_params(37, 23, 7, background=(0.25, 0.5, 0.75)))        # ragged tiles, odd spp
+    assert np.allclose(img, np.array([0.25, 0.5, 0.75]) * 7, rtol=1e-6) and st["rays"] == 37 * 23 * 7
+    # depth 0: black; depth 1: only directly visible emitters / background
+    a, b, spec = build_both(pkg, gpu, orc, "simple_light")
+    camg, camo = spec.camera(gpu, 33, 17), spec.camera(orc, 33, 17)
+    img, _ = a.render(camg, pkg.make_params(33, 17, 3, max_depth=0, background=(0.1, 0.1, 0.1)))
+    assert (img == 0).all()
+    for depth in (1, 2):
+        p = pkg.make_params(33, 17, 16, max_depth=depth, background=(0.1, 0.2, 0.3), seed=4)
+        img, _ = a.render(camg, p)
+        ref = b.render_oracle(camo, p, threads=0)
+        assert np.abs(img - ref["sum"]).max() <= 1e-3 * max(ref["sum"].max(), 1) + 0.35    # a handful of diverged paths at most
+        assert abs(img.mean() - ref["sum"].mean()) <= 0.01 * ref["sum"].mean() + 1e-3
+    # minimum size, spp = 1
+    img, st = a.render(spec.camera(gpu, 2, 2), pkg.make_params(2, 2, 1, background=(0, 0, 0)))
+    assert img.shape == (2, 2, 3) and st["paths"] == 4
+    with pytest.raises(pkg.RtwError):
+        a.render(camg, pkg.make_params(1, 1, 1))
+    # editing the scene after commit must be re-committed
+    a.push(a.sphere(1, (0, 0, 0), 1.0))
+    with pytest.raises(pkg.RtwError) as e:
+        a.render(camg, pkg.make_params(8, 8, 1))
+    assert e.value.code == -6
+
+
+def test_write_color_bit_exact(pkg, gpu, orc):
+    """write_color (src/math.rs:119-132): gamma 2, clamp, *256 truncation — byte-exact against the oracle."""
+    import ctypes as C
+    a, spec = pkg.scenes.build(gpu, "random_scene")
+    a.commit(1, 0)
+    spp = 10
+    img, _ = a.render(spec.camera(gpu, 200, 120), pkg.make_params(200, 120, spp, background=spec.background))
+    img[0, 0] = [np.nan, -1.0, 1e9]
+    n = img.shape[0] * img.shape[1]
+    out_g = np.zeros(n * 3, np.uint8); out_o = np.zeros(n * 3, np.uint8)
+    gpu.check(gpu.f("write_color")(img.ctypes.data_as(C.POINTER(C.c_float)), n, spp, out_g.ctypes.data_as(C.POINTER(C.c_uint8))))
+    d = img.astype(np.float64)
+    orc.f("write_color")(d.ctypes.data_as(C.POINTER(C.c_double)), n, spp, out_o.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert np.array_equal(out_g, out_o) and list(out_g[:3]) == [0, 0, 255]
+
+
+def test_two_gpus_in_process(pkg, gpu):
+    """Tiles from ONE atomic counter shared by both GPUs, finished tiles added into GPU 0's framebuffer over NVLink."""
+    if gpu.f("device_count")() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc, spec = pkg.scenes.build(gpu, "random_scene")
+    sc.commit(2, 0)
+    cam = spec.camera(gpu, 600, 400)
+    one, st1 = sc.render(cam, pkg.make_params(600, 400, 64, background=spec.background, n_gpus=1))
+    two, st2 = sc.render(cam, pkg.make_params(600, 400, 64, background=spec.background, n_gpus=2))
+    assert st2["n_devices"] == 2 and min(st2["units_per_device"][:2]) > 0.2 * sum(st2["units_per_device"])
+    assert np.abs(one - two).max() <= 2e-4 * one.max()

@@ -1,0 +1,157 @@
+"""Host-side logic and the C-ABI surface (no GPU needed): the library loads, exports every symbol declared in
+include/rtw.h, rejects bad input with status codes instead of panicking, flattens the reference's compositions,
+and fails loudly — never falls back to a CPU path — when asked to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported(rtw):
+    hdr = open(os.path.join(ROOT, "include", "rtw.h")).read()
+    names = sorted(set(re.findall(r"\b(rtw_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(rtw.dll, n)]
+    assert not missing, missing
+
+
+def test_product_does_not_link_or_load_the_oracle(rtw):
+    import subprocess
+    out = subprocess.run(["ldd", rtw.path], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    syms = subprocess.run(["nm", "-D", "--defined-only", rtw.path], capture_output=True, text=True).stdout
+    assert "orc_" not in syms
+    # no product source includes, links or dlopens anything under oracle/
+    pkg_dir = os.path.join(ROOT, "rust-ray-tracing-in-a-weekend_b200")
+    for base, _, files in os.walk(os.path.join(pkg_dir, "csrc")):
+        for f in files:
+            src = open(os.path.join(base, f), errors="ignore").read()
+            assert "oracle/" not in src and "liboracle" not in src and "orc_" not in src, f
+
+
+def test_struct_layouts(pkg):
+    assert C.sizeof(pkg.api.Camera) == 24 * 8
+    assert C.sizeof(pkg.api.RenderParams) == 16 + 24 + 8 + 8 + 16
+    assert C.sizeof(pkg.api.Stats) == 3 * 8 + 2 * 8 + 8 * 8 + 2 * 4 + 2 * 8 + 4 * 4
+
+
+def test_status_codes_instead_of_panics(pkg, rtw):
+    sc = pkg.Scene(rtw)
+    with pytest.raises(pkg.RtwError) as e:
+        sc.sphere(1, (0, 0, 0), 1.0)              # no material registered: reference would index out of range (main.rs:26)
+    assert e.value.code == -1
+    with pytest.raises(pkg.RtwError):
+        sc.lambertian(3)                           # unknown texture id
+    m = sc.lambertian(sc.tex_solid((1, 1, 1)))
+    assert m == 1                                  # 1-based handle like World::register_material (main.rs:46-49)
+    assert sc.metal((1, 1, 1), 0.1) == 2
+    with pytest.raises(pkg.RtwError):
+        sc.translate(99, (0, 0, 0))
+    with pytest.raises(pkg.RtwError):
+        sc.push(1234)
+    with pytest.raises(pkg.RtwError):
+        sc.tex_noise(np.zeros((256, 3)), np.full(256, 300), np.zeros(256), np.zeros(256), 1.0)
+    assert rtw.f("last_error")()
+
+
+def test_unsupported_nesting_is_reported(pkg, rtw):
+    sc = pkg.Scene(rtw)
+    m = sc.lambertian(sc.tex_solid((1, 1, 1)))
+    iso = sc.isotropic(sc.tex_solid((1, 1, 1)))
+    h = sc.sphere(m, (0, 0, 0), 1)
+    for _ in range(5):
+        h = sc.rotate_y(10, sc.translate(h, (1, 0, 0)))
+    sc.push(h)
+    with pytest.raises(pkg.RtwError) as e:
+        sc.debug_flatten()
+    assert e.value.code == -2
+    sc2 = pkg.Scene(rtw)
+    m = sc2.lambertian(sc2.tex_solid((1, 1, 1)))
+    iso = sc2.isotropic(sc2.tex_solid((1, 1, 1)))
+    med = sc2.constant_medium(sc2.sphere(m, (0, 0, 0), 1), 0.1, iso)
+    sc2.push(sc2.translate(med, (1, 0, 0)))
+    with pytest.raises(pkg.RtwError) as e:
+        sc2.debug_flatten()
+    assert e.value.code == -2
+    sc3 = pkg.Scene(rtw)
+    m = sc3.lambertian(sc3.tex_solid((1, 1, 1)))
+    iso = sc3.isotropic(sc3.tex_solid((1, 1, 1)))
+    sc3.push(sc3.constant_medium(sc3.constant_medium(sc3.sphere(m, (0, 0, 0), 1), 0.1, iso), 0.1, iso))
+    with pytest.raises(pkg.RtwError) as e:
+        sc3.debug_flatten()
+    assert e.value.code == -2
+
+
+@pytest.mark.parametrize("name,prims,media,xforms", [
+    ("random_scene", None, 0, 1), ("two_spheres", 2, 0, 1), ("two_perlin_spheres", 2, 0, 1), ("earth", 1, 0, 1),
+    ("simple_light", 3, 0, 1), ("cornell_box", 18, 0, 3), ("cornell_box_smoke", 18, 2, 3),
+    ("final_scene", 400 * 6 + 1 + 1 + 2 + 1 + 2 + 1000 + 2, 2, 2)])
+def test_flatten_reference_compositions(pkg, rtw, name, prims, media, xforms):
+    sc, spec = pkg.scenes.build(rtw, name)
+    d = sc.debug_flatten()                 # also runs the structural BVH validation
+    if prims is not None:
+        assert d["prims"] == prims
+    else:
+        assert d["prims"] == 1 + sum(spec.info.values()) + 3
+    assert d["media"] == media and d["xforms"] == xforms and d["depth"] <= 60
+    assert d["bvh_prims"] <= d["prims"] and d["nodes"] >= 1
+
+
+def test_scene_generators_are_seeded_and_shared(pkg, rtw, orc):
+    a, sa = pkg.scenes.build(rtw, "random_scene", seed=1)
+    b, sb = pkg.scenes.build(orc, "random_scene", seed=1)
+    c, sc_ = pkg.scenes.build(rtw, "random_scene", seed=2)
+    assert sa.info == sb.info and a.world == b.world and sa.info != sc_.info
+    vals = [pkg.scenes.HostRng(1).random_double() for _ in range(2)]
+    assert vals[0] == vals[1] and 0 <= vals[0] < 1
+    # SplitMix64 known answer: seed 0 -> first output 0xE220A8397B1DCDAF
+    assert pkg.scenes.HostRng(0).random_double() == (0xE220A8397B1DCDAF >> 11) / 2.0 ** 53
+
+
+def test_empty_world_and_single_prim_flatten(pkg, rtw):
+    sc = pkg.Scene(rtw)
+    d = sc.debug_flatten()
+    assert d["prims"] == 0 and d["nodes"] == 1
+    m = sc.lambertian(sc.tex_solid((1, 1, 1)))
+    sc.push(sc.sphere(m, (0, 0, 0), 1))
+    d = sc.debug_flatten()
+    assert d["prims"] == 1 and d["nodes"] == 1
+
+
+def test_no_cpu_fallback(pkg, rtw):
+    """Without a device every compute entry point must fail with NO_DEVICE — never compute on the host."""
+    if rtw.f("device_count")() > 0:
+        pytest.skip("a CUDA device is present")
+    sc, spec = pkg.scenes.build(rtw, "two_spheres")
+    with pytest.raises(pkg.RtwError) as e:
+        sc.commit(1, 0)
+    assert e.value.code == -5
+    with pytest.raises(pkg.RtwError) as e:
+        rtw.philox([0, 0, 0, 0], [0, 0])
+    assert e.value.code == -5
+    p = pkg.make_params(8, 8, 1)
+    with pytest.raises(pkg.RtwError) as e:
+        sc.render(spec.camera(rtw, 8, 8), p)
+    assert e.value.code == -6          # not committed
+    with pytest.raises(pkg.RtwError) as e:
+        sc.test_hit(-1, [[0, 0, 0]], [[0, 0, 1]])
+    assert e.value.code in (-5, -6)
+
+
+def test_golden_fixture_matches_oracle(pkg, orc):
+    """tests/golden/oracle_paths_v1.npz (made by tools/make_golden.py from THIS oracle) pins the restatement against
+    accidental edits: same scenes, same Philox keys, bit-identical radiance."""
+    path = os.path.join(ROOT, "tests", "golden", "oracle_paths_v1.npz")
+    g = np.load(path)
+    for name in pkg.scenes.SCENES:
+        sc, spec = pkg.scenes.build(orc, name, wrap_bvh=name not in ("cornell_box_smoke", "final_scene"))
+        sc.set_media_deferred(True)
+        W, H = int(g["size"][0]), int(g["size"][1])
+        p = pkg.make_params(W, H, 64, background=spec.background, seed=int(g["seed"]))
+        rgb, seg = sc.trace_paths(spec.camera(orc, W, H), p, g["px"], g["py"], g["sample"])
+        assert np.array_equal(seg, g[name + "_seg"]), name
+        assert np.allclose(rgb, g[name + "_rgb"], rtol=1e-12, atol=1e-14), name
