@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
-RTW_LIB_PATH = os.path.join(_HERE, "librtw.so")
+RTW_LIB_PATH = os.environ.get("RTW_LIB_PATH") or os.path.join(_HERE, "librtw.so")   # override: kernel experiments only
 ORACLE_LIB_PATH = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 RTW_IPC_HANDLE_BYTES = 160

@@ -23,10 +23,13 @@ using namespace rtwd;
 // =================================================================================================
 // kernels
 // =================================================================================================
-#define RTW_BLOCK 256
+#define RTW_BLOCK 128
 #define RTW_WARPS (RTW_BLOCK / 32)
+#ifndef RTW_MIN_BLOCKS
+#define RTW_MIN_BLOCKS 6
+#endif
 
-__global__ void __launch_bounds__(RTW_BLOCK, 2)
+__global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
 render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
     __shared__ float acc[RTW_WARPS][96];
@@ -577,32 +580,40 @@ int rtw_scene_commit(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     int rc = rtw::flatten(s->g, s->g.world, s->flat, err);
     if (rc) return fail(rc, err);
     Packed pk; pack(s->flat, pk);
-    free_replicas(s);
-    s->reps.resize(n_gpus);
+    // replicas (stream, events, grid size, blob allocation) are reused across commits on the same devices:
+    // a re-commit is then one flatten + one H2D copy per GPU
+    bool reuse = (int)s->reps.size() == n_gpus;
+    for (int i = 0; reuse && i < n_gpus; ++i) reuse = s->reps[i].device == first_device + i;
+    if (!reuse) { free_replicas(s); s->reps.resize(n_gpus); }
     s->h2d_commit = 0;
     for (int i = 0; i < n_gpus; ++i) {
         Replica& r = s->reps[i];
-        r.device = first_device + i;
-        CUDA_TRY(cudaSetDevice(r.device));
-        CUDA_TRY(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreate(&r.ev0)); CUDA_TRY(cudaEventCreate(&r.ev1));
-        CUDA_TRY(cudaMalloc(&r.blob, pk.bytes.size())); r.blob_bytes = pk.bytes.size();
-        CUDA_TRY(cudaMalloc(&r.stats, 16));
+        CUDA_TRY(cudaSetDevice(first_device + i));
+        if (!reuse) {
+            r.device = first_device + i;
+            CUDA_TRY(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreate(&r.ev0)); CUDA_TRY(cudaEventCreate(&r.ev1));
+            CUDA_TRY(cudaMalloc(&r.stats, 16));
+            int sms = 0, per_sm = 0;
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, RTW_BLOCK, 0));
+            if (per_sm < 1) per_sm = 1;
+            r.grid = sms * per_sm;
+            if (i > 0) {   // peers write the framebuffer / counter that live on the first device
+                int can = 0; CUDA_TRY(cudaDeviceCanAccessPeer(&can, r.device, first_device));
+                if (!can) return fail(RTW_ERR_CUDA, "peer access to the first device is not available");
+                cudaError_t e = cudaDeviceEnablePeerAccess(first_device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RTW_ERR_CUDA, cudaGetErrorString(e));
+                cudaGetLastError();
+            }
+        }
+        if (r.blob_bytes < pk.bytes.size()) {
+            if (r.blob) { CUDA_TRY(cudaFree(r.blob)); r.blob = nullptr; }
+            CUDA_TRY(cudaMalloc(&r.blob, pk.bytes.size())); r.blob_bytes = pk.bytes.size();
+        }
         CUDA_TRY(cudaMemcpyAsync(r.blob, pk.bytes.data(), pk.bytes.size(), cudaMemcpyHostToDevice, r.stream));
         s->h2d_commit += pk.bytes.size();
         r.ds = bind(s->flat, pk, r.blob);
-        cudaDeviceProp prop; CUDA_TRY(cudaGetDeviceProperties(&prop, r.device));
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, RTW_BLOCK, 0));
-        if (per_sm < 1) per_sm = 1;
-        r.grid = prop.multiProcessorCount * per_sm;
-        if (i > 0) {   // peers write the framebuffer / counter that live on the first device
-            int can = 0; CUDA_TRY(cudaDeviceCanAccessPeer(&can, r.device, first_device));
-            if (!can) return fail(RTW_ERR_CUDA, "peer access to the first device is not available");
-            cudaError_t e = cudaDeviceEnablePeerAccess(first_device, 0);
-            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(RTW_ERR_CUDA, cudaGetErrorString(e));
-            cudaGetLastError();
-        }
     }
     for (Replica& r : s->reps) { CUDA_TRY(cudaSetDevice(r.device)); CUDA_TRY(cudaStreamSynchronize(r.stream)); }
     s->committed = true;

@@ -40,7 +40,9 @@ RTW_DEV V3 refract(V3 uv, V3 n, float etai_over_etat) {                         
 }
 RTW_DEV bool near_zero(V3 v) { const float S = 1e-8f; return fabsf(v.x) < S && fabsf(v.y) < S && fabsf(v.z) < S; }  // :134-137
 RTW_DEV void sphere_uv(V3 p, float& u, float& v) {                                           // :288-300
-    float theta = acosf(-p.y);
+    // theta = acos(-p.y) evaluated as atan2(|(x,z)|, -y): identical for a unit vector, but keeps full relative
+    // precision at the poles where acos of an f32 within 1 ulp of +-1 loses everything
+    float theta = atan2f(sqrtf(p.x * p.x + p.z * p.z), -p.y);
     float phi = atan2f(-p.z, p.x) + RTW_PI_F;
     u = phi * (1.0f / (2.0f * RTW_PI_F));
     v = theta * (1.0f / RTW_PI_F);
@@ -197,11 +199,13 @@ struct HitRec {               // HitRecord :6-15
 struct TRay {
     V3 o, d; float time;
     double ox, oy, oz, dx, dy, dz, a;      // f64 copies for the sphere discriminant; a = |d|^2
+    float inv_a;                           // 1 / a
 };
 RTW_DEV TRay make_tray(const Ray& r) {
     TRay t; t.o = r.o; t.d = r.d; t.time = r.time;
     t.ox = r.o.x; t.oy = r.o.y; t.oz = r.o.z; t.dx = r.d.x; t.dy = r.d.y; t.dz = r.d.z;
     t.a = t.dx * t.dx + t.dy * t.dy + t.dz * t.dz;
+    t.inv_a = 1.0f / (float)t.a;
     return t;
 }
 
@@ -218,7 +222,9 @@ RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float time
 }
 
 // sphere_hit :254-288 — roots only.  oc, half_b, c and the discriminant in f64 (the reference's precision),
-// then the numerically stable root pair in f32.  Returns the accepted root or NaN.
+// then the numerically stable root pair in f32 (q = -(half_b + sign(half_b) sqrt(disc)); roots q/a and c/q).
+// Branch-free: a warp processes 32 different leaves, an early-out would only add divergence.
+// Returns the accepted root or NaN.
 RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi) {
     double cx, cy, cz, rad;
     load_prim_center(pp, type, r.time, cx, cy, cz, rad);
@@ -226,17 +232,16 @@ RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r,
     double half_b = ocx * r.dx + ocy * r.dy + ocz * r.dz;
     double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
     double disc = half_b * half_b - r.a * c;
-    if (disc < 0.0) return CUDART_NAN_F;
-    float sq = sqrtf((float)disc), hb = (float)half_b, a = (float)r.a, cf = (float)c;
-    float t_near, t_far;
-    if (hb < 0.0f) { float q = sq - hb; t_far = q / a; t_near = cf / q; }
-    else { float q = -hb - sq; t_near = q / a; t_far = cf / q; }
-    float root = t_near;                                                                   // :266-273
-    if (!(root >= t_lo && root <= t_hi)) {
-        root = t_far;
-        if (!(root >= t_lo && root <= t_hi)) return CUDART_NAN_F;
-    }
-    return root;
+    float discf = (float)disc, hb = (float)half_b, cf = (float)c;
+    float sq = sqrtf(fmaxf(discf, 0.0f));
+    bool neg = hb < 0.0f;
+    float q = neg ? sq - hb : -hb - sq;
+    float tq = q * r.inv_a, tc = __fdividef(cf, q);
+    float t_near = neg ? tc : tq, t_far = neg ? tq : tc;
+    bool near_ok = t_near >= t_lo && t_near <= t_hi;                                         // :266-273
+    float root = near_ok ? t_near : t_far;
+    bool ok = discf >= 0.0f && root >= t_lo && root <= t_hi;
+    return ok ? root : CUDART_NAN_F;
 }
 
 RTW_DEV void xform_ray(const DScene& sc, int xf, V3& o, V3& d) {                            // Translate :233, RotateY :390-394 (composed)
@@ -286,41 +291,50 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
 }
 
 #define RTW_STACK 64
+#define RTW_SENTINEL 0x7fffffff
 
 // Closest surface hit over the BVH (replaces hit_hittables :43-55 + bvh_node_hit :290-306 over the whole world).
+// "Speculative while-while" (Aila & Laine 2009): every lane keeps descending inner nodes until ALL lanes of the
+// warp hold a leaf (one leaf may be postponed per lane), then the warp intersects leaves together — node visits
+// and primitive tests each run with most lanes active instead of interleaving per lane.
 RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best) {
+    if (sc.n_bvh_prims == 0) return;
     V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     V3 oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
     int stack[RTW_STACK];
-    int sp = 0;
-    int node = 0;
-    if (sc.n_bvh_prims == 0) return;
-    for (;;) {
-        if (node >= 0) {
+    stack[0] = RTW_SENTINEL;
+    int sp = 1;
+    int node = 0, leaf = 0;                       // leaf >= 0: none postponed
+    while (node != RTW_SENTINEL) {
+        bool searching = true;
+        while (node >= 0 && node != RTW_SENTINEL) {
             const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
             float e0, e1;
             bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, t_min, t_best, e0);
             bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, t_min, t_best, e1);
-            if (h0 && h1) {
-                int nearc = n3.x, farc = n3.y;
-                if (e1 < e0) { nearc = n3.y; farc = n3.x; }
-                stack[sp++] = farc;
-                node = nearc;
-                continue;
+            if (!h0 && !h1) node = stack[--sp];
+            else {
+                node = h0 ? n3.x : n3.y;
+                if (h0 && h1) {
+                    int farc = n3.y;
+                    if (e1 < e0) { farc = node; node = n3.y; }
+                    stack[sp++] = farc;
+                }
             }
-            if (h0) { node = n3.x; continue; }
-            if (h1) { node = n3.y; continue; }
-        } else {
-            int code = ~node, first = code >> 3, count = (code & 7) + 1;
+            if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[--sp]; }   // postpone first leaf
+            if (!__any_sync(__activemask(), searching)) break;
+        }
+        while (leaf < 0) {
+            int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
             for (int i = 0; i < count; ++i) {
                 float t = prim_root(sc, first + i, r, t_min, t_best);
                 if (t == t) { t_best = t; prim_best = first + i; }       // not NaN: accepted, t <= t_best
             }
+            leaf = node;                                                  // a second leaf was reached meanwhile
+            if (node < 0) node = stack[--sp];
         }
-        if (sp == 0) break;
-        node = stack[--sp];
     }
 }
 
@@ -460,25 +474,20 @@ RTW_DEV V3 mat_color(const DScene& sc, const DMatRec& m, const HitRec& rec) {
 }
 
 // Returns true when a scattered ray exists.  `emitted` is always written.
+// Lambertian, Metal and Isotropic all start with the same unit-ball rejection loop (src/math.rs:51-58): it is
+// hoisted to ONE call site so the lanes of a warp run it — and the Philox blocks behind it — together.
 template <class R>
 RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const HitRec& rec, R& g, Ray& scattered, V3& attenuation, V3& emitted) {
     emitted = mk(0.f, 0.f, 0.f);
     scattered.o = rec.p; scattered.time = ray.time;
-    switch (m.kind) {
-    case MAT_LAMBERTIAN: {                                                                 // :36-48
-        V3 dir = rec.normal + random_unit_vector(g);
-        if (near_zero(dir)) dir = rec.normal;
-        scattered.d = dir;
-        attenuation = mat_color(sc, m, rec);
-        return true;
+    const int kind = m.kind;
+    if (kind == MAT_DIFFUSE_LIGHT) {                                                       // :20, :25-34 (both faces emit)
+        emitted = mat_color(sc, m, rec);
+        attenuation = mk(0.f, 0.f, 0.f);
+        scattered.d = mk(0.f, 0.f, 0.f);
+        return false;
     }
-    case MAT_METAL: {                                                                      // :50-60
-        V3 reflected = reflect(normalize(ray.d), rec.normal);
-        scattered.d = reflected + m.param * random_in_unit_sphere(g);
-        attenuation = mk(m.r, m.g, m.b);
-        return dot(scattered.d, rec.normal) > 0.0f;
-    }
-    case MAT_DIELECTRIC: {                                                                 // :62-82
+    if (kind == MAT_DIELECTRIC) {                                                          // :62-82
         attenuation = mk(1.f, 1.f, 1.f);
         float ratio = rec.front ? 1.0f / m.param : m.param;
         V3 unit_direction = normalize(ray.d);
@@ -491,15 +500,23 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
             scattered.d = refract(unit_direction, rec.normal, ratio);
         return true;
     }
-    case MAT_DIFFUSE_LIGHT:                                                                // :20, :25-34 (both faces emit)
-        emitted = mat_color(sc, m, rec);
-        attenuation = mk(0.f, 0.f, 0.f);
-        return false;
-    default:                                                                               // Isotropic :84-87
-        scattered.d = random_in_unit_sphere(g);
+    V3 ball = random_in_unit_sphere(g);                                                    // :37 / :52 / :85
+    if (kind == MAT_LAMBERTIAN) {                                                          // :36-48
+        V3 dir = rec.normal + normalize(ball);
+        if (near_zero(dir)) dir = rec.normal;
+        scattered.d = dir;
         attenuation = mat_color(sc, m, rec);
         return true;
     }
+    if (kind == MAT_METAL) {                                                               // :50-60
+        V3 reflected = reflect(normalize(ray.d), rec.normal);
+        scattered.d = reflected + m.param * ball;
+        attenuation = mk(m.r, m.g, m.b);
+        return dot(scattered.d, rec.normal) > 0.0f;
+    }
+    scattered.d = ball;                                                                    // Isotropic :84-87
+    attenuation = mat_color(sc, m, rec);
+    return true;
 }
 
 // ------------------------------------------------------------------------------------------------
