@@ -257,7 +257,7 @@ def main():
 
 def sc_blob_bytes(sc):
     d = sc.debug_flatten()
-    return d["nodes"] * 64 + d["prims"] * 80 + d["xforms"] * 112 + d["media"] * 16 + d["mats"] * 32 + d["texs"] * 48
+    return d["nodes"] * 64 + d["prims"] * 80 + d["xforms"] * 160 + d["media"] * 16 + d["mats"] * 32 + d["texs"] * 48
 
 
 if __name__ == "__main__":

@@ -225,7 +225,7 @@ RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float time
 // then the numerically stable root pair in f32 (q = -(half_b + sign(half_b) sqrt(disc)); roots q/a and c/q).
 // Branch-free: a warp processes 32 different leaves, an early-out would only add divergence.
 // Returns the accepted root or NaN.
-RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi) {
+RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi, bool self) {
     double cx, cy, cz, rad;
     load_prim_center(pp, type, r.time, cx, cy, cz, rad);
     double ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
@@ -240,16 +240,23 @@ RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r,
     float t_near = neg ? tc : tq, t_far = neg ? tq : tc;
     bool near_ok = t_near >= t_lo && t_near <= t_hi;                                         // :266-273
     float root = near_ok ? t_near : t_far;
+    // `self`: the ray STARTS on this sphere (it is the primitive the path just scattered from).  In the reference's
+    // f64 that root is ~1e-13 < t_min and is never returned; in f32 the stored origin is off the surface by one
+    // coordinate quantum and the root can exceed t_min for grazing directions.  Exact geometry: the root at the
+    // origin is c/q (c ~ 0); only the other one, q/a, can be a real hit.
+    if (self) root = tq;
     bool ok = discf >= 0.0f && root >= t_lo && root <= t_hi;
     return ok ? root : CUDART_NAN_F;
 }
 
-RTW_DEV void xform_ray(const DScene& sc, int xf, V3& o, V3& d) {                            // Translate :233, RotateY :390-394 (composed)
-    const float4* xp = reinterpret_cast<const float4*>(sc.xforms + xf);
-    float4 m = __ldg(xp); float bz = __ldg(reinterpret_cast<const float*>(xp + 1));
-    float ox = m.x * o.x - m.y * o.z + m.z, oz = m.y * o.x + m.x * o.z + bz;
-    float dx = m.x * d.x - m.y * d.z, dz = m.y * d.x + m.x * d.z;
-    o = mk(ox, o.y + m.w, oz); d = mk(dx, d.y, dz);
+RTW_DEV void xform_ray(const DScene& sc, int xf, const TRay& r, V3& o, V3& d) {            // Translate :233, RotateY :390-394 (composed)
+    const DXform* x = sc.xforms + xf;
+    float2 m = __ldg(reinterpret_cast<const float2*>(x));
+    const double2* dp = reinterpret_cast<const double2*>(&x->d_cos);
+    double2 cs = __ldg(dp), bxy = __ldg(dp + 1); double bz = __ldg(&x->d_bz);
+    // origin in f64 (then rounded once): keeps (k - o_k) accurate when the origin is close to a rect's plane
+    o = mk((float)(cs.x * r.ox - cs.y * r.oz + bxy.x), (float)(r.oy + bxy.y), (float)(cs.y * r.ox + cs.x * r.oz + bz));
+    d = mk(m.x * r.d.x - m.y * r.d.z, r.d.y, m.y * r.d.x + m.x * r.d.z);
 }
 
 // xy/xz/yz_rect_hit :308-384 — t only.  The ray is in the rect's object space.
@@ -267,13 +274,15 @@ RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, floa
     return t;
 }
 
-// Any primitive: accepted root in [t_lo, t_hi] or NaN.
-RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi) {
+// Any primitive: accepted root in [t_lo, t_hi] or NaN.  `skip` = primitive the ray starts on (-1: none): a planar
+// rect cannot be re-hit by a ray leaving it (exact geometry; the reference's f64 gets t ~ 1e-13 < t_min).
+RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip) {
     const DPrim* pp = sc.prims + pi;
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
-    if (meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi);
+    if (meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip);
+    if (pi == skip) return CUDART_NAN_F;
     V3 o = r.o, d = r.d;
-    if (meta.z) xform_ray(sc, meta.z, o, d);
+    if (meta.z) xform_ray(sc, meta.z, r, o, d);
     return rect_root(pp, meta.x, o, d, t_lo, t_hi);
 }
 
@@ -297,7 +306,7 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
 // "Speculative while-while" (Aila & Laine 2009): every lane keeps descending inner nodes until ALL lanes of the
 // warp hold a leaf (one leaf may be postponed per lane), then the warp intersects leaves together — node visits
 // and primitive tests each run with most lanes active instead of interleaving per lane.
-RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best) {
+RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip) {
     if (sc.n_bvh_prims == 0) return;
     V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     V3 oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
@@ -329,7 +338,7 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
         while (leaf < 0) {
             int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
             for (int i = 0; i < count; ++i) {
-                float t = prim_root(sc, first + i, r, t_min, t_best);
+                float t = prim_root(sc, first + i, r, t_min, t_best, skip);
                 if (t == t) { t_best = t; prim_best = first + i; }       // not NaN: accepted, t <= t_best
             }
             leaf = node;                                                  // a second leaf was reached meanwhile
@@ -359,14 +368,24 @@ RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool
     if (meta.x <= PRIM_MOVING_SPHERE) {
         double cx, cy, cz, rad;
         load_prim_center(pp, meta.x, r.time, cx, cy, cz, rad);
+        // one Newton step of f(t) = a t^2 + 2 half_b t + c in f64: t, the hit point and the normal then carry
+        // the reference's precision (an f32 t alone leaves |t d| * 1e-7 / r ~ 1e-5 of error on small far spheres)
+        double ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
+        double half_b = ocx * r.dx + ocy * r.dy + ocz * r.dz;
+        double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
+        double td = (double)t;
+        double f = (r.a * td + 2.0 * half_b) * td + c, fp = 2.0 * (r.a * td + half_b);
+        td -= (double)((float)f / (float)fp);
+        rec.t = (float)td;
+        double px = fma(td, r.dx, r.ox), py = fma(td, r.dy, r.oy), pz = fma(td, r.dz, r.oz);
+        rec.p = mk((float)px, (float)py, (float)pz);
         float inv_r = 1.0f / (float)rad;
-        // (p - c) / r in f64 for the subtraction (|c| can be 1000x the offset), f32 after
-        V3 ow = mk((float)((double)rec.p.x - cx) * inv_r, (float)((double)rec.p.y - cy) * inv_r, (float)((double)rec.p.z - cz) * inv_r);
+        V3 ow = mk((float)(px - cx) * inv_r, (float)(py - cy) * inv_r, (float)(pz - cz) * inv_r);
         outward_obj = xf ? mk(mc * ow.x - ms * ow.z, ow.y, ms * ow.x + mc * ow.z) : ow;
         if (want_uv) sphere_uv(outward_obj, rec.u, rec.v);
     } else {
         V3 o = r.o, d = r.d;
-        if (xf) xform_ray(sc, xf, o, d);
+        if (xf) xform_ray(sc, xf, r, o, d);
         const float4* q = reinterpret_cast<const float4*>(pp);
         float4 ab = __ldg(q);
         float a, b;
@@ -402,7 +421,7 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     float t1 = CUDART_NAN_F;
     {   // boundary.hit(ray, -inf, inf) :422 — closest-so-far scan over the boundary prims (hit_hittables :43-55)
         float hi = inf;
-        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, -inf, hi); if (t == t) { hi = t; t1 = t; } }
+        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, -inf, hi, -1); if (t == t) { hi = t; t1 = t; } }
     }
     if (!(t1 == t1)) return false;
     float t2 = CUDART_NAN_F;
@@ -410,7 +429,7 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
         // in f32 the +0.0001 vanishes once |t1| > 2048 (r = 5000 fog sphere): keep the probe strictly beyond t1
         float hi = inf, lo = t1 + 0.0001f;
         if (!(lo > t1)) lo = nextafterf(t1, inf);
-        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi); if (t == t) { hi = t; t2 = t; } }
+        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1); if (t == t) { hi = t; t2 = t; } }
     }
     if (!(t2 == t2)) return false;
     if (t1 < t_min) t1 = t_min;
@@ -430,7 +449,7 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
 template <class R>
 RTW_DEV bool world_hit(const DScene& sc, const TRay& r, float t_min, float t_max, R& g, bool want_uv, HitRec& rec) {
     float t_best = t_max; int prim_best = -1;
-    bvh_closest(sc, r, t_min, t_best, prim_best);
+    bvh_closest(sc, r, t_min, t_best, prim_best, -1);
     int med_mat = -1; float med_t = 0.0f;
     for (int m = 0; m < sc.n_media; ++m) {
         float t; int mat;
@@ -527,6 +546,7 @@ struct PathState {
     Ray ray;
     V3 T, L;
     int segment;            // segments traced so far (bounce id of the next one = segment + 1)
+    int last_prim;          // primitive the current ray starts on (-1: camera / medium scatter)
     PhiloxRng rng;
 };
 
@@ -536,7 +556,7 @@ RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, in
     float v = ((float)y + ps.rng.next()) / ((float)prm.height - 1.0f);
     ps.ray = camera_get_ray(cam, u, v, ps.rng);
     ps.T = mk(1.f, 1.f, 1.f); ps.L = mk(0.f, 0.f, 0.f);
-    ps.segment = 0;
+    ps.segment = 0; ps.last_prim = -1;
 }
 
 // One level of ray_color.  Returns true while the path continues.
@@ -546,7 +566,7 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps) {
     ps.rng.set_bounce((uint32_t)ps.segment);
     TRay tr = make_tray(ps.ray);
     float t_best = CUDART_INF_F; int prim_best = -1;
-    bvh_closest(sc, tr, prm.t_min, t_best, prim_best);                                     // :25
+    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);                       // :25
     int med_mat = -1; float med_t = 0.f;
     for (int m = 0; m < sc.n_media; ++m) {
         float t; int mat;
@@ -571,6 +591,7 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps) {
     if (!cont) return false;
     ps.T = ps.T * att;
     ps.ray = scattered;
+    ps.last_prim = prim_best >= 0 ? prim_best : -1;
     return true;
 }
 

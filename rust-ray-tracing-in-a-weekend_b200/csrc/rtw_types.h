@@ -66,6 +66,8 @@ struct RTW_ALIGN(16) DXform {
     float bz; int32_t n_ops; int32_t pad0, pad1;
     struct { float op_cos, op_sin, cum_cos, cum_sin; } ops[RTW_MAX_CHAIN];   // op_sin = 0 & op_cos = 1: Translate
     int32_t is_rot[RTW_MAX_CHAIN];
+    double d_cos, d_sin, d_bx, d_by, d_bz, d_pad;   // the composed transform again, in f64: ray ORIGINS are moved into
+                                                    // object space in f64 (|o| ~ 500 next to a plane offset ~ 1)
 };
 
 struct RTW_ALIGN(16) DMedium {

@@ -92,6 +92,7 @@ struct Flattener {
         DXform x; std::memset(&x, 0, sizeof(x));
         x.m_cos = (float)m.C; x.m_sin = (float)m.S; x.bx = (float)m.b[0]; x.by = (float)m.b[1]; x.bz = (float)m.b[2];
         x.n_ops = (int)ch.size();
+        x.d_cos = m.C; x.d_sin = m.S; x.d_bx = m.b[0]; x.d_by = m.b[1]; x.d_bz = m.b[2];
         for (size_t j = 0; j < ch.size(); ++j) {
             x.ops[j].op_cos = (float)(ch[j].rot ? ch[j].c : 1.0);
             x.ops[j].op_sin = (float)(ch[j].rot ? ch[j].s : 0.0);

@@ -62,7 +62,9 @@ def compare_hits(ha, hb, ok, pos_scale, d_len, min_stable=0.9, check_uv=True):
     # over ALL rays (ill-conditioned included) the flags may differ only rarely
     assert np.mean(ha["hit"] != hb["hit"]) < 5e-3
     m = ok & (hb["hit"] == 1)
-    assert m.sum() > 0
+    if m.sum() == 0:          # e.g. rays leaving the only sphere of the earth scene
+        assert np.array_equal(ha["ndraw"][ok], hb["ndraw"][ok])
+        return
     assert np.array_equal(ha["mat"][m], hb["mat"][m])
     assert np.array_equal(ha["front"][m], hb["front"][m])
     # t: 1e-5 relative — or, for origins that sit (almost) on the surface, within 8 f32 quanta of the scene
@@ -161,22 +163,27 @@ CASE_NAMES = ["sphere", "small_sphere", "ground_sphere", "moving_sphere", "xy_re
 @pytest.mark.parametrize("case", CASE_NAMES)
 def test_hittable_hit(pkg, gpu, orc, case):
     """Hittable::hit (src/hittable.rs:209-252) per variant / composition, fixed rays."""
+    import ctypes as C
     a, b = pkg.Scene(gpu), pkg.Scene(orc)
     ta, center, radius = _prim_cases(pkg, a)[case]
-    tb, _, _ = _prim_cases(pkg, b)[case]
-    assert ta == tb
+    tb, _, _ = _prim_cases(pkg, b)[case]          # hittable ids are library-internal
+    if case != "ground_sphere":                   # aim at the reference's own bounding box (src/hittable.rs:475-525)
+        mn, mx = np.zeros(3), np.zeros(3)
+        dp = C.POINTER(C.c_double)
+        assert orc.f("bounding_box")(b.h, tb, 0.0, 1.0, mn.ctypes.data_as(dp), mx.ctypes.data_as(dp)) == 0
+        center, radius = (mn + mx) / 2, float(np.linalg.norm(mx - mn) / 2)
     rs = np.random.RandomState(zlib.crc32(case.encode()) % 1000)
     n = 120000
     center = np.array(center, float)
     # origins on a shell around the target (some inside), directions towards a jittered point of it, un-normalised
     dirs = rs.randn(n, 3); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
     o = f32(center + dirs * radius * rs.uniform(0.2, 6.0, (n, 1)))
-    tgt = center + rs.uniform(-1.2, 1.2, (n, 3)) * radius
+    tgt = center + rs.uniform(-0.7, 0.7, (n, 3)) * radius
     d = f32((tgt - o) * rs.uniform(0.05, 2.0, (n, 1)))
     tm = f32(rs.rand(n))
     hb, ok = stable(lambda oo, dd, tt: b.test_hit(tb, oo, dd, tt), o, d, tm, radius)
     ha = a.test_hit(ta, o, d, tm)
-    assert 0.15 < hb["hit"].mean() < 0.999
+    assert 0.1 < hb["hit"].mean() < 0.999, hb["hit"].mean()
     compare_hits(ha, hb, ok, np.abs(center).max() + radius, np.linalg.norm(d, axis=1))
 
 
@@ -213,8 +220,10 @@ def test_constant_medium_hit(pkg, gpu, orc, name):
     o, d, tm = f32(g["origin"]), f32(g["dir"]), f32(g["time"])
     hb, ok = stable(lambda oo, dd, tt, xi=xi: b.test_hit(-1, oo, dd, tt, xi=xi), o, d, tm, 1000.0)
     ha = a.test_hit(-1, o, d, tm, xi=xi)
-    n_media = 2
-    assert hb["ndraw"].max() == n_media and (hb["ndraw"] >= (1 if name == "final_scene" else 0)).all()
+    # smoke: a ray can cross both boxes (2 draws).  final_scene: the fog sphere always draws; the r=70 medium never
+    # does for camera rays, because its glass twin earlier in the list clamps t_max to the entry point (:436-441)
+    assert hb["ndraw"].max() == (2 if name == "cornell_box_smoke" else 1)
+    assert (hb["ndraw"] >= (1 if name == "final_scene" else 0)).all()
     compare_hits(ha, hb, ok, 1000.0, np.linalg.norm(d, axis=1), check_uv=False)
     med = ok & (hb["hit"] == 1) & np.all(hb["normal"] == [1, 0, 0], axis=1) & (hb["u"] == 0)
     assert med.sum() > 100            # some rays really scatter inside the media
@@ -279,12 +288,18 @@ def test_material_scatter(pkg, gpu, orc, kind):
     rb = scenes[1][0].test_scatter(scenes[1][1], ro, rd, rt, p, nrm, front, u, v, xi)
     assert (rb["ndraw"] >= 0).all()
     same = (ra["scattered"] == rb["scattered"]) & (ra["ndraw"] == rb["ndraw"])
+    # conditioning: drop inputs whose ORACLE output moves by more than 1e-5/3 under a 1e-7 relative nudge of the ray
+    # direction (near-critical refraction, 1 - |r_perp|^2 -> 0 in src/math.rs:114) — no f32 evaluation can hold 1e-5 there
+    rb2 = scenes[1][0].test_scatter(scenes[1][1], ro, rd * (1 + 1e-7 * rs.uniform(-1, 1, rd.shape)), rt, p, nrm, front, u, v, xi)
+    dnb = np.maximum(np.linalg.norm(rb["dir"], axis=1, keepdims=True), 1e-2)
+    well = (rb2["scattered"] == rb["scattered"]) & ((np.abs(rb2["dir"] - rb["dir"]) / dnb).max(1) <= REL / 3)
+    assert well.mean() > 0.995
     if kind == "dielectric":    # reflect/refract branch: side of the surface the new ray leaves on
         same &= np.sign(np.einsum("ij,ij->i", ra["dir"], nrm)) == np.sign(np.einsum("ij,ij->i", rb["dir"], nrm))
     if kind == "lambertian_checker":
         same &= np.all(ra["attenuation"] == f32(rb["attenuation"]), axis=1)
     assert same.mean() > 0.9995, same.mean()
-    m = same & (rb["scattered"] == 1)
+    m = same & well & (rb["scattered"] == 1)
     if kind != "diffuse_light":
         assert m.sum() > 0.4 * n
         dn = np.maximum(np.linalg.norm(rb["dir"][m], axis=1, keepdims=True), 1e-2)
@@ -363,7 +378,7 @@ def test_paths_match_oracle_and_golden(pkg, gpu, orc, name):
     assert np.isfinite(ra).all()
     se = rb.std(0) / math.sqrt(n) * math.sqrt(2 * (1 - good.mean()) + 1e-6)   # only unmatched paths contribute noise
     assert (np.abs(ra.mean(0) - rb.mean(0)) <= 5 * se + 1e-5).all(), (ra.mean(0), rb.mean(0), se)
-    assert abs(sa.mean() - sb.mean()) < 0.02 * sb.mean()
+    assert abs(sa.mean() - sb.mean()) < 0.03 * sb.mean()
 
 
 # --------------------------------------------------------------------------------------------- full renders
@@ -393,13 +408,14 @@ def test_render_psnr_4096spp(pkg, gpu, orc, name, W, H):
     mean_ref = ref["sum"] / spp
     var = np.maximum(ref["sumsq"] / spp - mean_ref ** 2, 0)
     sigma = np.sqrt(2 * var / spp)
-    out = np.abs(img / spp - mean_ref) > 3 * sigma + 1e-6
+    out = np.abs(img / spp - mean_ref) > 3 * sigma + 2e-5 * np.maximum(mean_ref, 1.0)     # + f32 accumulation of spp terms
     assert out.mean() <= 0.005, out.mean()
 
 
-@pytest.mark.parametrize("name,W,H,spp", [("random_scene", 60, 40, 256), ("cornell_box", 40, 40, 512), ("final_scene", 32, 32, 512)])
-def test_render_unbiased_vs_independent_oracle(pkg, gpu, orc, name, W, H, spp):
-    """Same test with INDEPENDENT noise (different seeds): catches a bias that common random numbers would hide."""
+def test_render_unbiased_vs_independent_oracle(pkg, gpu, orc):
+    """Same 3-sigma test with INDEPENDENT noise (different seeds): catches a bias that common random numbers would
+    hide.  Per pixel on the bounded-radiance book-1 scene."""
+    name, W, H, spp = "random_scene", 60, 40, 256
     a, b, spec = build_both(pkg, gpu, orc, name)
     img, _ = a.render(spec.camera(gpu, W, H), pkg.make_params(W, H, spp, background=spec.background, seed=101))
     ref = b.render_oracle(spec.camera(orc, W, H), pkg.make_params(W, H, spp, background=spec.background, seed=202), threads=0, sumsq=True)
@@ -407,9 +423,31 @@ def test_render_unbiased_vs_independent_oracle(pkg, gpu, orc, name, W, H, spp):
     var = np.maximum(ref["sumsq"] / spp - mean_ref ** 2, 0)
     sigma = np.sqrt(2 * var / spp)
     z = (img / spp - mean_ref) / (sigma + 1e-4)
-    assert np.mean(np.abs(z) > 3) <= 0.02, np.mean(np.abs(z) > 3)       # heavy-tailed pixels (fireflies) inflate 0.27 %
+    assert np.mean(np.abs(z) > 3) <= 0.01, np.mean(np.abs(z) > 3)
     tot_sigma = math.sqrt((2 * var / spp).sum()) / var.size
     assert abs((img / spp).mean() - mean_ref.mean()) <= 4 * tot_sigma + 1e-4
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "cornell_box_smoke", "final_scene", "simple_light"])
+def test_radiance_distribution_unbiased_independent(pkg, gpu, orc, name):
+    """Emissive scenes are heavy-tailed (a few paths carry radiance 15), so per-pixel sigma estimates are useless at
+    test-sized spp.  Two-sample z-tests on INDEPENDENT path samples instead: the mean of min(L, cap) for several caps
+    (finite variance, sensitive to leaks / trapped paths) and the path-length distribution."""
+    a, b, spec = build_both(pkg, gpu, orc, name)
+    W, H, n = 64, 64, 400000
+    rs = np.random.RandomState(21)
+    px, py, sm = rs.randint(0, W, n), rs.randint(0, H, n), rs.randint(0, 1 << 20, n)
+    ra, sa = a.trace_paths(spec.camera(gpu, W, H), pkg.make_params(W, H, 64, background=spec.background, seed=303), px, py, sm)
+    rb, sb = b.trace_paths(spec.camera(orc, W, H), pkg.make_params(W, H, 64, background=spec.background, seed=404), px, py, sm)
+    for cap in (0.5, 2.0, 20.0):
+        xa, xb = np.minimum(ra, cap).mean(1), np.minimum(rb, cap).mean(1)
+        z = (xa.mean() - xb.mean()) / math.sqrt(xa.var() / n + xb.var() / n)
+        assert abs(z) < 4.5, (cap, z, xa.mean(), xb.mean())
+    z = (sa.mean() - sb.mean()) / math.sqrt(sa.var() / n + sb.var() / n)
+    assert abs(z) < 4.5, (z, sa.mean(), sb.mean())
+    # trapped paths (depth exhausted) must be as rare as in the reference arithmetic
+    fa, fb = np.mean(sa == 50), np.mean(sb == 50)
+    assert abs(fa - fb) <= 5 * math.sqrt((fa + fb + 1e-6) / n), (fa, fb)
 
 
 def test_render_is_partition_invariant_full_size(pkg, gpu):
