@@ -71,6 +71,8 @@ typedef struct rtw_render_params {
 } rtw_render_params;
 
 #define RTW_FLAG_DEVICE_OUT 1   /* out_rgb_sum is a device pointer on the first device (no D2H) */
+#define RTW_FLAG_KERNEL_MEGA 2  /* force the one-path-per-lane megakernel */
+#define RTW_FLAG_KERNEL_POOL 4  /* force the warp-pool (shared-memory wavefront) kernel; default: chosen by measurement */
 
 typedef struct rtw_stats {
     double ms_render;           /* CUDA-event time of the render kernels, max over devices */

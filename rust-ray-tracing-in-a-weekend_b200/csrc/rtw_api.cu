@@ -9,6 +9,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -16,6 +17,7 @@
 
 #include "../../include/rtw.h"
 #include "rtw_device.cuh"
+#include "rtw_pool.cuh"
 #include "scene_host.hpp"
 
 using namespace rtwd;
@@ -25,8 +27,14 @@ using namespace rtwd;
 // =================================================================================================
 #define RTW_BLOCK 128
 #define RTW_WARPS (RTW_BLOCK / 32)
+#ifndef RTW_DEFAULT_MODE
+#define RTW_DEFAULT_MODE 0
+#endif
+#ifndef RTW_DEFAULT_POOL_MODE
+#define RTW_DEFAULT_POOL_MODE 2
+#endif
 #ifndef RTW_MIN_BLOCKS
-#define RTW_MIN_BLOCKS 6
+#define RTW_MIN_BLOCKS 8
 #endif
 
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
@@ -69,11 +77,12 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
             if (!__any_sync(0xffffffffu, alive)) { if (next >= n_items) break; continue; }
             if (alive) {
                 ++rays;
-                if (!path_step(sc, prm, ps)) {
-                    atomicAdd(&acc[warp][pix * 3 + 0], ps.L.x);
-                    atomicAdd(&acc[warp][pix * 3 + 1], ps.L.y);
-                    atomicAdd(&acc[warp][pix * 3 + 2], ps.L.z);
-                    alive = false;
+                V3 add;
+                alive = path_step(sc, prm, ps, add);
+                if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
+                    atomicAdd(&acc[warp][pix * 3 + 0], add.x);
+                    atomicAdd(&acc[warp][pix * 3 + 1], add.y);
+                    atomicAdd(&acc[warp][pix * 3 + 2], add.z);
                 }
             }
         }
@@ -94,6 +103,87 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
     if (lane == 0) { atomicAdd(stats, rays); atomicAdd(stats + 1, units); }
 }
 
+// The warp-pool kernel (see rtw_pool.cuh): same work units, same Philox keys, same framebuffer protocol as
+// render_kernel — only the scheduling of the four stages differs.
+template <int POOL>
+__global__ void __launch_bounds__(RTW_BLOCK)
+render_pool_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
+                   unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(16) unsigned char pool_raw[];
+    PoolSmem<POOL>* pools = reinterpret_cast<PoolSmem<POOL>*>(pool_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    PoolSmem<POOL>& P = pools[warp];
+    unsigned long long rays = 0, units = 0;
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= prm.n_units) break;
+        ++units;
+        const int tile = (int)(unit / (unsigned)prm.chunks), chunk = (int)(unit % (unsigned)prm.chunks);
+        const int s0 = chunk * prm.chunk_spp;
+        const int s1 = min(prm.spp, s0 + prm.chunk_spp);
+        const int tile_x0 = (tile % prm.tiles_x) * 8, tile_y0 = (tile / prm.tiles_x) * 4;
+        const int tw = min(8, prm.width - tile_x0), th = min(4, prm.height - tile_y0), npix = tw * th;   // ragged edge tiles
+        const int n_items = prm.max_depth >= 1 ? npix * (s1 - s0) : 0;
+        for (int i = lane; i < POOL; i += 32) { P.meta[i] = POOL_FREE; P.freel[i] = (unsigned char)i; }
+        P.acc[lane] = 0.f; P.acc[lane + 32] = 0.f; P.acc[lane + 64] = 0.f;
+        if (lane < 8) P.cnt[lane] = lane == C_FREE ? POOL : 0;
+        __syncwarp();
+        int next_item = 0;
+        for (;;) {
+            // ---- regenerate: free slots <- camera rays (main.rs:517-520).  freel is a stack, trav a list.
+            const int n_free = P.cnt[C_FREE];
+            const int n_cont = P.cnt[C_TRAV];                  // paths continuing from the last shade stage
+            const int n_new = min(n_free, n_items - next_item);
+            __syncwarp();
+            for (int i = lane; i < n_new; i += 32) {
+                const int slot = P.freel[n_free - 1 - i];
+                const int idx = next_item + i, pl = idx % npix, sample = s0 + idx / npix;
+                const int px = pl % tw, py = pl / tw, pix = py * 8 + px;
+                PathState ps;
+                path_begin(cam, prm, tile_x0 + px, tile_y0 + py, sample, ps);
+                P.ox[slot] = ps.ray.o.x; P.oy[slot] = ps.ray.o.y; P.oz[slot] = ps.ray.o.z;
+                P.dx[slot] = ps.ray.d.x; P.dy[slot] = ps.ray.d.y; P.dz[slot] = ps.ray.d.z; P.tm[slot] = ps.ray.time;
+                P.tr[slot] = 1.f; P.tg[slot] = 1.f; P.tb[slot] = 1.f;
+                P.last[slot] = -1;
+                P.meta[slot] = meta_pack(pix, 1, 0, sample);
+                P.trav[n_cont + i] = (unsigned char)slot;
+            }
+            next_item += n_new;
+            const int n_trav = n_cont + n_new;
+            __syncwarp();
+            if (lane < 8) P.cnt[lane] = lane == C_FREE ? n_free - n_new : 0;
+            __syncwarp();
+            if (n_trav == 0) break;                            // nothing alive and nothing left to start
+            // ---- traverse (hittable.rs:43-55) + classify
+            rays += traverse_stage<POOL>(P, lane, lt_mask, n_trav, sc, prm, tile_x0, tile_y0);
+            __syncwarp();
+            // ---- shade, one dense loop per material kind (material.rs:15-94)
+            shade_list<POOL, K_MISS>(P, lane, sc, prm, tile_x0, tile_y0);
+            shade_list<POOL, K_LAMB>(P, lane, sc, prm, tile_x0, tile_y0);
+            shade_list<POOL, K_METAL>(P, lane, sc, prm, tile_x0, tile_y0);
+            shade_list<POOL, K_DIEL>(P, lane, sc, prm, tile_x0, tile_y0);
+            shade_list<POOL, K_LIGHT>(P, lane, sc, prm, tile_x0, tile_y0);
+            shade_list<POOL, K_ISO>(P, lane, sc, prm, tile_x0, tile_y0);
+            __syncwarp();
+        }
+        {   // tile -> framebuffer, row 0 = top (y = H-1 of src/main.rs:591)
+            const int x = tile_x0 + (lane & 7), y = tile_y0 + (lane >> 3);
+            if (x < prm.width && y < prm.height) {
+                float* dst = fb + ((size_t)(prm.height - 1 - y) * prm.width + x) * 3;
+                const float r = P.acc[lane * 3], g = P.acc[lane * 3 + 1], b = P.acc[lane * 3 + 2];
+                if (prm.accumulate) { atomicAdd_system(dst, r); atomicAdd_system(dst + 1, g); atomicAdd_system(dst + 2, b); }
+                else { dst[0] = r; dst[1] = g; dst[2] = b; }
+            }
+        }
+        __syncwarp();
+    }
+    for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0) { atomicAdd(stats, rays); atomicAdd(stats + 1, units); }
+}
+
 // per-path radiance with the render's Philox keys (parity hook rtw_trace_paths)
 __global__ void trace_paths_kernel(DScene sc, DCamera cam, DParams prm, int n, const int* __restrict__ px, const int* __restrict__ py,
                                    const int* __restrict__ smp, double* __restrict__ out_rgb, int* __restrict__ out_seg) {
@@ -101,8 +191,10 @@ __global__ void trace_paths_kernel(DScene sc, DCamera cam, DParams prm, int n, c
     if (i >= n) return;
     PathState ps;
     path_begin(cam, prm, px[i], py[i], smp[i], ps);
-    while (path_step(sc, prm, ps)) {}
-    out_rgb[3 * i] = ps.L.x; out_rgb[3 * i + 1] = ps.L.y; out_rgb[3 * i + 2] = ps.L.z;
+    V3 L = mk(0.f, 0.f, 0.f), add;
+    bool go = true;
+    while (go) { go = path_step(sc, prm, ps, add); L = L + add; }
+    out_rgb[3 * i] = L.x; out_rgb[3 * i + 1] = L.y; out_rgb[3 * i + 2] = L.z;
     out_seg[i] = ps.segment;
 }
 
@@ -214,6 +306,8 @@ int fail(int code, const std::string& m) { g_err = m; return code; }
                                            std::string(#x) + ": " + cudaGetErrorString(e_));        \
     } while (0)
 
+#define TRY(x) do { int rc_ = (x); if (rc_ < 0) return rc_; } while (0)
+
 struct Replica {
     int device = -1;
     uint8_t* blob = nullptr;
@@ -222,7 +316,9 @@ struct Replica {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* stats = nullptr;    // [0] rays [1] units
-    int grid = 0;
+    int grid = 0;                           // megakernel grid (also sizes the work units)
+    int pool_grid[4] = {0, 0, 0, 0};        // warp-pool kernel grids for POOL = 64/128/192/256 (lazy)
+    int sms = 0;
 };
 
 struct SharedFb {          // framebuffer + unit counter reachable by every GPU / rank
@@ -357,15 +453,57 @@ int ensure_fb(SharedFb& fb, int device, int w, int h) {
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// Launch the megakernel on replicas [0, n) against (counter, fb); sync; fill stats.
-int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp, unsigned int* counter, float* fb, rtw_stats* st) {
+// kernel choice: 0 = megakernel (one path per lane), 1..4 = warp-pool kernel with 64/128/192/256 slots per warp
+int kernel_mode(int flags) {
+    static int env_mode = -2;
+    if (env_mode == -2) {
+        env_mode = -1;
+        if (const char* e = getenv("RTW_KERNEL")) {
+            if (!strcmp(e, "mega")) env_mode = 0;
+            else if (!strcmp(e, "pool64")) env_mode = 1;
+            else if (!strcmp(e, "pool128")) env_mode = 2;
+            else if (!strcmp(e, "pool192")) env_mode = 3;
+            else if (!strcmp(e, "pool256")) env_mode = 4;
+        }
+    }
+    if (flags & RTW_FLAG_KERNEL_MEGA) return 0;
+    if (flags & RTW_FLAG_KERNEL_POOL) return RTW_DEFAULT_POOL_MODE;
+    if (env_mode >= 0) return env_mode;
+    return RTW_DEFAULT_MODE;
+}
+
+template <int POOL>
+int launch_pool(Replica& r, int slot, const DCamera& dc, const DParams& dp, unsigned int* counter, float* fb) {
+    const size_t smem = RTW_WARPS * sizeof(PoolSmem<POOL>);
+    if (!r.pool_grid[slot]) {
+        CUDA_TRY(cudaFuncSetAttribute(render_pool_kernel<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pool_kernel<POOL>, RTW_BLOCK, smem));
+        if (per_sm < 1) return fail(RTW_ERR_CUDA, "warp-pool kernel does not fit on an SM");
+        r.pool_grid[slot] = r.sms * per_sm;
+    }
+    render_pool_kernel<POOL><<<r.pool_grid[slot], RTW_BLOCK, smem, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats);
+    return 0;
+}
+
+// Launch the render kernel on replicas [0, n) against (counter, fb); sync; fill stats.
+int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp, unsigned int* counter, float* fb, rtw_stats* st, int mode) {
     DCamera dc = to_dcamera(*cam);
+    uint32_t rk[20];
+    for (int k = 0; k < 10; ++k) { rk[2 * k] = dp.seed_lo + 0x9E3779B9u * (uint32_t)k; rk[2 * k + 1] = dp.seed_hi + 0xBB67AE85u * (uint32_t)k; }
     for (int i = 0; i < n_rep; ++i) {
         Replica& r = s->reps[i];
         CUDA_TRY(cudaSetDevice(r.device));
+        CUDA_TRY(cudaMemcpyToSymbolAsync(c_philox_rk, rk, sizeof(rk), 0, cudaMemcpyHostToDevice, r.stream));
         CUDA_TRY(cudaMemsetAsync(r.stats, 0, 16, r.stream));
         CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
-        render_kernel<<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats);
+        switch (mode) {
+        case 1: TRY(launch_pool<64>(r, 0, dc, dp, counter, fb)); break;
+        case 2: TRY(launch_pool<128>(r, 1, dc, dp, counter, fb)); break;
+        case 3: TRY(launch_pool<192>(r, 2, dc, dp, counter, fb)); break;
+        case 4: TRY(launch_pool<256>(r, 3, dc, dp, counter, fb)); break;
+        default: render_kernel<<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats);
+        }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
     }
@@ -409,7 +547,6 @@ struct Scratch {
         return 0;
     }
 };
-#define TRY(x) do { int rc_ = (x); if (rc_ < 0) return rc_; } while (0)
 
 int need_device() {
     int n = 0;
@@ -598,7 +735,8 @@ int rtw_scene_commit(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, RTW_BLOCK, 0));
             if (per_sm < 1) per_sm = 1;
-            r.grid = sms * per_sm;
+            r.grid = sms * per_sm; r.sms = sms;
+            for (int k = 0; k < 4; ++k) r.pool_grid[k] = 0;
             if (i > 0) {   // peers write the framebuffer / counter that live on the first device
                 int can = 0; CUDA_TRY(cudaDeviceCanAccessPeer(&can, r.device, first_device));
                 if (!can) return fail(RTW_ERR_CUDA, "peer access to the first device is not available");
@@ -641,7 +779,7 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
     if (dp.accumulate) CUDA_TRY(cudaMemsetAsync(fb, 0, fb_bytes, r0.stream));
     if (n_rep > 1) CUDA_TRY(cudaStreamSynchronize(r0.stream));   // peers must see the zeroed buffers
-    TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, st));
+    TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, st, kernel_mode(p->flags)));
     if (!dev_out) {
         CUDA_TRY(cudaSetDevice(r0.device));
         CUDA_TRY(cudaMemcpy(out, fb, fb_bytes, cudaMemcpyDeviceToHost));
@@ -709,7 +847,7 @@ int rtw_render_shared(rtw_scene* s, const rtw_camera* cam, const rtw_render_para
     DParams dp; TRY(make_params(*p, world * s->reps[0].grid * RTW_WARPS, dp));
     dp.accumulate = 1;
     if (st) { std::memset(st, 0, sizeof(*st)); fill_scene_stats(s, st); }
-    TRY(launch_all(s, 1, cam, dp, s->shared.counter(), s->shared.fb(), st));
+    TRY(launch_all(s, 1, cam, dp, s->shared.counter(), s->shared.fb(), st, kernel_mode(p->flags)));
     if (st) { st->paths = (uint64_t)p->width * p->height * p->spp; st->ms_total = now_ms() - t0; }
     return RTW_OK;
 }
@@ -841,6 +979,9 @@ int rtw_trace_paths(rtw_scene* s, const rtw_camera* cam, const rtw_render_params
     TRY(need_device());
     View vw; TRY(make_view(s, -1, vw));
     DParams dp; TRY(make_params(*p, 1, dp));
+    uint32_t rk[20];
+    for (int k = 0; k < 10; ++k) { rk[2 * k] = dp.seed_lo + 0x9E3779B9u * (uint32_t)k; rk[2 * k + 1] = dp.seed_hi + 0xBB67AE85u * (uint32_t)k; }
+    CUDA_TRY(cudaMemcpyToSymbol(c_philox_rk, rk, sizeof(rk)));
     Scratch sc; int *d_x, *d_y, *d_s, *d_seg; double* d_rgb;
     TRY(sc.up(px, n, d_x)); TRY(sc.up(py, n, d_y)); TRY(sc.up(smp, n, d_s)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_rgb)); TRY(sc.up((int*)nullptr, n, d_seg));
     trace_paths_kernel<<<(n + 127) / 128, 128>>>(vw.ds, to_dcamera(*cam), dp, n, d_x, d_y, d_s, d_rgb, d_seg);

@@ -30,7 +30,7 @@ RTW_DEV V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
 RTW_DEV V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
 RTW_DEV float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }       // :82-84
 RTW_DEV float length_squared(V3 a) { return dot(a, a); }                                    // :86-88
-RTW_DEV V3 normalize(V3 v) { float inv = 1.0f / sqrtf(length_squared(v)); return inv * v; } // :102-104 ((1/len)*v, :260-266)
+RTW_DEV V3 normalize(V3 v) { float inv = rsqrtf(length_squared(v)); return inv * v; }        // :102-104 ((1/len)*v, :260-266); MUFU.RSQ, 2 ulp
 RTW_DEV V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }                       // :106-108
 RTW_DEV V3 refract(V3 uv, V3 n, float etai_over_etat) {                                      // :110-117
     float cos_theta = fminf(dot(-uv, n), 1.0f);
@@ -64,16 +64,28 @@ RTW_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-struct PhiloxRng {
-    uint32_t k0, k1, pixel, sample, bounce, draw;
-    uint32_t w0, w1, w2, w3;
-    RTW_DEV void init(uint32_t seed_lo, uint32_t seed_hi, uint32_t px, uint32_t s) {
-        k0 = seed_lo; k1 = seed_hi; pixel = px; sample = s; bounce = 0; draw = 0;
+// The key is the same for every block of a launch: its 10-round schedule sits in constant memory (c_philox_rk, set
+// per launch from the seed) and feeds the LOP3s directly — 20 integer adds fewer per block than bumping the key.
+__constant__ uint32_t c_philox_rk[20];
+RTW_DEV void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                              uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ c_philox_rk[2 * r]; c1 = lo1; c2 = hi0 ^ c3 ^ c_philox_rk[2 * r + 1]; c3 = lo0;
     }
+    o0 = c0; o1 = c1; o2 = c2; o3 = c3;
+}
+
+struct PhiloxRng {
+    uint32_t pixel, sample, bounce, draw;          // the key (seed) lives in c_philox_rk
+    uint32_t w0, w1, w2, w3;
+    RTW_DEV void init(uint32_t, uint32_t, uint32_t px, uint32_t s) { pixel = px; sample = s; bounce = 0; draw = 0; }
     RTW_DEV void set_bounce(uint32_t b) { bounce = b; draw = 0; }
     RTW_DEV float next() {                               // random_double()
         uint32_t i = draw & 3u;
-        if (i == 0) philox4x32_10(draw >> 2, bounce, pixel, sample, k0, k1, w0, w1, w2, w3);
+        if (i == 0) philox4x32_10_rk(draw >> 2, bounce, pixel, sample, w0, w1, w2, w3);
         ++draw;
         uint32_t w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
         return (float)(w >> 8) * (1.0f / 16777216.0f);
@@ -196,16 +208,33 @@ struct HitRec {               // HitRecord :6-15
 };
 
 // Per-segment ray data kept in registers during traversal.
+#ifndef RTW_LAZY_F64
+#define RTW_LAZY_F64 0
+#endif
 struct TRay {
     V3 o, d; float time;
+#if RTW_LAZY_F64
+    float inv_a;                           // f64 copies are re-derived at each sphere test (frees 14 registers)
+    RTW_DEV double gox() const { return (double)o.x; } RTW_DEV double goy() const { return (double)o.y; } RTW_DEV double goz() const { return (double)o.z; }
+    RTW_DEV double gdx() const { return (double)d.x; } RTW_DEV double gdy() const { return (double)d.y; } RTW_DEV double gdz() const { return (double)d.z; }
+    RTW_DEV double ga() const { double x = d.x, y = d.y, z = d.z; return x * x + y * y + z * z; }
+#else
     double ox, oy, oz, dx, dy, dz, a;      // f64 copies for the sphere discriminant; a = |d|^2
     float inv_a;                           // 1 / a
+    RTW_DEV double gox() const { return ox; } RTW_DEV double goy() const { return oy; } RTW_DEV double goz() const { return oz; }
+    RTW_DEV double gdx() const { return dx; } RTW_DEV double gdy() const { return dy; } RTW_DEV double gdz() const { return dz; }
+    RTW_DEV double ga() const { return a; }
+#endif
 };
 RTW_DEV TRay make_tray(const Ray& r) {
     TRay t; t.o = r.o; t.d = r.d; t.time = r.time;
+#if RTW_LAZY_F64
+    t.inv_a = 1.0f / (float)t.ga();
+#else
     t.ox = r.o.x; t.oy = r.o.y; t.oz = r.o.z; t.dx = r.d.x; t.dy = r.d.y; t.dz = r.d.z;
     t.a = t.dx * t.dx + t.dy * t.dy + t.dz * t.dz;
     t.inv_a = 1.0f / (float)t.a;
+#endif
     return t;
 }
 
@@ -228,10 +257,10 @@ RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float time
 RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi, bool self) {
     double cx, cy, cz, rad;
     load_prim_center(pp, type, r.time, cx, cy, cz, rad);
-    double ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
-    double half_b = ocx * r.dx + ocy * r.dy + ocz * r.dz;
+    double ocx = r.gox() - cx, ocy = r.goy() - cy, ocz = r.goz() - cz;
+    double half_b = ocx * r.gdx() + ocy * r.gdy() + ocz * r.gdz();
     double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
-    double disc = half_b * half_b - r.a * c;
+    double disc = half_b * half_b - r.ga() * c;
     float discf = (float)disc, hb = (float)half_b, cf = (float)c;
     float sq = sqrtf(fmaxf(discf, 0.0f));
     bool neg = hb < 0.0f;
@@ -255,7 +284,7 @@ RTW_DEV void xform_ray(const DScene& sc, int xf, const TRay& r, V3& o, V3& d) { 
     const double2* dp = reinterpret_cast<const double2*>(&x->d_cos);
     double2 cs = __ldg(dp), bxy = __ldg(dp + 1); double bz = __ldg(&x->d_bz);
     // origin in f64 (then rounded once): keeps (k - o_k) accurate when the origin is close to a rect's plane
-    o = mk((float)(cs.x * r.ox - cs.y * r.oz + bxy.x), (float)(r.oy + bxy.y), (float)(cs.y * r.ox + cs.x * r.oz + bz));
+    o = mk((float)(cs.x * r.gox() - cs.y * r.goz() + bxy.x), (float)(r.goy() + bxy.y), (float)(cs.y * r.gox() + cs.x * r.goz() + bz));
     d = mk(m.x * r.d.x - m.y * r.d.z, r.d.y, m.y * r.d.x + m.x * r.d.z);
 }
 
@@ -308,31 +337,32 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
 // and primitive tests each run with most lanes active instead of interleaving per lane.
 RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip) {
     if (sc.n_bvh_prims == 0) return;
-    V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    // 1/d by MUFU.RCP (1 ulp): the slab test is conservative by construction, exact division buys nothing here
+    V3 inv = mk(__fdividef(1.0f, r.d.x), __fdividef(1.0f, r.d.y), __fdividef(1.0f, r.d.z));
     V3 oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
     int stack[RTW_STACK];
     stack[0] = RTW_SENTINEL;
-    int sp = 1;
+    int* sp = stack + 1;                          // points at the next free entry
     int node = 0, leaf = 0;                       // leaf >= 0: none postponed
     while (node != RTW_SENTINEL) {
         bool searching = true;
         while (node >= 0 && node != RTW_SENTINEL) {
             const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-            int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
+            int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
             float e0, e1;
-            bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, t_min, t_best, e0);
-            bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, t_min, t_best, e1);
-            if (!h0 && !h1) node = stack[--sp];
-            else {
-                node = h0 ? n3.x : n3.y;
-                if (h0 && h1) {
-                    int farc = n3.y;
-                    if (e1 < e0) { farc = node; node = n3.y; }
-                    stack[sp++] = farc;
-                }
-            }
-            if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[--sp]; }   // postpone first leaf
+            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, t_min, t_best, e0);
+            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, t_min, t_best, e1);
+            // straight-line child selection: nearer hit child next, the other one pushed
+            const bool second = h1 && (!h0 || e1 < e0);
+            const int nearc = second ? ch.y : ch.x, farc = second ? ch.x : ch.y;
+            const bool both = h0 && h1, none = !(h0 || h1);
+            if (both) *sp = farc;
+            sp += both ? 1 : 0;
+            const int top = sp[-1];                // one predictable local load per visit
+            node = none ? top : nearc;
+            sp -= none ? 1 : 0;
+            if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = sp[-1]; --sp; }   // postpone first leaf
             if (!__any_sync(__activemask(), searching)) break;
         }
         while (leaf < 0) {
@@ -342,7 +372,7 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
                 if (t == t) { t_best = t; prim_best = first + i; }       // not NaN: accepted, t <= t_best
             }
             leaf = node;                                                  // a second leaf was reached meanwhile
-            if (node < 0) node = stack[--sp];
+            if (node < 0) { node = sp[-1]; --sp; }
         }
     }
 }
@@ -370,14 +400,14 @@ RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool
         load_prim_center(pp, meta.x, r.time, cx, cy, cz, rad);
         // one Newton step of f(t) = a t^2 + 2 half_b t + c in f64: t, the hit point and the normal then carry
         // the reference's precision (an f32 t alone leaves |t d| * 1e-7 / r ~ 1e-5 of error on small far spheres)
-        double ocx = r.ox - cx, ocy = r.oy - cy, ocz = r.oz - cz;
-        double half_b = ocx * r.dx + ocy * r.dy + ocz * r.dz;
+        double ocx = r.gox() - cx, ocy = r.goy() - cy, ocz = r.goz() - cz;
+        double half_b = ocx * r.gdx() + ocy * r.gdy() + ocz * r.gdz();
         double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
         double td = (double)t;
-        double f = (r.a * td + 2.0 * half_b) * td + c, fp = 2.0 * (r.a * td + half_b);
+        double f = (r.ga() * td + 2.0 * half_b) * td + c, fp = 2.0 * (r.ga() * td + half_b);
         td -= (double)((float)f / (float)fp);
         rec.t = (float)td;
-        double px = fma(td, r.dx, r.ox), py = fma(td, r.dy, r.oy), pz = fma(td, r.dz, r.oz);
+        double px = fma(td, r.gdx(), r.gox()), py = fma(td, r.gdy(), r.goy()), pz = fma(td, r.gdz(), r.goz());
         rec.p = mk((float)px, (float)py, (float)pz);
         float inv_r = 1.0f / (float)rad;
         V3 ow = mk((float)(px - cx) * inv_r, (float)(py - cy) * inv_r, (float)(pz - cz) * inv_r);
@@ -544,7 +574,7 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
 // ------------------------------------------------------------------------------------------------
 struct PathState {
     Ray ray;
-    V3 T, L;
+    V3 T;                   // throughput; the radiance terms T*emitted / T*background are handed to the caller
     int segment;            // segments traced so far (bounce id of the next one = segment + 1)
     int last_prim;          // primitive the current ray starts on (-1: camera / medium scatter)
     PhiloxRng rng;
@@ -555,12 +585,13 @@ RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, in
     float u = ((float)x + ps.rng.next()) / ((float)prm.width - 1.0f);
     float v = ((float)y + ps.rng.next()) / ((float)prm.height - 1.0f);
     ps.ray = camera_get_ray(cam, u, v, ps.rng);
-    ps.T = mk(1.f, 1.f, 1.f); ps.L = mk(0.f, 0.f, 0.f);
+    ps.T = mk(1.f, 1.f, 1.f);
     ps.segment = 0; ps.last_prim = -1;
 }
 
-// One level of ray_color.  Returns true while the path continues.
-RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps) {
+// One level of ray_color.  Returns true while the path continues; `add` = this level's radiance term (often 0).
+RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps, V3& add) {
+    add = mk(0.f, 0.f, 0.f);
     if (ps.segment >= prm.max_depth) return false;                                         // :21-23
     ps.segment++;
     ps.rng.set_bounce((uint32_t)ps.segment);
@@ -573,7 +604,7 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps) {
         if (medium_hit(sc, m, tr, prm.t_min, t_best, ps.rng, t, mat)) { t_best = t; med_t = t; med_mat = mat; prim_best = -2; }
     }
     if (prim_best == -1) {                                                                 // :37
-        ps.L = ps.L + ps.T * mk(prm.bg_r, prm.bg_g, prm.bg_b);
+        add = ps.T * mk(prm.bg_r, prm.bg_g, prm.bg_b);
         return false;
     }
     HitRec rec; DMatRec m;
@@ -587,7 +618,7 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps) {
     }
     Ray scattered; V3 att, em;
     bool cont = scatter(sc, m, ps.ray, rec, ps.rng, scattered, att, em);                  // :28-33
-    ps.L = ps.L + ps.T * em;
+    add = ps.T * em;
     if (!cont) return false;
     ps.T = ps.T * att;
     ps.ray = scattered;

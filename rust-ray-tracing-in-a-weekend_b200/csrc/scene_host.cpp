@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -201,8 +202,9 @@ struct Builder {
     std::vector<int> idx;
     std::vector<BuildNode> nodes;
     int max_depth = 0;
-    static constexpr int NBINS = 16, MAX_LEAF = 4;
-    static constexpr double C_TRAV = 1.0, C_ISECT = 1.5;
+    static constexpr int NBINS = 16;
+    static int MAX_LEAF;
+    static double C_TRAV, C_ISECT;
 
     explicit Builder(const std::vector<Box3>& b) : boxes(b) {
         size_t n = b.size();
@@ -267,6 +269,10 @@ struct Builder {
         return me;
     }
 };
+
+int Builder::MAX_LEAF = 4;
+double Builder::C_TRAV = 1.0;
+double Builder::C_ISECT = 1.5;
 
 inline float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
 inline float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
@@ -335,7 +341,9 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
     for (const DMedium& m : out.media) if (m.mat < 0 || m.mat >= (int)out.mats.size()) { err = "phase material handle out of range"; return RTW_ERR_INVALID_ARG; }
     const int n = (int)fl.bvh_prims.size();
     if (n >= (1 << 28)) { err = "too many primitives"; return RTW_ERR_INVALID_ARG; }
-    // BVH
+    // BVH (RTW_BVH_LEAF / RTW_BVH_CI: tuning overrides for kernel experiments)
+    if (const char* e = getenv("RTW_BVH_LEAF")) Builder::MAX_LEAF = std::max(1, std::min(8, atoi(e)));
+    if (const char* e = getenv("RTW_BVH_CI")) Builder::C_ISECT = atof(e);
     Builder b(fl.bvh_boxes);
     DNode root; std::memset(&root, 0, sizeof(root));
     if (n == 0) {

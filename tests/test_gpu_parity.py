@@ -528,6 +528,19 @@ def test_render_edge_cases(pkg, gpu, orc):
     assert e.value.code == -6
 
 
+@pytest.mark.parametrize("name,W,H,spp", [("random_scene", 203, 117, 48), ("cornell_box_smoke", 96, 96, 64), ("final_scene", 100, 100, 32), ("earth", 120, 67, 32)])
+def test_pool_kernel_equals_megakernel(pkg, gpu, name, W, H, spp):
+    """The warp-pool (shared-memory wavefront) kernel and the megakernel schedule the SAME per-(pixel, sample) paths
+    (same Philox keys, same device functions): their images must agree to f32 summation order.  Ragged sizes on purpose."""
+    sc, spec = pkg.scenes.build(gpu, name)
+    sc.commit(1, 0)
+    cam = spec.camera(gpu, W, H)
+    mega, st0 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=5, flags=pkg.api.RTW_FLAG_KERNEL_MEGA))
+    pool, st1 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=5, flags=pkg.api.RTW_FLAG_KERNEL_POOL))
+    assert st0["rays"] == st1["rays"] and st0["paths"] == st1["paths"]
+    assert np.abs(mega - pool).max() <= 2e-4 * max(np.abs(mega).max(), 1.0)
+
+
 def test_write_color_bit_exact(pkg, gpu, orc):
     """write_color (src/math.rs:119-132): gamma 2, clamp, *256 truncation — byte-exact against the oracle."""
     import ctypes as C
