@@ -112,6 +112,8 @@ int rtw_mat_isotropic(rtw_scene*, int tex);
 
 /* Hittable (src/hittable.rs:29-41) -> hittable id.  Ids may be reused (= Rust .clone()). */
 int rtw_sphere(rtw_scene*, int mat, const double center[3], double radius);
+/* n static spheres pushed straight into the world (= n x { rtw_sphere; rtw_world_push }); for the 1M-16M sweep */
+int rtw_sphere_batch(rtw_scene*, int32_t n, const int32_t* mats, const double* centers /*3n*/, const double* radii);
 int rtw_moving_sphere(rtw_scene*, int mat, const double center0[3], const double center1[3],
                       double time0, double time1, double radius);
 int rtw_xy_rect(rtw_scene*, int mat, double x0, double x1, double y0, double y1, double k);

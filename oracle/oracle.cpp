@@ -797,6 +797,14 @@ int orc_sphere(orc_scene* s, int mat, const double c[3], double r) {
     if (!mat_ok(s, mat)) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
     Hittable h; h.kind = H_SPHERE; h.mat = mat; h.c0 = v3(c); h.radius = r; return push_node(s, h);
 }
+int orc_sphere_batch(orc_scene* s, int32_t n, const int32_t* mats, const double* centers, const double* radii) {
+    for (int i = 0; i < n; ++i) {
+        int id = orc_sphere(s, mats[i], centers + 3 * i, radii[i]);
+        if (id < 0) return id;
+        SC(s)->world.push_back(id);
+    }
+    return 0;
+}
 int orc_moving_sphere(orc_scene* s, int mat, const double c0[3], const double c1[3], double t0, double t1, double r) {
     if (!mat_ok(s, mat)) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
     Hittable h; h.kind = H_MOVING_SPHERE; h.mat = mat; h.c0 = v3(c0); h.c1 = v3(c1); h.time0 = t0; h.time1 = t1; h.radius = r;

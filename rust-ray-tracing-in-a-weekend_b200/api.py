@@ -143,6 +143,8 @@ class Lib:
         f("mat_isotropic").argtypes = [vp, C.c_int]
         f("sphere").argtypes = [vp, C.c_int, dp, C.c_double]
         f("moving_sphere").argtypes = [vp, C.c_int, dp, dp, C.c_double, C.c_double, C.c_double]
+        f("sphere_batch").argtypes = [vp, C.c_int32, ip, dp, dp]
+        f("sphere_batch").restype = C.c_int
         for n in ("xy_rect", "xz_rect", "yz_rect"):
             f(n).argtypes = [vp, C.c_int] + [C.c_double] * 5
         f("box").argtypes = [vp, dp, dp, C.c_int]
@@ -305,6 +307,11 @@ class Scene:
     # --- Hittable (src/hittable.rs:29-41)
     def sphere(self, mat, center, radius):
         return self._c("sphere", mat, _d3(center), float(radius))
+
+    def sphere_batch(self, mats, centers, radii):
+        """n static spheres straight into the world (rtw_sphere_batch) — the 1M-16M sweep."""
+        m, c, r = _i32(mats), _f64(centers).reshape(-1, 3), _f64(radii)
+        self._c("sphere_batch", len(m), _p(m, C.c_int32), _p(c), _p(r))
 
     def moving_sphere(self, mat, c0, c1, t0, t1, radius):
         return self._c("moving_sphere", mat, _d3(c0), _d3(c1), float(t0), float(t1), float(radius))

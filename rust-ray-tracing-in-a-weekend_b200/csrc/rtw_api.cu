@@ -632,6 +632,18 @@ int rtw_sphere(rtw_scene* s, int mat, const double c[3], double r) {
     if (!mat_ok(s, mat) || !c) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
     rtw::HNode h; h.kind = rtw::H_SPHERE; h.mat = mat; h.c0 = v3(c); h.radius = r; return push_node(s, h);
 }
+int rtw_sphere_batch(rtw_scene* s, int32_t n, const int32_t* mats, const double* centers, const double* radii) {
+    if (!s || n <= 0 || !mats || !centers || !radii) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    for (int i = 0; i < n; ++i) if (!mat_ok(s, mats[i])) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    size_t base = s->g.bulk.size();
+    s->g.bulk.resize(base + (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        rtw::BulkSphere& b = s->g.bulk[base + i];
+        b.c[0] = centers[3 * i]; b.c[1] = centers[3 * i + 1]; b.c[2] = centers[3 * i + 2]; b.r = radii[i]; b.mat = mats[i];
+    }
+    s->committed = false;
+    return RTW_OK;
+}
 int rtw_moving_sphere(rtw_scene* s, int mat, const double c0[3], const double c1[3], double t0, double t1, double r) {
     if (!mat_ok(s, mat) || !c0 || !c1) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
     rtw::HNode h; h.kind = rtw::H_MOVING_SPHERE; h.mat = mat; h.c0 = v3(c0); h.c1 = v3(c1); h.time0 = t0; h.time1 = t1; h.radius = r;

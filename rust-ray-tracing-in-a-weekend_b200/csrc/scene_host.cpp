@@ -13,7 +13,11 @@
 #include "scene_host.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -194,55 +198,74 @@ struct Flattener {
 };
 
 // ---- binned-SAH BVH ----------------------------------------------------------------------------
-struct BuildNode { Box3 box; int left = -1, right = -1; int first = 0, count = 0; };
+// Works on a compact, physically partitioned array of float boxes (rounded OUTWARD from the f64 primitive boxes, so
+// every union below is exact and conservative): each level streams its range sequentially instead of chasing indices.
+inline float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
+inline float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
+
+struct FBox {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    void grow(const FBox& b) { for (int i = 0; i < 3; ++i) { mn[i] = std::min(mn[i], b.mn[i]); mx[i] = std::max(mx[i], b.mx[i]); } }
+    void grow_pt(const float p[3]) { for (int i = 0; i < 3; ++i) { mn[i] = std::min(mn[i], p[i]); mx[i] = std::max(mx[i], p[i]); } }
+    double area() const {
+        double dx = (double)mx[0] - mn[0], dy = (double)mx[1] - mn[1], dz = (double)mx[2] - mn[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0;
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+struct Item { FBox b; int id; };
+struct BuildNode { FBox box; int left = -1, right = -1; int first = 0, count = 0; };
+struct BuildTask { int node, first, count, depth; };
 
 struct Builder {
-    const std::vector<Box3>& boxes;
-    std::vector<double> cen;          // 3 per prim
-    std::vector<int> idx;
+    std::vector<Item> items;
     std::vector<BuildNode> nodes;
     int max_depth = 0;
     static constexpr int NBINS = 16;
     static int MAX_LEAF;
     static double C_TRAV, C_ISECT;
 
-    explicit Builder(const std::vector<Box3>& b) : boxes(b) {
-        size_t n = b.size();
-        cen.resize(3 * n); idx.resize(n);
-        for (size_t i = 0; i < n; ++i) {
-            idx[i] = (int)i;
-            for (int a = 0; a < 3; ++a) cen[3 * i + a] = 0.5 * (b[i].mn[a] + b[i].mx[a]);
+    explicit Builder(const std::vector<Box3>& b) {
+        items.resize(b.size());
+        for (size_t i = 0; i < b.size(); ++i) {
+            for (int a = 0; a < 3; ++a) { items[i].b.mn[a] = down(b[i].mn[a]); items[i].b.mx[a] = up(b[i].mx[a]); }
+            items[i].id = (int)i;
         }
     }
+    static void centroid(const Item& it, float c[3]) { for (int a = 0; a < 3; ++a) c[a] = 0.5f * (it.b.mn[a] + it.b.mx[a]); }
 
-    int build(int first, int count, int depth) {
-        max_depth = std::max(max_depth, depth);
-        int me = (int)nodes.size();
-        nodes.emplace_back();
-        Box3 box, cbox;
-        for (int i = first; i < first + count; ++i) {
-            box.grow(boxes[idx[i]]);
-            cbox.grow(&cen[3 * idx[i]]);
-        }
-        nodes[me].box = box; nodes[me].first = first; nodes[me].count = count;
+    // Top-down binned SAH.  With `tasks` set, subtrees of at most `cutoff` prims are not built but recorded, so that
+    // they can be built by worker threads afterwards (disjoint item ranges, private node vectors).
+    int build(std::vector<BuildNode>& out, int first, int count, int depth, int& depth_max, std::vector<BuildTask>* tasks, int cutoff) {
+        depth_max = std::max(depth_max, depth);
+        int me = (int)out.size();
+        out.emplace_back();
+        out[me].first = first; out[me].count = count;
+        if (tasks && depth > 0 && count <= cutoff && count > MAX_LEAF) { tasks->push_back(BuildTask{me, first, count, depth}); return me; }
+        FBox box, cbox;
+        for (int i = first; i < first + count; ++i) { float c[3]; centroid(items[i], c); box.grow(items[i].b); cbox.grow_pt(c); }
+        out[me].box = box;
         if (count <= 1) return me;
-        // pick split
+        // one pass fills the bins of all three axes
+        FBox bb[3][NBINS]; int bc[3][NBINS] = {};
+        float lo[3], scale[3];
+        for (int a = 0; a < 3; ++a) { lo[a] = cbox.mn[a]; float ext = cbox.mx[a] - cbox.mn[a]; scale[a] = ext > 0 ? NBINS / ext : 0.f; }
+        for (int i = first; i < first + count; ++i) {
+            float c[3]; centroid(items[i], c);
+            for (int a = 0; a < 3; ++a) {
+                int k = std::min(NBINS - 1, std::max(0, (int)((c[a] - lo[a]) * scale[a])));
+                bb[a][k].grow(items[i].b); bc[a][k]++;
+            }
+        }
         double best_cost = 1e300; int best_axis = -1, best_bin = -1;
         double parent_area = std::max(box.area(), 1e-300);
         for (int a = 0; a < 3; ++a) {
-            double lo = cbox.mn[a], hi = cbox.mx[a];
-            if (!(hi > lo)) continue;
-            double scale = NBINS / (hi - lo);
-            Box3 bb[NBINS]; int bc[NBINS] = {0};
-            for (int i = first; i < first + count; ++i) {
-                int k = std::min(NBINS - 1, std::max(0, (int)((cen[3 * idx[i] + a] - lo) * scale)));
-                bb[k].grow(boxes[idx[i]]); bc[k]++;
-            }
+            if (!(scale[a] > 0)) continue;
             double la[NBINS], ra[NBINS]; int lc[NBINS], rc[NBINS];
-            Box3 acc; int n = 0;
-            for (int k = 0; k < NBINS; ++k) { if (bc[k]) acc.grow(bb[k]); n += bc[k]; la[k] = acc.area(); lc[k] = n; }
-            acc = Box3(); n = 0;
-            for (int k = NBINS - 1; k >= 0; --k) { if (bc[k]) acc.grow(bb[k]); n += bc[k]; ra[k] = acc.area(); rc[k] = n; }
+            FBox acc; int n = 0;
+            for (int k = 0; k < NBINS; ++k) { if (bc[a][k]) acc.grow(bb[a][k]); n += bc[a][k]; la[k] = acc.area(); lc[k] = n; }
+            acc = FBox(); n = 0;
+            for (int k = NBINS - 1; k >= 0; --k) { if (bc[a][k]) acc.grow(bb[a][k]); n += bc[a][k]; ra[k] = acc.area(); rc[k] = n; }
             for (int k = 0; k < NBINS - 1; ++k) {
                 if (lc[k] == 0 || rc[k + 1] == 0) continue;
                 double cost = C_TRAV + C_ISECT * (la[k] * lc[k] + ra[k + 1] * rc[k + 1]) / parent_area;
@@ -255,18 +278,51 @@ struct Builder {
         if (best_axis < 0) {
             mid = first + count / 2;       // coincident centroids: split by index
         } else {
-            double lo = cbox.mn[best_axis], hi = cbox.mx[best_axis], scale = NBINS / (hi - lo);
-            auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](int p) {
-                int k = std::min(NBINS - 1, std::max(0, (int)((cen[3 * p + best_axis] - lo) * scale)));
+            const int ax = best_axis; const float l0 = lo[ax], sc = scale[ax];
+            auto it = std::partition(items.begin() + first, items.begin() + first + count, [&](const Item& p) {
+                float c = 0.5f * (p.b.mn[ax] + p.b.mx[ax]);
+                int k = std::min(NBINS - 1, std::max(0, (int)((c - l0) * sc)));
                 return k <= best_bin;
             });
-            mid = (int)(it - idx.begin());
+            mid = (int)(it - items.begin());
             if (mid == first || mid == first + count) mid = first + count / 2;
         }
-        int l = build(first, mid - first, depth + 1);
-        int r = build(mid, first + count - mid, depth + 1);
-        nodes[me].left = l; nodes[me].right = r;
+        int l = build(out, first, mid - first, depth + 1, depth_max, tasks, cutoff);
+        int r = build(out, mid, first + count - mid, depth + 1, depth_max, tasks, cutoff);
+        out[me].left = l; out[me].right = r;
         return me;
+    }
+
+    void build_all(int n) {
+        nodes.reserve(2 * (size_t)n);
+        unsigned hw = std::thread::hardware_concurrency();
+        int n_threads = (int)std::min<unsigned>(hw ? hw : 1, 32);
+        if (n < (1 << 16) || n_threads < 2) { build(nodes, 0, n, 0, max_depth, nullptr, 0); return; }
+        std::vector<BuildTask> tasks;
+        build(nodes, 0, n, 0, max_depth, &tasks, std::max(1024, n / (8 * n_threads)));
+        std::vector<std::vector<BuildNode>> sub(tasks.size());
+        std::vector<int> sub_depth(tasks.size(), 0);
+        std::atomic<size_t> next(0);
+        auto worker = [&]() {
+            for (;;) {
+                size_t t = next.fetch_add(1);
+                if (t >= tasks.size()) break;
+                sub[t].reserve(2 * (size_t)tasks[t].count);
+                build(sub[t], tasks[t].first, tasks[t].count, tasks[t].depth, sub_depth[t], nullptr, 0);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int i = 1; i < n_threads; ++i) th.emplace_back(worker);
+        worker();
+        for (auto& t : th) t.join();
+        for (size_t t = 0; t < tasks.size(); ++t) {            // splice: local root replaces the placeholder
+            max_depth = std::max(max_depth, sub_depth[t]);
+            const int off = (int)nodes.size() - 1;             // local index c >= 1  ->  off + c
+            auto remap = [&](BuildNode b) { if (b.left >= 0) { b.left += off; b.right += off; } return b; };
+            nodes[tasks[t].node] = remap(sub[t][0]);
+            for (size_t c = 1; c < sub[t].size(); ++c) nodes.push_back(remap(sub[t][c]));
+            std::vector<BuildNode>().swap(sub[t]);
+        }
     }
 };
 
@@ -274,13 +330,10 @@ int Builder::MAX_LEAF = 4;
 double Builder::C_TRAV = 1.0;
 double Builder::C_ISECT = 1.5;
 
-inline float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
-inline float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
-
-void set_child_box(DNode& n, int which, const Box3* b) {
+void set_child_box(DNode& n, int which, const FBox* b) {
     const float inf = std::numeric_limits<float>::infinity();
-    float mnx = inf, mxx = -inf, mny = inf, mxy = -inf, mnz = inf, mxz = -inf;
-    if (b) { mnx = down(b->mn[0]); mxx = up(b->mx[0]); mny = down(b->mn[1]); mxy = up(b->mx[1]); mnz = down(b->mn[2]); mxz = up(b->mx[2]); }
+    float mnx = inf, mxx = inf, mny = inf, mxy = inf, mnz = inf, mxz = inf;      // unused slot: never hit (see DNode)
+    if (b) { mnx = b->mn[0]; mxx = b->mx[0]; mny = b->mn[1]; mxy = b->mx[1]; mnz = b->mn[2]; mxz = b->mx[2]; }
     if (which == 0) { n.c0minx = mnx; n.c0maxx = mxx; n.c0miny = mny; n.c0maxy = mxy; n.c0minz = mnz; n.c0maxz = mxz; }
     else { n.c1minx = mnx; n.c1maxx = mxx; n.c1miny = mny; n.c1maxy = mxy; n.c1minz = mnz; n.c1maxz = mxz; }
 }
@@ -327,6 +380,9 @@ void pack_materials(const SceneGraph& g, FlatScene& out) {
 }  // namespace
 
 int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, std::string& err) {
+    const bool timing = getenv("RTW_TIMING") != nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[flatten] %s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     out = FlatScene();
     DXform ident; std::memset(&ident, 0, sizeof(ident)); ident.m_cos = 1.f;
     out.xforms.push_back(ident);
@@ -336,6 +392,19 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         int rc = fl.emit(id, ch, false, 0);
         if (rc) return rc;
     }
+    if (&roots == &g.world) {           // bulk spheres belong to the world, not to a single-hittable view
+        fl.bvh_prims.reserve(fl.bvh_prims.size() + g.bulk.size());
+        fl.bvh_boxes.reserve(fl.bvh_boxes.size() + g.bulk.size());
+        for (const BulkSphere& b : g.bulk) {
+            DPrim p; std::memset(&p, 0, sizeof(p));
+            p.s.cx = b.c[0]; p.s.cy = b.c[1]; p.s.cz = b.c[2]; p.s.r = b.r; p.type = PRIM_SPHERE; p.mat = b.mat - 1;
+            double ar = std::fabs(b.r);
+            Box3 bx; double lo[3] = {b.c[0] - ar, b.c[1] - ar, b.c[2] - ar}, hi[3] = {b.c[0] + ar, b.c[1] + ar, b.c[2] + ar};
+            bx.grow(lo); bx.grow(hi);
+            fl.bvh_prims.push_back(p); fl.bvh_boxes.push_back(bx);
+        }
+    }
+    lap("emit");
     pack_materials(g, out);
     for (const DPrim& p : fl.bvh_prims) if (p.mat < 0 || p.mat >= (int)out.mats.size()) { err = "material handle out of range"; return RTW_ERR_INVALID_ARG; }
     for (const DMedium& m : out.media) if (m.mat < 0 || m.mat >= (int)out.mats.size()) { err = "phase material handle out of range"; return RTW_ERR_INVALID_ARG; }
@@ -351,11 +420,12 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         root.child0 = root.child1 = leaf_code(0, 1);
         out.nodes.push_back(root);
     } else {
-        b.nodes.reserve(2 * (size_t)n);
-        b.build(0, n, 0);
+        lap("builder init");
+        b.build_all(n);
+        lap("build");
         // leaf order
         out.prims.resize(n);
-        for (int i = 0; i < n; ++i) out.prims[i] = fl.bvh_prims[b.idx[i]];
+        for (int i = 0; i < n; ++i) out.prims[i] = fl.bvh_prims[b.items[i].id];
         if (b.nodes[0].left < 0) {     // the whole scene is one leaf
             // one leaf: both slots point at it (tested twice, like the reference's duplicated single-object
             // leaves, src/hittable.rs:96-98); an "empty" slot cannot be encoded with min/max slabs
@@ -383,6 +453,7 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
             out.sah_cost = sah;
         }
     }
+    lap("emit nodes");
     out.max_depth = b.max_depth;
     out.n_bvh_prims = n;
     // boundary prims follow; shift media ranges
@@ -407,7 +478,7 @@ bool validate_bvh(const FlatScene& f, std::string& err) {
             int ch = c ? n.child1 : n.child0;
             float mnx = c ? n.c1minx : n.c0minx, mxx = c ? n.c1maxx : n.c0maxx;
             if (ch >= 0) { stack.push_back(ch); continue; }
-            if (mnx > mxx) continue;   // empty slot
+            if (mnx > mxx || std::isinf(mnx)) continue;   // unused slot (empty world)
             int code = ~ch, first = code >> 3, count = (code & 7) + 1;
             if (first < 0 || first + count > f.n_bvh_prims) { err = "leaf range out of bounds"; return false; }
             for (int i = first; i < first + count; ++i) seen[i]++;

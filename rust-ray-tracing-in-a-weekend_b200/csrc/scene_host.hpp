@@ -45,11 +45,15 @@ struct HMaterial {
     double fuzz = 0, ir = 1;
 };
 
+// compact record for rtw_sphere_batch (the 1M-16M sphere sweep would not fit as HNodes)
+struct BulkSphere { double c[3]; double r; int mat; };
+
 struct SceneGraph {
     std::vector<HTexture> textures;
     std::vector<HMaterial> materials;
     std::vector<HNode> nodes;
     std::vector<int> world;
+    std::vector<BulkSphere> bulk;          // all of them are world members (pushed after `world`)
 };
 
 // The flattened scene, still on the host, ready to be packed into one blob.

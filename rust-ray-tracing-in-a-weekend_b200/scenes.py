@@ -295,10 +295,7 @@ def sweep_scene(sc, n_spheres, seed=None, wrap_bvh=False):
             mats.append(sc.dielectric(1.5))
     centers = rs.uniform(-L / 2, L / 2, (n_spheres, 3))
     which = rs.randint(0, 256, n_spheres)
-    w = _World(sc, wrap_bvh)
-    for c, m in zip(centers, which):
-        w.push(sc.sphere(mats[m], tuple(c), r))
-    w.done()
+    sc.sphere_batch(np.asarray(mats, np.int32)[which], centers, np.full(n_spheres, r))
     return SceneSpec(f"sweep_{n_spheres}", (2.2 * L, 0.6 * L, 1.1 * L), (0.0, 0.0, 0.0), 30.0, (0.7, 0.8, 1.0),
                      3840, 2160, 256, aperture=0.0, focus_dist=10.0)
 

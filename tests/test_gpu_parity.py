@@ -568,3 +568,26 @@ def test_two_gpus_in_process(pkg, gpu):
     two, st2 = sc.render(cam, pkg.make_params(600, 400, 64, background=spec.background, n_gpus=2))
     assert st2["n_devices"] == 2 and min(st2["units_per_device"][:2]) > 0.2 * sum(st2["units_per_device"])
     assert np.abs(one - two).max() <= 2e-4 * one.max()
+
+
+@pytest.mark.parametrize("scene_id,name", [(0, "random_scene"), (5, "cornell_box"), (7, "final_scene")])
+def test_cpp_mirror_main_matches_python_path(pkg, gpu, scene_id, name, tmp_path):
+    """The replacement main (host/rtw_main.cpp: reference constructors -> flatten -> rtw_render -> write_color -> P3)
+    prints the same image as the ctypes path, byte for byte up to f32 summation order (<= 1 LSB on a few bytes)."""
+    import subprocess
+    exe = os.path.join(ROOT, "rust-ray-tracing-in-a-weekend_b200", "host", "rtw_main")
+    earth = tmp_path / "earth.rgb"
+    earth.write_bytes(pkg.scenes.earth_texels().tobytes())
+    W, H, spp = 96, 64, 16
+    r = subprocess.run([exe, "--scene", str(scene_id), "--width", str(W), "--height", str(H), "--spp", str(spp), "--earth", str(earth)],
+                       capture_output=True, text=True, check=True)
+    assert r.stdout.startswith(f"P3\n{W} {H}\n255\n\n")                  # src/main.rs:472 header, byte-compatible
+    vals = np.array(r.stdout.split()[4:], dtype=np.int64).reshape(H, W, 3)
+    sc, spec = pkg.scenes.build(gpu, name)
+    sc.commit(1, 0)
+    img, _ = sc.render(spec.camera(gpu, W, H), pkg.make_params(W, H, spp, background=spec.background, seed=1))
+    import ctypes as C
+    out = np.zeros(W * H * 3, np.uint8)
+    gpu.check(gpu.f("write_color")(img.ctypes.data_as(C.POINTER(C.c_float)), W * H, spp, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    diff = np.abs(vals - out.reshape(H, W, 3).astype(np.int64))
+    assert diff.max() <= 1 and np.mean(diff > 0) < 0.01

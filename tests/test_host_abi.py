@@ -155,3 +155,26 @@ def test_golden_fixture_matches_oracle(pkg, orc):
         rgb, seg = sc.trace_paths(spec.camera(orc, W, H), p, g["px"], g["py"], g["sample"])
         assert np.array_equal(seg, g[name + "_seg"]), name
         assert np.allclose(rgb, g[name + "_rgb"], rtol=1e-12, atol=1e-14), name
+
+
+SCENE_IDS = {"random_scene": 0, "two_spheres": 1, "two_perlin_spheres": 2, "earth": 3, "simple_light": 4, "cornell_box": 5,
+             "cornell_box_smoke": 6, "final_scene": 7}
+
+
+@pytest.mark.parametrize("name", list(SCENE_IDS))
+def test_cpp_mirror_flattens_like_the_python_binding(pkg, rtw, name):
+    """host/rtw.hpp + scenes.hpp (C++ twin of the Rust shim: reference type/constructor names, World -> flatten -> C ABI)
+    must hand the backend the same scene as scenes.py: same seeded streams, same primitive / node / material counts."""
+    import subprocess
+    exe = os.path.join(ROOT, "rust-ray-tracing-in-a-weekend_b200", "host", "rtw_main")
+    if not os.path.exists(exe):
+        import __graft_entry__
+        __graft_entry__.build()
+    out = subprocess.run([exe, "--scene", str(SCENE_IDS[name]), "--dry-run"], capture_output=True, text=True, check=True).stdout.split()
+    got = dict(zip(out[0::2], map(int, out[1::2])))
+    sc, _ = pkg.scenes.build(rtw, name)
+    want = sc.debug_flatten()
+    for k in ("prims", "bvh_prims", "nodes", "xforms", "media", "mats", "depth"):
+        assert got[k] == want[k], (k, got, want)
+    r = subprocess.run([exe, "--scene", "9", "--dry-run"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unsupported scene selected" in r.stderr          # src/main.rs:461-463, as an error not a panic
