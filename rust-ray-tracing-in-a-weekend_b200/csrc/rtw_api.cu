@@ -76,9 +76,10 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
             }
             if (!__any_sync(0xffffffffu, alive)) { if (next >= n_items) break; continue; }
             if (alive) {
-                ++rays;
                 V3 add;
+                const int seg0 = ps.segment;
                 alive = path_step(sc, prm, ps, add);
+                rays += (unsigned)(ps.segment - seg0);                      // 0 when the depth budget was already spent
                 if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
                     atomicAdd(&acc[warp][pix * 3 + 0], add.x);
                     atomicAdd(&acc[warp][pix * 3 + 1], add.y);

@@ -337,8 +337,8 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
 // and primitive tests each run with most lanes active instead of interleaving per lane.
 RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip) {
     if (sc.n_bvh_prims == 0) return;
-    // 1/d by MUFU.RCP (1 ulp): the slab test is conservative by construction, exact division buys nothing here
-    V3 inv = mk(__fdividef(1.0f, r.d.x), __fdividef(1.0f, r.d.y), __fdividef(1.0f, r.d.z));
+    // exact 1/d: the 2-ulp padding of the slab test (Ize) assumes correctly rounded reciprocals
+    V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     V3 oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
     int stack[RTW_STACK];
     stack[0] = RTW_SENTINEL;
@@ -537,16 +537,27 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
         return false;
     }
     if (kind == MAT_DIELECTRIC) {                                                          // :62-82
+        // f64 island: near the critical angle 1 - |r_perp|^2 (src/math.rs:114) cancels to ~1e-5 and an f32 cos(theta)
+        // (1e-7 absolute) would leave 1e-4 on the refracted direction.  B200: FP64 at half rate, 8 % of the hits.
         attenuation = mk(1.f, 1.f, 1.f);
-        float ratio = rec.front ? 1.0f / m.param : m.param;
-        V3 unit_direction = normalize(ray.d);
-        float cos_theta = fminf(dot(-unit_direction, rec.normal), 1.0f);
-        float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
-        bool cannot_refract = ratio * sin_theta > 1.0f;
-        if (cannot_refract || reflectance(cos_theta, ratio) > g.next())                   // short-circuit draw :72
-            scattered.d = reflect(unit_direction, rec.normal);
-        else
-            scattered.d = refract(unit_direction, rec.normal, ratio);
+        const double ratio = rec.front ? 1.0 / (double)m.param : (double)m.param;
+        const double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z, nx = rec.normal.x, ny = rec.normal.y, nz = rec.normal.z;
+        const double dd = dx * dx + dy * dy + dz * dz;
+        double inv = (double)rsqrtf((float)dd);
+        inv = inv * (1.5 - 0.5 * dd * inv * inv);                                          // one Newton step: 2e-7 -> 1e-13
+        const double ux = dx * inv, uy = dy * inv, uz = dz * inv;                          // unit_direction :66
+        const double cos_theta = fmin(-(ux * nx + uy * ny + uz * nz), 1.0);                // :67
+        const double sin2 = 1.0 - cos_theta * cos_theta;
+        const bool cannot_refract = ratio * ratio * sin2 > 1.0;                            // ratio * sin_theta > 1 :70
+        if (cannot_refract || reflectance((float)cos_theta, (float)ratio) > g.next()) {   // short-circuit draw :72
+            const double k2 = 2.0 * (ux * nx + uy * ny + uz * nz);                         // reflect :106-108
+            scattered.d = mk((float)(ux - k2 * nx), (float)(uy - k2 * ny), (float)(uz - k2 * nz));
+        } else {                                                                           // refract :110-117
+            const double px = ratio * (ux + cos_theta * nx), py = ratio * (uy + cos_theta * ny), pz = ratio * (uz + cos_theta * nz);
+            const double k = 1.0 - (px * px + py * py + pz * pz);
+            const double par = -(double)sqrtf((float)fabs(k));
+            scattered.d = mk((float)(px + par * nx), (float)(py + par * ny), (float)(pz + par * nz));
+        }
         return true;
     }
     V3 ball = random_in_unit_sphere(g);                                                    // :37 / :52 / :85

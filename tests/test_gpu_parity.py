@@ -290,9 +290,11 @@ def test_material_scatter(pkg, gpu, orc, kind):
     same = (ra["scattered"] == rb["scattered"]) & (ra["ndraw"] == rb["ndraw"])
     # conditioning: drop inputs whose ORACLE output moves by more than 1e-5/3 under a 1e-7 relative nudge of the ray
     # direction (near-critical refraction, 1 - |r_perp|^2 -> 0 in src/math.rs:114) — no f32 evaluation can hold 1e-5 there
-    rb2 = scenes[1][0].test_scatter(scenes[1][1], ro, rd * (1 + 1e-7 * rs.uniform(-1, 1, rd.shape)), rt, p, nrm, front, u, v, xi)
     dnb = np.maximum(np.linalg.norm(rb["dir"], axis=1, keepdims=True), 1e-2)
-    well = (rb2["scattered"] == rb["scattered"]) & ((np.abs(rb2["dir"] - rb["dir"]) / dnb).max(1) <= REL / 3)
+    well = np.ones(n, bool)
+    for _ in range(4):
+        rb2 = scenes[1][0].test_scatter(scenes[1][1], ro, rd * (1 + 1e-7 * rs.uniform(-1, 1, rd.shape)), rt, p, nrm, front, u, v, xi)
+        well &= (rb2["scattered"] == rb["scattered"]) & ((np.abs(rb2["dir"] - rb["dir"]) / dnb).max(1) <= REL / 3)
     assert well.mean() > 0.995
     if kind == "dielectric":    # reflect/refract branch: side of the surface the new ray leaves on
         same &= np.sign(np.einsum("ij,ij->i", ra["dir"], nrm)) == np.sign(np.einsum("ij,ij->i", rb["dir"], nrm))
@@ -537,7 +539,8 @@ def test_pool_kernel_equals_megakernel(pkg, gpu, name, W, H, spp):
     cam = spec.camera(gpu, W, H)
     mega, st0 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=5, flags=pkg.api.RTW_FLAG_KERNEL_MEGA))
     pool, st1 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=5, flags=pkg.api.RTW_FLAG_KERNEL_POOL))
-    assert st0["rays"] == st1["rays"] and st0["paths"] == st1["paths"]
+    assert st0["paths"] == st1["paths"]
+    assert st0["rays"] == st1["rays"]
     assert np.abs(mega - pool).max() <= 2e-4 * max(np.abs(mega).max(), 1.0)
 
 
@@ -591,3 +594,27 @@ def test_cpp_mirror_main_matches_python_path(pkg, gpu, scene_id, name, tmp_path)
     gpu.check(gpu.f("write_color")(img.ctypes.data_as(C.POINTER(C.c_float)), W * H, spp, out.ctypes.data_as(C.POINTER(C.c_uint8))))
     diff = np.abs(vals - out.reshape(H, W, 3).astype(np.int64))
     assert diff.max() <= 1 and np.mean(diff > 0) < 0.01
+
+
+def test_sweep_scene_parity_and_bulk_api(pkg, gpu, orc):
+    """BASELINE config 5 generator at test size (20k spheres through rtw_sphere_batch): world BVH hit parity and
+    path parity against the oracle's flat world list over the same spheres."""
+    a, b = pkg.Scene(gpu), pkg.Scene(orc)
+    spec = pkg.scenes.sweep_scene(a, 20000, seed=3)
+    pkg.scenes.sweep_scene(b, 20000, seed=3, wrap_bvh=False)
+    a.commit(1, 0)
+    d = a.debug_flatten()
+    assert d["prims"] == 20000 and d["nodes"] > 5000
+    rs = np.random.RandomState(5)
+    W, H, n = 96, 54, 6000
+    px, py, sm = rs.randint(0, W, n), rs.randint(0, H, n), rs.randint(0, 64, n)
+    p = pkg.make_params(W, H, 64, background=spec.background, seed=2)
+    ra, sa = a.trace_paths(spec.camera(gpu, W, H), p, px, py, sm)
+    rb, sb = b.trace_paths(spec.camera(orc, W, H), p, px, py, sm)      # flat list of 20k spheres: ~1 s
+    good = (sa == sb) & (np.abs(ra - rb).max(1) <= 1e-3 * np.maximum(1.0, np.abs(rb).max(1)))
+    # far camera (|o| ~ 2500) and r = 8.4 spheres: a hit point stored in f32 is known to 3e-5, i.e. 4e-6 of a radius, and
+    # every specular bounce multiplies that by distance/radius — paths decorrelate after a few bounces (5 rays/path here)
+    assert good.mean() >= 0.85, good.mean()
+    assert np.mean(sa[:2000] == sb[:2000]) > 0.85
+    se = rb.std(0) / math.sqrt(n) * math.sqrt(2 * (1 - good.mean()))
+    assert (np.abs(ra.mean(0) - rb.mean(0)) <= 5 * se + 1e-4).all()
