@@ -288,19 +288,20 @@ RTW_DEV void xform_ray(const DScene& sc, int xf, const TRay& r, V3& o, V3& d) { 
     d = mk(m.x * r.d.x - m.y * r.d.z, r.d.y, m.y * r.d.x + m.x * r.d.z);
 }
 
-// xy/xz/yz_rect_hit :308-384 — t only.  The ray is in the rect's object space.
+// xy/xz/yz_rect_hit :308-384 — t only.  The ray is in the rect's object space.  The three variants differ only in
+// which component plays k / a / b: selected with predicated moves so that lanes holding different rect kinds (the six
+// faces of a box sit in neighbouring leaves) run ONE instruction stream.
 RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, float t_lo, float t_hi) {
     const float4* q = reinterpret_cast<const float4*>(pp);
     float4 ab = __ldg(q); float k = __ldg(reinterpret_cast<const float*>(q + 1));
-    float ok, dk, oa, da, ob, db;
-    if (type == PRIM_XY) { ok = o.z; dk = d.z; oa = o.x; da = d.x; ob = o.y; db = d.y; }
-    else if (type == PRIM_XZ) { ok = o.y; dk = d.y; oa = o.x; da = d.x; ob = o.z; db = d.z; }
-    else { ok = o.x; dk = d.x; oa = o.y; da = d.y; ob = o.z; db = d.z; }
+    const bool xy = type == PRIM_XY, yz = type == PRIM_YZ;
+    const float ok = xy ? o.z : (yz ? o.x : o.y), dk = xy ? d.z : (yz ? d.x : d.y);
+    const float oa = yz ? o.y : o.x, da = yz ? d.y : d.x;
+    const float ob = xy ? o.y : o.z, db = xy ? d.y : d.z;
     float t = (k - ok) / dk;
-    if (!(t >= t_lo && t <= t_hi)) return CUDART_NAN_F;
     float a = oa + t * da, b = ob + t * db;
-    if (a < ab.x || a > ab.y || b < ab.z || b > ab.w) return CUDART_NAN_F;
-    return t;
+    bool okk = t >= t_lo && t <= t_hi && !(a < ab.x || a > ab.y || b < ab.z || b > ab.w);
+    return okk ? t : CUDART_NAN_F;
 }
 
 // Any primitive: accepted root in [t_lo, t_hi] or NaN.  `skip` = primitive the ray starts on (-1: none): a planar
@@ -310,8 +311,8 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
     if (meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip);
     if (pi == skip) return CUDART_NAN_F;
-    V3 o = r.o, d = r.d;
-    if (meta.z) xform_ray(sc, meta.z, r, o, d);
+    V3 o, d;
+    xform_ray(sc, meta.z, r, o, d);           // xform 0 is the identity: no branch, one instruction stream
     return rect_root(pp, meta.x, o, d, t_lo, t_hi);
 }
 
@@ -329,6 +330,9 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
 }
 
 #define RTW_STACK 64
+#ifndef RTW_SPECULATIVE
+#define RTW_SPECULATIVE 1
+#endif
 #define RTW_SENTINEL 0x7fffffff
 
 // Closest surface hit over the BVH (replaces hit_hittables :43-55 + bvh_node_hit :290-306 over the whole world).
@@ -362,8 +366,13 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             const int top = sp[-1];                // one predictable local load per visit
             node = none ? top : nearc;
             sp -= none ? 1 : 0;
+#if RTW_SPECULATIVE
             if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = sp[-1]; --sp; }   // postpone first leaf
             if (!__any_sync(__activemask(), searching)) break;
+#else
+            (void)searching;
+            if (node < 0) { leaf = node; node = sp[-1]; --sp; break; }
+#endif
         }
         while (leaf < 0) {
             int code = ~leaf, first = code >> 3, count = (code & 7) + 1;

@@ -384,7 +384,7 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[flatten] %s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     out = FlatScene();
-    DXform ident; std::memset(&ident, 0, sizeof(ident)); ident.m_cos = 1.f;
+    DXform ident; std::memset(&ident, 0, sizeof(ident)); ident.m_cos = 1.f; ident.d_cos = 1.0;
     out.xforms.push_back(ident);
     Flattener fl(g, out, err);
     Chain ch;
