@@ -25,6 +25,14 @@ using namespace rtwd;
 // =================================================================================================
 // kernels
 // =================================================================================================
+#ifdef RTW_INSTRUMENT
+__device__ unsigned long long g_dbg_counters[6];
+extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
+    if (cudaMemcpyFromSymbol(out, g_dbg_counters, 48) != cudaSuccess) return -3;
+    if (reset) { unsigned long long z[6] = {0}; cudaMemcpyToSymbol(g_dbg_counters, z, 48); }
+    return 0;
+}
+#endif
 #define RTW_BLOCK 128
 #define RTW_WARPS (RTW_BLOCK / 32)
 #ifndef RTW_DEFAULT_MODE
@@ -44,6 +52,9 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long rays = 0, units = 0;
+#ifdef RTW_INSTRUMENT
+    unsigned long long dbg[6] = {0, 0, 0, 0, 0, 0};
+#endif
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
@@ -75,9 +86,15 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
                 next += __popc(mask);
             }
             if (!__any_sync(0xffffffffu, alive)) { if (next >= n_items) break; continue; }
+#ifdef RTW_INSTRUMENT
+            const bool was_alive = alive;
+#endif
             if (alive) {
                 V3 add;
                 const int seg0 = ps.segment;
+#ifdef RTW_INSTRUMENT
+                ps.dbg_visits = 0; ps.dbg_prims = 0;
+#endif
                 alive = path_step(sc, prm, ps, add);
                 rays += (unsigned)(ps.segment - seg0);                      // 0 when the depth budget was already spent
                 if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
@@ -86,6 +103,18 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
                     atomicAdd(&acc[warp][pix * 3 + 2], add.z);
                 }
             }
+#ifdef RTW_INSTRUMENT
+            {   // per warp-iteration: lanes alive, sum and max of node visits / prim tests over the lanes
+                int v = was_alive ? ps.dbg_visits : 0, p = was_alive ? ps.dbg_prims : 0, a = was_alive ? 1 : 0;
+                int vs = v, vm = v, pss = p, pm = p, as = a;
+                for (int o = 16; o; o >>= 1) {
+                    vs += __shfl_xor_sync(0xffffffffu, vs, o); vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, o));
+                    pss += __shfl_xor_sync(0xffffffffu, pss, o); pm = max(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+                    as += __shfl_xor_sync(0xffffffffu, as, o);
+                }
+                if (lane == 0) { dbg[0] += 1; dbg[1] += as; dbg[2] += vs; dbg[3] += vm; dbg[4] += pss; dbg[5] += pm; }
+            }
+#endif
         }
         __syncwarp();
         {   // tile -> framebuffer, row 0 = top (y = H-1 of src/main.rs:591)
@@ -102,6 +131,9 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
     // ray statistics: one atomic per warp
     for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
     if (lane == 0) { atomicAdd(stats, rays); atomicAdd(stats + 1, units); }
+#ifdef RTW_INSTRUMENT
+    if (lane == 0) for (int k = 0; k < 6; ++k) atomicAdd(&g_dbg_counters[k], dbg[k]);
+#endif
 }
 
 // The warp-pool kernel (see rtw_pool.cuh): same work units, same Philox keys, same framebuffer protocol as

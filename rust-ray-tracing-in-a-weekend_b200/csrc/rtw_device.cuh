@@ -339,7 +339,19 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
 // "Speculative while-while" (Aila & Laine 2009): every lane keeps descending inner nodes until ALL lanes of the
 // warp hold a leaf (one leaf may be postponed per lane), then the warp intersects leaves together — node visits
 // and primitive tests each run with most lanes active instead of interleaving per lane.
-RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip) {
+#ifdef RTW_INSTRUMENT
+__device__ int g_dbg_visits, g_dbg_prims;
+#define RTW_DBG_VISIT() (++dbg_visits)
+#define RTW_DBG_PRIM() (++dbg_prims)
+#else
+#define RTW_DBG_VISIT()
+#define RTW_DBG_PRIM()
+#endif
+RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip
+#ifdef RTW_INSTRUMENT
+                         , int& dbg_visits, int& dbg_prims
+#endif
+                         ) {
     if (sc.n_bvh_prims == 0) return;
     // exact 1/d: the 2-ulp padding of the slab test (Ize) assumes correctly rounded reciprocals
     V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
@@ -351,6 +363,7 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
     while (node != RTW_SENTINEL) {
         bool searching = true;
         while (node >= 0 && node != RTW_SENTINEL) {
+            RTW_DBG_VISIT();
             const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
@@ -377,6 +390,7 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
         while (leaf < 0) {
             int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
             for (int i = 0; i < count; ++i) {
+                RTW_DBG_PRIM();
                 float t = prim_root(sc, first + i, r, t_min, t_best, skip);
                 if (t == t) { t_best = t; prim_best = first + i; }       // not NaN: accepted, t <= t_best
             }
@@ -488,7 +502,12 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
 template <class R>
 RTW_DEV bool world_hit(const DScene& sc, const TRay& r, float t_min, float t_max, R& g, bool want_uv, HitRec& rec) {
     float t_best = t_max; int prim_best = -1;
+#ifdef RTW_INSTRUMENT
+    int dv = 0, dp = 0;
+    bvh_closest(sc, r, t_min, t_best, prim_best, -1, dv, dp);
+#else
     bvh_closest(sc, r, t_min, t_best, prim_best, -1);
+#endif
     int med_mat = -1; float med_t = 0.0f;
     for (int m = 0; m < sc.n_media; ++m) {
         float t; int mat;
@@ -597,6 +616,9 @@ struct PathState {
     V3 T;                   // throughput; the radiance terms T*emitted / T*background are handed to the caller
     int segment;            // segments traced so far (bounce id of the next one = segment + 1)
     int last_prim;          // primitive the current ray starts on (-1: camera / medium scatter)
+#ifdef RTW_INSTRUMENT
+    int dbg_visits, dbg_prims;
+#endif
     PhiloxRng rng;
 };
 
@@ -617,7 +639,11 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps, V3& 
     ps.rng.set_bounce((uint32_t)ps.segment);
     TRay tr = make_tray(ps.ray);
     float t_best = CUDART_INF_F; int prim_best = -1;
+#ifdef RTW_INSTRUMENT
+    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, ps.dbg_visits, ps.dbg_prims);
+#else
     bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);                       // :25
+#endif
     int med_mat = -1; float med_t = 0.f;
     for (int m = 0; m < sc.n_media; ++m) {
         float t; int mat;
