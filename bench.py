@@ -188,7 +188,7 @@ def main():
     # ---------------- e2e arm: host buffers in, host framebuffer out, every step ----------------------
     e2e_wall, h2d, d2h = 0.0, 0, 0
     host_img = None
-    host_out = np.zeros((H, W, 3), np.float32)          # caller-allocated host framebuffer, reused every step
+    host_out = rtw.pinned_image(H, W)                   # caller-allocated, page-locked host framebuffer, reused every step
     blob_bytes = int(sc_blob_bytes(sc))
     for i in range(2 + args.steps):
         comm.barrier()
@@ -200,7 +200,7 @@ def main():
         else:
             st2 = shared.step(cam, prm)
             if rank == 0:
-                host_img = shared.read()
+                host_img = shared.read(host_out)
             h2d_i, d2h_i = blob_bytes, (W * H * 12 if rank == 0 else 0)
         comm.barrier()
         if i >= 2:

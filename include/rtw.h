@@ -139,6 +139,10 @@ int rtw_scene_commit(rtw_scene*, int32_t n_gpus, int32_t first_device);
  * row-major H x W x 3 float, row 0 = TOP (= y = H-1 of src/main.rs:591). */
 int rtw_render(rtw_scene*, const rtw_camera*, const rtw_render_params*, float* out_rgb_sum, rtw_stats* stats);
 
+/* Page-locked host memory for out_rgb_sum: the D2H of the framebuffer then runs at PCIe speed (optional). */
+void* rtw_host_alloc(uint64_t bytes);
+void rtw_host_free(void* p);
+
 /* write_color (src/math.rs:119-132) on the device: sums -> 8-bit rgb, same row order. */
 int rtw_write_color(const float* rgb_sum, int32_t n_pixels, int32_t spp, uint8_t* out_rgb8);
 

@@ -191,6 +191,10 @@ class Lib:
             f("render_shared").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.POINTER(Stats)]
             f("shared_read").argtypes = [vp, fp]
             f("shared_close").argtypes = [vp]
+            f("host_alloc").argtypes = [C.c_uint64]
+            f("host_alloc").restype = C.c_void_p
+            f("host_free").argtypes = [C.c_void_p]
+            f("host_free").restype = None
             f("debug_flatten").argtypes = [vp, ip, dp]
 
     def check(self, rc):
@@ -204,6 +208,18 @@ class Lib:
         self.check(self.f("camera_new")(_d3(look_from), _d3(look_at), _d3(vup), vfov, aspect, aperture, focus_dist,
                                          time0, time1, C.byref(cam)))
         return cam
+
+    def pinned_image(self, height, width):
+        """H x W x 3 float32 array in page-locked host memory (rtw_host_alloc); falls back to pageable memory."""
+        n = height * width * 3
+        p = self.f("host_alloc")(n * 4) if not self.is_oracle else None
+        if not p:
+            return np.zeros((height, width, 3), np.float32)
+        buf = (C.c_float * n).from_address(p)
+        arr = np.frombuffer(buf, dtype=np.float32).reshape(height, width, 3)
+        arr[:] = 0
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return arr
 
     def philox(self, counter, key):
         counter = np.ascontiguousarray(counter, dtype=np.uint32).reshape(-1, 4)

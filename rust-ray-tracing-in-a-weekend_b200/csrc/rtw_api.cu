@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
 render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
     __shared__ float acc[RTW_WARPS][96];
+    __shared__ float ring[RTW_WARPS][8][64];              // camera-ray ring: o(3) d(3) time meta, 64 entries per warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long rays = 0, units = 0;
@@ -64,28 +65,57 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
         const int tile = (int)(unit / (unsigned)prm.chunks), chunk = (int)(unit % (unsigned)prm.chunks);
         const int s0 = chunk * prm.chunk_spp;
         const int s1 = min(prm.spp, s0 + prm.chunk_spp);
-        const int n_items = 32 * (s1 - s0);
         const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
+        const int tw = min(8, prm.width - tx * 8), th = min(4, prm.height - ty * 4), npix = tw * th;     // ragged edge tiles
+        const int n_items = npix * (s1 - s0);
         acc[warp][lane] = 0.f; acc[warp][lane + 32] = 0.f; acc[warp][lane + 64] = 0.f;
         __syncwarp();
         int next = 0, pix = 0;
+        int ring_head = 0, ring_count = 0;                     // warp-uniform
         bool alive = false;
         PathState ps;
         for (;;) {
+            // ---- path regeneration (main.rs:517-520).  Camera rays are produced 32 at a time by ALL lanes into a
+            // 64-entry ring in shared memory and handed out one by one: the two Philox blocks + get_ray of a new path are
+            // issued once per ~3 iterations at full width instead of every iteration for the ~11 lanes that died.
             const bool need = !alive;
             const unsigned mask = __ballot_sync(0xffffffffu, need);
-            if (mask) {
-                if (need) {
-                    const int idx = next + __popc(mask & lt_mask);
-                    if (idx < n_items) {
-                        pix = idx & 31;
-                        const int x = tx * 8 + (pix & 7), y = ty * 4 + (pix >> 3);
-                        if (x < prm.width && y < prm.height) { path_begin(cam, prm, x, y, s0 + (idx >> 5), ps); alive = true; }
-                    }
+            const int n_need = __popc(mask);
+            if (ring_count < n_need && next < n_items) {
+                const int idx = next + lane;
+                if (idx < n_items) {
+                    const int pl = idx % npix, sample = s0 + idx / npix;
+                    const int px = pl % tw, py = pl / tw;
+                    PathState np;
+                    path_begin(cam, prm, tx * 8 + px, ty * 4 + py, sample, np);
+                    const int e = (ring_head + ring_count + lane) & 63;
+                    float* rg = ring[warp][0] + e;
+                    rg[0] = np.ray.o.x; rg[64] = np.ray.o.y; rg[128] = np.ray.o.z;
+                    rg[192] = np.ray.d.x; rg[256] = np.ray.d.y; rg[320] = np.ray.d.z; rg[384] = np.ray.time;
+                    rg[448] = __int_as_float((py * 8 + px) | (sample << 5));
                 }
-                next += __popc(mask);
+                const int gen = min(32, n_items - next);
+                next += gen; ring_count += gen;
+                __syncwarp();
             }
-            if (!__any_sync(0xffffffffu, alive)) { if (next >= n_items) break; continue; }
+            if (need) {
+                const int rnk = __popc(mask & lt_mask);
+                if (rnk < ring_count) {
+                    const float* rg = ring[warp][0] + ((ring_head + rnk) & 63);
+                    ps.ray.o = mk(rg[0], rg[64], rg[128]); ps.ray.d = mk(rg[192], rg[256], rg[320]); ps.ray.time = rg[384];
+                    const int meta = __float_as_int(rg[448]);
+                    pix = meta & 31;
+                    ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)(meta >> 5));
+                    ps.T = mk(1.f, 1.f, 1.f); ps.segment = 0; ps.last_prim = -1;
+                    alive = true;
+                }
+            }
+            {
+                const int taken = min(n_need, ring_count);
+                ring_head = (ring_head + taken) & 63; ring_count -= taken;
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, alive)) { if (next >= n_items && ring_count == 0) break; continue; }
 #ifdef RTW_INSTRUMENT
             const bool was_alive = alive;
 #endif
@@ -520,7 +550,12 @@ int launch_pool(Replica& r, int slot, const DCamera& dc, const DParams& dp, unsi
 }
 
 // Launch the render kernel on replicas [0, n) against (counter, fb); sync; fill stats.
+// The Philox key schedule lives in a __constant__ symbol: renders of one process are serialised on this mutex
+// (rtw_render is blocking anyway), so concurrent host threads with different seeds cannot interleave set + launch.
+std::mutex g_launch_mutex;
+
 int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp, unsigned int* counter, float* fb, rtw_stats* st, int mode) {
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
     DCamera dc = to_dcamera(*cam);
     uint32_t rk[20];
     for (int k = 0; k < 10; ++k) { rk[2 * k] = dp.seed_lo + 0x9E3779B9u * (uint32_t)k; rk[2 * k + 1] = dp.seed_hi + 0xBB67AE85u * (uint32_t)k; }
@@ -834,6 +869,13 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     return RTW_OK;
 }
 
+void* rtw_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); fail(RTW_ERR_OOM, "cudaMallocHost failed"); return nullptr; }
+    return p;
+}
+void rtw_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 int rtw_write_color(const float* rgb_sum, int32_t n_pixels, int32_t spp, uint8_t* out_rgb8) {
     if (!rgb_sum || !out_rgb8 || n_pixels <= 0 || spp <= 0) return fail(RTW_ERR_INVALID_ARG, "bad argument");
     TRY(need_device());
@@ -1026,6 +1068,7 @@ int rtw_trace_paths(rtw_scene* s, const rtw_camera* cam, const rtw_render_params
     DParams dp; TRY(make_params(*p, 1, dp));
     uint32_t rk[20];
     for (int k = 0; k < 10; ++k) { rk[2 * k] = dp.seed_lo + 0x9E3779B9u * (uint32_t)k; rk[2 * k + 1] = dp.seed_hi + 0xBB67AE85u * (uint32_t)k; }
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
     CUDA_TRY(cudaMemcpyToSymbol(c_philox_rk, rk, sizeof(rk)));
     Scratch sc; int *d_x, *d_y, *d_s, *d_seg; double* d_rgb;
     TRY(sc.up(px, n, d_x)); TRY(sc.up(py, n, d_y)); TRY(sc.up(smp, n, d_s)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_rgb)); TRY(sc.up((int*)nullptr, n, d_seg));

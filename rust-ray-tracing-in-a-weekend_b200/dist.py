@@ -109,9 +109,10 @@ class SharedRender:
         self.comm.barrier()
         return st.as_dict()
 
-    def read(self):
+    def read(self, out=None):
         assert self.comm.rank == 0
-        out = np.zeros((self.h, self.w, 3), np.float32)
+        if out is None:
+            out = np.zeros((self.h, self.w, 3), np.float32)
         self.scene._c("shared_read", out.ctypes.data_as(self.C.POINTER(self.C.c_float)))
         return out
 
