@@ -308,7 +308,7 @@ __global__ void aabb_kernel(int n, const double* __restrict__ bmin, const double
     V3 oi = mk(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
     float e;
     hit[i] = slab((float)bmin[3 * i], (float)bmax[3 * i], (float)bmin[3 * i + 1], (float)bmax[3 * i + 1], (float)bmin[3 * i + 2],
-                  (float)bmax[3 * i + 2], inv, oi, t_min, t_max, e) ? 1 : 0;
+                  (float)bmax[3 * i + 2], inv, oi, slab_slack(oi), t_min, t_max, e) ? 1 : 0;
 }
 
 __global__ void scatter_kernel(DScene sc, int mat, int n, const double* __restrict__ ro, const double* __restrict__ rd, const double* __restrict__ rt,

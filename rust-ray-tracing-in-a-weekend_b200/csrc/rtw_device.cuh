@@ -316,15 +316,18 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
     return rect_root(pp, meta.x, o, d, t_lo, t_hi);
 }
 
-// AABB::hit (src/aabb.rs:77-103) for the two children of a node, with precomputed 1/d and o/d.  Conservative
-// (closed interval, upper bound padded by 2 ulp — Ize, "Robust BVH ray traversal") so that the f32 slab test can
-// never cull a primitive the f64 reference would hit; the primitive tests decide.
-RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float t_lo, float t_hi, float& t_enter) {
+// AABB::hit (src/aabb.rs:77-103) for the two children of a node, with precomputed 1/d and o/d.  Conservative: closed
+// interval, boxes rounded outward, and the exit distance padded by 2 ulp (Ize, "Robust BVH ray traversal") PLUS an
+// absolute slack of 4 ulp of max|o/d| — the fma form t = p*inv - o*inv carries the rounding of o*inv, which is not
+// relative to t when the origin is far from the box.  The f32 test can then never cull a primitive the f64 reference
+// would hit; the primitive tests decide.  `slack` is per ray (see slab_slack), folded into one FFMA.
+RTW_DEV float slab_slack(V3 oi) { return 2.384185791015625e-07f * fmaxf(fmaxf(fabsf(oi.x), fabsf(oi.y)), fabsf(oi.z)); }
+RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
     float x0 = fmaf(mnx, inv.x, -oi.x), x1 = fmaf(mxx, inv.x, -oi.x);
     float y0 = fmaf(mny, inv.y, -oi.y), y1 = fmaf(mxy, inv.y, -oi.y);
     float z0 = fmaf(mnz, inv.z, -oi.z), z1 = fmaf(mxz, inv.z, -oi.z);
     float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
-    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)) * 1.0000004f;
+    float tf = fmaf(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)), 1.0000004f, slack);
     t_enter = tn;
     return tn <= tf;
 }
@@ -356,6 +359,7 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
     // exact 1/d: the 2-ulp padding of the slab test (Ize) assumes correctly rounded reciprocals
     V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     V3 oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
+    const float slack = slab_slack(oi);
     int stack[RTW_STACK];
     stack[0] = RTW_SENTINEL;
     int* sp = stack + 1;                          // points at the next free entry
@@ -368,8 +372,8 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
             float e0, e1;
-            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, t_min, t_best, e0);
-            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, t_min, t_best, e1);
+            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, t_min, t_best, e0);
+            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, t_min, t_best, e1);
             // straight-line child selection: nearer hit child next, the other one pushed
             const bool second = h1 && (!h0 || e1 < e0);
             const int nearc = second ? ch.y : ch.x, farc = second ? ch.x : ch.y;

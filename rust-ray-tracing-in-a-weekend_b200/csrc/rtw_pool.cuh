@@ -112,7 +112,7 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
     int q_next = 0;
     bool active = false;
     int slot = 0;
-    TRay r; V3 inv = mk(0, 0, 0), oi = mk(0, 0, 0);
+    TRay r; V3 inv = mk(0, 0, 0), oi = mk(0, 0, 0); float slack = 0.f;
     float t_best = 0.f; int prim_best = -1, skip = -1;
     int stack[RTW_STACK]; int sp = 1, node = RTW_SENTINEL, leaf = 0;
     stack[0] = RTW_SENTINEL;
@@ -127,6 +127,7 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                     r = make_tray(ray);
                     inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
                     oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
+                    slack = slab_slack(oi);
                     t_best = CUDART_INF_F; prim_best = -1; skip = P.last[slot];
                     sp = 1; leaf = 0; node = sc.n_bvh_prims ? 0 : RTW_SENTINEL;
                     active = true; ++rays;
@@ -143,8 +144,8 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                     float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
                     int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
                     float e0, e1;
-                    bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, prm.t_min, t_best, e0);
-                    bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, prm.t_min, t_best, e1);
+                    bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, prm.t_min, t_best, e0);
+                    bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, prm.t_min, t_best, e1);
                     if (!h0 && !h1) node = stack[--sp];
                     else {
                         node = h0 ? n3.x : n3.y;

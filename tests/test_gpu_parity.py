@@ -124,7 +124,11 @@ def test_aabb_is_conservative_and_agrees(gpu, orc):
         t0, t1 = (mn - o) / d, (mx - o) / d
     lo, hi = np.minimum(t0, t1).max(1), np.maximum(t0, t1).min(1)
     lo = np.maximum(lo, 0.001)
-    degenerate = np.abs(hi - lo) <= 1e-4 * np.maximum(np.abs(hi), 1.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        oi = np.nanmax(np.abs(o / d), axis=1)
+    # the device pads the exit distance by 2 ulp and by 4 ulp of max|o/d| (rounding of the fma form): agreement is
+    # required wherever the f64 interval is wider than that
+    degenerate = np.abs(hi - lo) <= 1e-4 * np.maximum(np.abs(hi), 1.0) + 1e-6 * oi
     assert not (ga != gb)[~degenerate].any()
     assert 0.2 < gb.mean() < 0.95
 
