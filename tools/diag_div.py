@@ -1,3 +1,5 @@
+"""Lane-efficiency diagnosis: needs the instrumented library (make -C rust-ray-tracing-in-a-weekend_b200/csrc instr) and
+RTW_LIB_PATH=.../variants/instr.so.  Prints, per warp iteration, live lanes and mean vs max traversal length."""
 import os, sys, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, rtw_pkg
