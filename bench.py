@@ -206,6 +206,10 @@ def main():
         if i >= 2:
             e2e_wall += time.perf_counter() - t0
             h2d, d2h = h2d_i, d2h_i
+    t0 = time.perf_counter()
+    for _ in range(5):
+        sc.commit(1, local_rank)
+    commit_ms = 1e3 * (time.perf_counter() - t0) / 5          # flatten + SAH BVH + upload, reported separately
     e2e_wall = comm.reduce_max(e2e_wall)
     h2d = comm.reduce_sum(h2d)
     d2h = comm.reduce_sum(d2h)
@@ -229,7 +233,7 @@ def main():
             "config": {"workload": f"book-1 random_scene (seed 1, 485 spheres) {W}x{H} {spp}spp depth {DEPTH}", "paths_per_step": n_paths,
                        "l2": "256 MiB buffer written between timed iterations", "parallelism": f"tiles x sample-chunks from one atomic counter over {world} GPU(s)",
                        "vs_baseline_ref": "README.md:6 (10 CPU threads, older commit of the scene)"},
-            "wall_time_s": wall / args.steps, "kernel_ms_per_step": kernel_ms, "rays_per_path": rays / (n_paths * args.steps),
+            "wall_time_s": wall / args.steps, "kernel_ms_per_step": kernel_ms, "commit_ms": commit_ms, "rays_per_path": rays / (n_paths * args.steps),
             "mrays_per_s": rays / wall / 1e6,
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * e2e_wall / args.steps, "includes": "scene flatten + BVH build + upload, render, framebuffer D2H"},

@@ -504,6 +504,23 @@ def test_full_resolution_configs(pkg, gpu, orc, name, W, H, spp):
     assert np.abs(blk(small) - blk(refm)).max() <= 0.12 * max(blk(refm).max(), 0.05)
 
 
+def test_final_scene_full_config(pkg, gpu):
+    """BASELINE config 4 at FULL size (800x800, 10 000 spp, depth 50 = 6.4 G paths, ~8 s): finite, non-negative, the
+    per-pixel sums of the first 1 000 samples (a separate render with the same Philox keys) are a prefix of it — the
+    sample index is a counter coordinate, so mean(10 000 spp) must sit within MC noise of mean(1 000 spp) — and f32
+    accumulation of 10 000 terms up to 7.0 stays within 1e-3 relative of the image mean."""
+    sc, spec = pkg.scenes.build(gpu, "final_scene")
+    sc.commit(1, 0)
+    cam = spec.camera(gpu, 800, 800)
+    full, st = sc.render(cam, pkg.make_params(800, 800, 10000, background=spec.background, seed=1))
+    part, _ = sc.render(cam, pkg.make_params(800, 800, 1000, background=spec.background, seed=1))
+    assert st["paths"] == 6_400_000_000 and np.isfinite(full).all() and full.min() >= 0
+    m_full, m_part = full.mean() / 10000, part.mean() / 1000
+    assert abs(m_full - m_part) <= 0.01 * m_full
+    blk = lambda x: x.reshape(8, 100, 8, 100, 3).mean((1, 3))
+    assert np.abs(blk(full) / 10000 - blk(part) / 1000).max() <= 0.05 * blk(full).max() / 10000
+
+
 def test_render_edge_cases(pkg, gpu, orc):
     # empty world: every sample returns the background (src/main.rs:37)
     sc = pkg.Scene(gpu)
