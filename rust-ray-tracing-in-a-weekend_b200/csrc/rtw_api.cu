@@ -48,8 +48,9 @@ extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
 render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
-    __shared__ float acc[RTW_WARPS][96];
-    __shared__ float ring[RTW_WARPS][8][64];              // camera-ray ring: o(3) d(3) time meta, 64 entries per warp
+    __shared__ float acc[RTW_WARPS][96];                  // per-warp tile accumulator (32 px x rgb)
+    __shared__ float ring[RTW_WARPS][12][64];             // secondary-ray ring: o(3) d(3) time T(3) last_prim meta, 64 per warp
+    __shared__ int tlist[RTW_WARPS][RTW_TILE_LIST];       // primitives the tile's primary rays can touch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long rays = 0, units = 0;
@@ -67,75 +68,115 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
         const int s1 = min(prm.spp, s0 + prm.chunk_spp);
         const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
         const int tw = min(8, prm.width - tx * 8), th = min(4, prm.height - ty * 4), npix = tw * th;     // ragged edge tiles
-        const int n_items = npix * (s1 - s0);
+        const int n_items = prm.max_depth >= 1 ? npix * (s1 - s0) : 0;
         acc[warp][lane] = 0.f; acc[warp][lane + 32] = 0.f; acc[warp][lane + 64] = 0.f;
+        // every primitive a primary ray of this tile can touch (-1: too many, traverse instead)
+        const int list_n = build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp],
+                                           reinterpret_cast<int*>(ring[warp][0]), lane);
         __syncwarp();
+        if (lane == 0) { if (list_n >= 0) atomicAdd(stats + 2, (unsigned long long)list_n); else atomicAdd(stats + 3, 1ull); }
         int next = 0, pix = 0;
         int ring_head = 0, ring_count = 0;                     // warp-uniform
         bool alive = false;
         PathState ps;
+        // Each iteration of this loop is EITHER a primary batch or a secondary step; both run the SAME copy of the
+        // closest-hit and shading code (two inlined copies doubled the kernel to 145 KB and cost 40 % in i-cache misses).
+        //  primary batch : taken when the ring cannot serve the lanes that need a path.  All 32 lanes queue their
+        //                  in-flight path in the ring, start a new camera path each (main.rs:517-520), intersect it with the tile's
+        //                  candidate list (dense: same trip count in every lane) and shade it.  Paths that end on their
+        //                  first hit are accumulated right away; the survivors' SECONDARY rays go into the ring.
+        //  secondary step: dead lanes take a ray from the ring, every live lane traces + shades one more segment.
+        // The divergent BVH traversal therefore only ever sees secondary rays (63 % of the rays in C1).
         for (;;) {
-            // ---- path regeneration (main.rs:517-520).  Camera rays are produced 32 at a time by ALL lanes into a
-            // 64-entry ring in shared memory and handed out one by one: the two Philox blocks + get_ray of a new path are
-            // issued once per ~3 iterations at full width instead of every iteration for the ~11 lanes that died.
             const bool need = !alive;
             const unsigned mask = __ballot_sync(0xffffffffu, need);
             const int n_need = __popc(mask);
-            if (ring_count < n_need && next < n_items) {
+            const bool primary = ring_count < n_need && next < n_items;      // warp-uniform
+            bool work = false;
+            int wpix = 0;
+            if (primary) {
+                // in-flight paths go to the back of the ring (their segment count travels in the entry); after the batch
+                // every lane is free and refills from the ring in FIFO order
+                const unsigned ma = __ballot_sync(0xffffffffu, alive);
+                if (alive) {
+                    float* rg = ring[warp][0] + ((ring_head + ring_count + __popc(ma & lt_mask)) & 63);
+                    rg[0] = ps.ray.o.x; rg[64] = ps.ray.o.y; rg[128] = ps.ray.o.z;
+                    rg[192] = ps.ray.d.x; rg[256] = ps.ray.d.y; rg[320] = ps.ray.d.z; rg[384] = ps.ray.time;
+                    rg[448] = ps.T.x; rg[512] = ps.T.y; rg[576] = ps.T.z;
+                    rg[640] = __int_as_float(ps.last_prim);
+                    rg[704] = __int_as_float(pix | (ps.segment << 5) | ((int)ps.rng.sample << 11));
+                    alive = false;
+                }
+                ring_count += __popc(ma);
                 const int idx = next + lane;
                 if (idx < n_items) {
                     const int pl = idx % npix, sample = s0 + idx / npix;
                     const int px = pl % tw, py = pl / tw;
-                    PathState np;
-                    path_begin(cam, prm, tx * 8 + px, ty * 4 + py, sample, np);
-                    const int e = (ring_head + ring_count + lane) & 63;
-                    float* rg = ring[warp][0] + e;
-                    rg[0] = np.ray.o.x; rg[64] = np.ray.o.y; rg[128] = np.ray.o.z;
-                    rg[192] = np.ray.d.x; rg[256] = np.ray.d.y; rg[320] = np.ray.d.z; rg[384] = np.ray.time;
-                    rg[448] = __int_as_float((py * 8 + px) | (sample << 5));
+                    wpix = py * 8 + px;
+                    path_begin(cam, prm, tx * 8 + px, ty * 4 + py, sample, ps);
+                    ps.segment = 1;
+                    ps.rng.set_bounce(1u);
+                    work = true;
                 }
-                const int gen = min(32, n_items - next);
-                next += gen; ring_count += gen;
-                __syncwarp();
-            }
-            if (need) {
-                const int rnk = __popc(mask & lt_mask);
-                if (rnk < ring_count) {
-                    const float* rg = ring[warp][0] + ((ring_head + rnk) & 63);
-                    ps.ray.o = mk(rg[0], rg[64], rg[128]); ps.ray.d = mk(rg[192], rg[256], rg[320]); ps.ray.time = rg[384];
-                    const int meta = __float_as_int(rg[448]);
-                    pix = meta & 31;
-                    ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)(meta >> 5));
-                    ps.T = mk(1.f, 1.f, 1.f); ps.segment = 0; ps.last_prim = -1;
-                    alive = true;
+            } else {
+                if (need) {
+                    const int rnk = __popc(mask & lt_mask);
+                    if (rnk < ring_count) {
+                        const float* rg = ring[warp][0] + ((ring_head + rnk) & 63);
+                        ps.ray.o = mk(rg[0], rg[64], rg[128]); ps.ray.d = mk(rg[192], rg[256], rg[320]); ps.ray.time = rg[384];
+                        ps.T = mk(rg[448], rg[512], rg[576]);
+                        ps.last_prim = __float_as_int(rg[640]);
+                        const int meta = __float_as_int(rg[704]);
+                        pix = meta & 31;
+                        ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)(meta >> 11));
+                        ps.segment = (meta >> 5) & 63;
+                        alive = true;
+                    }
                 }
-            }
-            {
                 const int taken = min(n_need, ring_count);
                 ring_head = (ring_head + taken) & 63; ring_count -= taken;
-            }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, alive)) { if (next >= n_items && ring_count == 0) break; continue; }
-#ifdef RTW_INSTRUMENT
-            const bool was_alive = alive;
-#endif
-            if (alive) {
-                V3 add;
-                const int seg0 = ps.segment;
-#ifdef RTW_INSTRUMENT
-                ps.dbg_visits = 0; ps.dbg_prims = 0;
-#endif
-                alive = path_step(sc, prm, ps, add);
-                rays += (unsigned)(ps.segment - seg0);                      // 0 when the depth budget was already spent
-                if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
-                    atomicAdd(&acc[warp][pix * 3 + 0], add.x);
-                    atomicAdd(&acc[warp][pix * 3 + 1], add.y);
-                    atomicAdd(&acc[warp][pix * 3 + 2], add.z);
+                if (!__any_sync(0xffffffffu, alive)) break;     // ring empty, nothing in flight, no items left
+                if (alive) {
+                    if (ps.segment >= prm.max_depth) alive = false;                          // main.rs:21-23
+                    else { ps.segment++; ps.rng.set_bounce((uint32_t)ps.segment); work = true; wpix = pix; }
                 }
             }
 #ifdef RTW_INSTRUMENT
-            {   // per warp-iteration: lanes alive, sum and max of node visits / prim tests over the lanes
-                int v = was_alive ? ps.dbg_visits : 0, p = was_alive ? ps.dbg_prims : 0, a = was_alive ? 1 : 0;
+            int dbg_v = 0, dbg_p = 0;
+#endif
+            // ---- closest surface hit (main.rs:25)
+            TRay tr; float t_best = CUDART_INF_F; int prim_best = -1;
+            if (work) {
+                tr = make_tray(ps.ray);
+                if (primary && list_n >= 0) {
+                    for (int i = 0; i < list_n; ++i) {
+                        const int pi = tlist[warp][i];
+                        const float t = prim_root(sc, pi, tr, prm.t_min, t_best, -1);
+                        if (t == t) { t_best = t; prim_best = pi; }
+                    }
+                } else {
+#ifdef RTW_INSTRUMENT
+                    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, dbg_v, dbg_p);
+#else
+                    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);
+#endif
+                }
+            }
+            // ---- media, miss, hit record, emitted + scatter (main.rs:26-37)
+            bool cont = false;
+            if (work) {
+                V3 add;
+                cont = path_finish(sc, prm, ps, tr, t_best, prim_best, add);
+                ++rays;
+                if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
+                    atomicAdd(&acc[warp][wpix * 3 + 0], add.x);
+                    atomicAdd(&acc[warp][wpix * 3 + 1], add.y);
+                    atomicAdd(&acc[warp][wpix * 3 + 2], add.z);
+                }
+            }
+#ifdef RTW_INSTRUMENT
+            if (!primary) {   // per secondary step: lanes at work, sum and max of node visits / prim tests over the lanes
+                int v = dbg_v, p = dbg_p, a = work ? 1 : 0;
                 int vs = v, vm = v, pss = p, pm = p, as = a;
                 for (int o = 16; o; o >>= 1) {
                     vs += __shfl_xor_sync(0xffffffffu, vs, o); vm = max(vm, __shfl_xor_sync(0xffffffffu, vm, o));
@@ -145,6 +186,20 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
                 if (lane == 0) { dbg[0] += 1; dbg[1] += as; dbg[2] += vs; dbg[3] += vm; dbg[4] += pss; dbg[5] += pm; }
             }
 #endif
+            if (primary) {
+                const unsigned mc = __ballot_sync(0xffffffffu, cont);
+                if (cont) {
+                    float* rg = ring[warp][0] + ((ring_head + ring_count + __popc(mc & lt_mask)) & 63);
+                    rg[0] = ps.ray.o.x; rg[64] = ps.ray.o.y; rg[128] = ps.ray.o.z;
+                    rg[192] = ps.ray.d.x; rg[256] = ps.ray.d.y; rg[320] = ps.ray.d.z; rg[384] = ps.ray.time;
+                    rg[448] = ps.T.x; rg[512] = ps.T.y; rg[576] = ps.T.z;
+                    rg[640] = __int_as_float(ps.last_prim);
+                    rg[704] = __int_as_float(wpix | (ps.segment << 5) | ((int)ps.rng.sample << 11));
+                }
+                ring_count += __popc(mc);
+                next += min(32, n_items - next);
+                __syncwarp();
+            } else if (work) alive = cont;
         }
         __syncwarp();
         {   // tile -> framebuffer, row 0 = top (y = H-1 of src/main.rs:591)
@@ -563,7 +618,7 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         Replica& r = s->reps[i];
         CUDA_TRY(cudaSetDevice(r.device));
         CUDA_TRY(cudaMemcpyToSymbolAsync(c_philox_rk, rk, sizeof(rk), 0, cudaMemcpyHostToDevice, r.stream));
-        CUDA_TRY(cudaMemsetAsync(r.stats, 0, 16, r.stream));
+        CUDA_TRY(cudaMemsetAsync(r.stats, 0, 32, r.stream));
         CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
         switch (mode) {
         case 1: TRY(launch_pool<64>(r, 0, dc, dp, counter, fb)); break;
@@ -582,9 +637,10 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         CUDA_TRY(cudaStreamSynchronize(r.stream));
         float ms = 0; CUDA_TRY(cudaEventElapsedTime(&ms, r.ev0, r.ev1));
         if (ms > ms_max) ms_max = ms;
-        unsigned long long h[2];
-        CUDA_TRY(cudaMemcpy(h, r.stats, 16, cudaMemcpyDeviceToHost));
+        unsigned long long h[4];
+        CUDA_TRY(cudaMemcpy(h, r.stats, 32, cudaMemcpyDeviceToHost));
         rays += h[0];
+        if (getenv("RTW_DEBUG_STATS") && h[1]) fprintf(stderr, "[rtw] device %d: units %llu, mean tile-list length %.2f, list overflows %llu\n", r.device, h[1], (double)h[2] / (double)h[1], h[3]);
         if (st && i < 8) st->units_per_device[i] = h[1];
     }
     if (st) { st->ms_render = ms_max; st->rays = rays; st->kernel_launches += n_rep; st->n_devices = n_rep; }
@@ -810,7 +866,7 @@ int rtw_scene_commit(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
             r.device = first_device + i;
             CUDA_TRY(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreate(&r.ev0)); CUDA_TRY(cudaEventCreate(&r.ev1));
-            CUDA_TRY(cudaMalloc(&r.stats, 16));
+            CUDA_TRY(cudaMalloc(&r.stats, 32));
             int sms = 0, per_sm = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, RTW_BLOCK, 0));

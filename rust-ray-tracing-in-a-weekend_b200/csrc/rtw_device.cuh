@@ -635,19 +635,11 @@ RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, in
     ps.segment = 0; ps.last_prim = -1;
 }
 
-// One level of ray_color.  Returns true while the path continues; `add` = this level's radiance term (often 0).
-RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps, V3& add) {
+// Second half of one level of ray_color: media (list order, after the surfaces), miss -> background, otherwise
+// hit record + Material::emitted/scatter.  `tr`/(t_best, prim_best) = the segment's ray and its closest surface hit.
+// Returns true while the path continues; `add` = this level's radiance term (often 0).
+RTW_DEV bool path_finish(const DScene& sc, const DParams& prm, PathState& ps, const TRay& tr, float t_best, int prim_best, V3& add) {
     add = mk(0.f, 0.f, 0.f);
-    if (ps.segment >= prm.max_depth) return false;                                         // :21-23
-    ps.segment++;
-    ps.rng.set_bounce((uint32_t)ps.segment);
-    TRay tr = make_tray(ps.ray);
-    float t_best = CUDART_INF_F; int prim_best = -1;
-#ifdef RTW_INSTRUMENT
-    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, ps.dbg_visits, ps.dbg_prims);
-#else
-    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);                       // :25
-#endif
     int med_mat = -1; float med_t = 0.f;
     for (int m = 0; m < sc.n_media; ++m) {
         float t; int mat;
@@ -674,6 +666,135 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps, V3& 
     ps.ray = scattered;
     ps.last_prim = prim_best >= 0 ? prim_best : -1;
     return true;
+}
+
+// One level of ray_color: closest hit through the BVH, then path_finish.
+RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps, V3& add) {
+    add = mk(0.f, 0.f, 0.f);
+    if (ps.segment >= prm.max_depth) return false;                                         // :21-23
+    ps.segment++;
+    ps.rng.set_bounce((uint32_t)ps.segment);
+    TRay tr = make_tray(ps.ray);
+    float t_best = CUDART_INF_F; int prim_best = -1;
+#ifdef RTW_INSTRUMENT
+    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, ps.dbg_visits, ps.dbg_prims);
+#else
+    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);                       // :25
+#endif
+    return path_finish(sc, prm, ps, tr, t_best, prim_best, add);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile culling for PRIMARY rays.  All camera rays of one work unit leave a lens disk of radius R and cross an 8x4-pixel
+// window of the focus plane: origin and direction are confined to two small boxes (interval arithmetic over pixel
+// range, jitter and lens offset; src/camera.rs:58-66, src/main.rs:517-518).  One conservative interval-slab walk of
+// the BVH per unit collects every primitive such a ray could touch (moving spheres: node boxes span the shutter);
+// the unit's thousands of primary rays then test that short list instead of traversing — dense, same trip count in
+// every lane.  Exactness: the list is a superset of what any of those rays can hit, the primitive tests are the same.
+// ------------------------------------------------------------------------------------------------
+#define RTW_TILE_LIST 48
+
+// Lens box L (where every ray starts, tau = 0) and focus-plane window Wd (where every ray is at tau = 1; it does not
+// depend on the lens offset: o + d = origin + llc_rel + s h + t v).  A ray of the tile is at (1 - tau) l + tau w for some
+// l in L, w in Wd — keeping that correlation makes the bundle as thin as the pixel window near the focus plane instead
+// of one lens diameter wide.
+struct RayBounds { float ll[3], lh[3], wl[3], wh[3]; };
+
+RTW_DEV RayBounds tile_ray_bounds(const DCamera& c, const DParams& prm, int x0, int y0, int tw, int th) {
+    const float s_lo = (float)x0 / ((float)prm.width - 1.0f), s_hi = (float)(x0 + tw) / ((float)prm.width - 1.0f);
+    const float t_lo = (float)y0 / ((float)prm.height - 1.0f), t_hi = (float)(y0 + th) / ((float)prm.height - 1.0f);
+    const float sc_ = 0.5f * (s_lo + s_hi), ds = 0.5f * (s_hi - s_lo), tc = 0.5f * (t_lo + t_hi), dt = 0.5f * (t_hi - t_lo);
+    const float R = fabsf(c.lens_radius);
+    const float o[3] = {c.ox, c.oy, c.oz}, l[3] = {c.lx, c.ly, c.lz}, h[3] = {c.hx, c.hy, c.hz}, v[3] = {c.vx, c.vy, c.vz};
+    const float u[3] = {c.ux, c.uy, c.uz}, w[3] = {c.wx, c.wy, c.wz};
+    RayBounds b;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float off = R * (fabsf(u[a]) + fabsf(w[a]));
+        const float wc = o[a] + l[a] + sc_ * h[a] + tc * v[a];
+        const float wh_ = fabsf(h[a]) * ds + fabsf(v[a]) * dt;
+        const float pad = 2e-5f * (fabsf(o[a]) + fabsf(wc) + off + wh_) + 1e-6f;      // f32 rounding of the real rays
+        b.ll[a] = o[a] - off - pad; b.lh[a] = o[a] + off + pad;
+        b.wl[a] = wc - wh_ - pad;   b.wh[a] = wc + wh_ + pad;
+    }
+    return b;
+}
+
+// tau-interval on which  x + tau * dx <= hi  (le = true)  or  x + tau * dx >= lo  (le = false), intersected into [a, b]
+RTW_DEV void clip_linear(float x, float dx, float bound, bool le, float& a, float& b) {
+    const float n = bound - x;
+    if (dx == 0.0f) { if (le ? (n < 0.0f) : (n > 0.0f)) { a = 1.0f; b = 0.0f; } return; }
+    const float t = n / dx;
+    if ((dx > 0.0f) == le) b = fminf(b, t); else a = fmaxf(a, t);
+}
+
+// Could ANY ray of the tile hit the box for some tau >= t_min?  Conservative (per-axis intervals).
+RTW_DEV bool bounds_hit_box(const RayBounds& rb, float mnx, float mxx, float mny, float mxy, float mnz, float mxz, float t_min) {
+    const float mn[3] = {mnx, mny, mnz}, mx[3] = {mxx, mxy, mxz};
+    // region A: tau in [t_min, 1]: position in [ll + tau (wl - ll), lh + tau (wh - lh)]
+    float a0 = t_min, a1 = 1.0f;
+    // region B: tau in [1, inf):  (1 - tau) <= 0 swaps the lens bounds: [lh + tau (wl - lh), ll + tau (wh - ll)]
+    float b0 = 1.0f, b1 = CUDART_INF_F;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        clip_linear(rb.ll[k], rb.wl[k] - rb.ll[k], mx[k], true, a0, a1);
+        clip_linear(rb.lh[k], rb.wh[k] - rb.lh[k], mn[k], false, a0, a1);
+        clip_linear(rb.lh[k], rb.wl[k] - rb.lh[k], mx[k], true, b0, b1);
+        clip_linear(rb.ll[k], rb.wh[k] - rb.ll[k], mn[k], false, b0, b1);
+    }
+    const float sa = 1e-5f * (fabsf(a0) + fabsf(a1)) + 1e-6f, sb = 1e-5f * (fabsf(b0) + (b1 < CUDART_INF_F ? fabsf(b1) : 0.0f)) + 1e-6f;
+    return (a0 <= a1 + sa) || (b0 <= b1 + sb);
+}
+
+// Warp-cooperative, breadth-first walk of the BVH with the tile's ray bundle: each lane tests one (node, child) pair
+// per round, surviving inner children form the next frontier, surviving leaves append their primitives to `list`.
+// `scratch` = 2 x 64 frontier ints + 2 counters of per-warp shared memory (the ring, empty at unit start).
+// Returns the number of candidates, or -1 when the list (RTW_TILE_LIST) or a frontier (64) overflows — the caller
+// then traverses the BVH per ray as usual.
+RTW_DEV int build_tile_list(const DScene& sc, const RayBounds& rb, float t_min, int* list, int* scratch, int lane) {
+    if (sc.n_bvh_prims == 0) return 0;
+    int* front[2] = {scratch, scratch + 64};
+    int* cnt = scratch + 128;                    // [0] next frontier size, [1] list size
+    int cur = 0, n_front = 1;
+    if (lane == 0) { front[0][0] = 0; cnt[0] = 0; cnt[1] = 0; }
+    __syncwarp();
+    bool overflow = false;
+    while (n_front > 0) {
+        const int n_tests = 2 * n_front;
+        for (int base = 0; base < n_tests; base += 32) {
+            const int i = base + lane;
+            if (i < n_tests) {
+                const int node = front[cur][i >> 1], c = i & 1;
+                const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+                const float4 bx = __ldg(np + c), n2 = __ldg(np + 2);
+                const int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
+                const int child = c ? ch.y : ch.x;
+                const bool dup = c && ch.y == ch.x;                      // single-leaf root fills both slots
+                if (!dup && bounds_hit_box(rb, bx.x, bx.y, bx.z, bx.w, c ? n2.z : n2.x, c ? n2.w : n2.y, t_min)) {
+                    if (child >= 0) {
+                        const int pos = atomicAdd(&cnt[0], 1);
+                        if (pos < 64) front[cur ^ 1][pos] = child;
+                    } else {
+                        const int code = ~child, first = code >> 3, count = (code & 7) + 1;
+                        const int pos = atomicAdd(&cnt[1], count);
+                        if (pos + count <= RTW_TILE_LIST) for (int k = 0; k < count; ++k) list[pos + k] = first + k;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        n_front = cnt[0];
+        overflow |= n_front > 64 || cnt[1] > RTW_TILE_LIST;
+        __syncwarp();
+        if (lane == 0) cnt[0] = 0;
+        cur ^= 1;
+        if (overflow) break;
+        __syncwarp();
+    }
+    __syncwarp();
+    const int n = cnt[1];
+    __syncwarp();
+    return overflow ? -1 : n;
 }
 
 }  // namespace rtwd
