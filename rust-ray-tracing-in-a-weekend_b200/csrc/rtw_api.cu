@@ -45,6 +45,7 @@ extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
 #define RTW_MIN_BLOCKS 8
 #endif
 
+template <int F>
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
 render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
@@ -151,14 +152,14 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
                 if (primary && list_n >= 0) {
                     for (int i = 0; i < list_n; ++i) {
                         const int pi = tlist[warp][i];
-                        const float t = prim_root(sc, pi, tr, prm.t_min, t_best, -1);
+                        const float t = prim_root<F>(sc, pi, tr, prm.t_min, t_best, -1);
                         if (t == t) { t_best = t; prim_best = pi; }
                     }
                 } else {
 #ifdef RTW_INSTRUMENT
-                    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, dbg_v, dbg_p);
+                    bvh_closest<F>(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, dbg_v, dbg_p);
 #else
-                    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);
+                    bvh_closest<F>(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);
 #endif
                 }
             }
@@ -166,7 +167,7 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
             bool cont = false;
             if (work) {
                 V3 add;
-                cont = path_finish(sc, prm, ps, tr, t_best, prim_best, add);
+                cont = path_finish<F>(sc, prm, ps, tr, t_best, prim_best, add);
                 ++rays;
                 if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
                     atomicAdd(&acc[warp][wpix * 3 + 0], add.x);
@@ -625,7 +626,19 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         case 2: TRY(launch_pool<128>(r, 1, dc, dp, counter, fb)); break;
         case 3: TRY(launch_pool<192>(r, 2, dc, dp, counter, fb)); break;
         case 4: TRY(launch_pool<256>(r, 3, dc, dp, counter, fb)); break;
-        default: render_kernel<<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats);
+        default: {
+            // smallest kernel variant that covers the scene's features (code size = instruction-cache pressure)
+            const int f = s->flat.features;
+#define RTW_TRY_VARIANT(V) if ((f & ~(V)) == 0) { render_kernel<V><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); break; }
+            RTW_TRY_VARIANT(0)                                         // spheres, solid / checker         (C1, two_spheres)
+            RTW_TRY_VARIANT(FEAT_NOISE)                                // + Perlin                         (two_perlin_spheres)
+            RTW_TRY_VARIANT(FEAT_IMAGE)                                // + image                          (earth)
+            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM)                    // rects, boxes, instances          (cornell_box)
+            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM | FEAT_NOISE)       //                                  (simple_light)
+            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM | FEAT_MEDIA)       // + media                          (cornell_box_smoke)
+            RTW_TRY_VARIANT(FEAT_ALL)                                  //                                  (final_scene)
+#undef RTW_TRY_VARIANT
+        }
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
@@ -869,7 +882,7 @@ int rtw_scene_commit(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
             CUDA_TRY(cudaMalloc(&r.stats, 32));
             int sms = 0, per_sm = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, RTW_BLOCK, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FEAT_ALL>, RTW_BLOCK, 0));
             if (per_sm < 1) per_sm = 1;
             r.grid = sms * per_sm; r.sms = sms;
             for (int k = 0; k < 4; ++k) r.pool_grid[k] = 0;

@@ -15,6 +15,11 @@
 namespace rtwd {
 
 #define RTW_DEV __device__ __forceinline__
+
+// Scene features a kernel instantiation must support.  The render kernel is compiled twice: FEAT_ALL and a lean
+// variant for scenes made of (moving) spheres with solid / checker textures only (book-1: config 1) — the full
+// kernel is 90 KB of SASS and the instruction cache is the first thing it runs out of (ncu: stall_no_instruction).
+enum { FEAT_RECT = 1, FEAT_XFORM = 2, FEAT_MEDIA = 4, FEAT_NOISE = 8, FEAT_IMAGE = 16, FEAT_ALL = 31 };
 #define RTW_PI_F 3.14159265358979323846f
 
 // ------------------------------------------------------------------------------------------------
@@ -173,6 +178,7 @@ RTW_DEV float perlin_turb(const uint8_t* __restrict__ tbl, V3 p, int depth) {
 // ------------------------------------------------------------------------------------------------
 // src/texture.rs:30-75 — get_color_value
 // ------------------------------------------------------------------------------------------------
+template <int F = FEAT_ALL>
 RTW_DEV V3 texture_value(const DScene& sc, int tex, float u, float v, V3 p) {
     const float4* tp = reinterpret_cast<const float4*>(sc.texs + tex);
     float4 t0 = __ldg(tp), t1 = __ldg(tp + 1);
@@ -182,8 +188,9 @@ RTW_DEV V3 texture_value(const DScene& sc, int tex, float u, float v, V3 p) {
         float sines = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
         return sines < 0.0f ? mk(t1.x, t1.y, t1.z) : mk(t0.x, t0.y, t0.z);
     }
+    if (!(F & (FEAT_NOISE | FEAT_IMAGE))) return mk(t0.x, t0.y, t0.z);
     int4 ti = __ldg(reinterpret_cast<const int4*>(tp + 2));
-    if (kind == TEX_NOISE) {                                                               // :43-45
+    if ((F & FEAT_NOISE) && (kind == TEX_NOISE || !(F & FEAT_IMAGE))) {                                                               // :43-45
         float c = 0.5f * (1.0f + sinf(t0.w * p.z + 10.0f * perlin_turb(sc.perlin + (size_t)ti.x * RTW_PERLIN_BYTES, p, 7)));
         return mk(c, c, c);
     }
@@ -306,10 +313,11 @@ RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, floa
 
 // Any primitive: accepted root in [t_lo, t_hi] or NaN.  `skip` = primitive the ray starts on (-1: none): a planar
 // rect cannot be re-hit by a ray leaving it (exact geometry; the reference's f64 gets t ~ 1e-13 < t_min).
+template <int F = FEAT_ALL>
 RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip) {
     const DPrim* pp = sc.prims + pi;
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
-    if (meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip);
+    if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip);
     if (pi == skip) return CUDART_NAN_F;
     V3 o, d;
     xform_ray(sc, meta.z, r, o, d);           // xform 0 is the identity: no branch, one instruction stream
@@ -350,6 +358,7 @@ __device__ int g_dbg_visits, g_dbg_prims;
 #define RTW_DBG_VISIT()
 #define RTW_DBG_PRIM()
 #endif
+template <int F = FEAT_ALL>
 RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip
 #ifdef RTW_INSTRUMENT
                          , int& dbg_visits, int& dbg_prims
@@ -395,7 +404,7 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
             for (int i = 0; i < count; ++i) {
                 RTW_DBG_PRIM();
-                float t = prim_root(sc, first + i, r, t_min, t_best, skip);
+                float t = prim_root<F>(sc, first + i, r, t_min, t_best, skip);
                 if (t == t) { t_best = t; prim_best = first + i; }       // not NaN: accepted, t <= t_best
             }
             leaf = node;                                                  // a second leaf was reached meanwhile
@@ -412,6 +421,7 @@ RTW_DEV void set_face_normal(V3 dir, V3 outward, V3& normal, int& front) {
 
 // Fill the HitRecord for the accepted (prim, t): sphere_hit :275-287, rect_hit :322-329, then the wrapper chain
 // (Translate :236-239, hit_rotate_y :398-410) with the reference's nested set_face_normal calls replayed literally.
+template <int F = FEAT_ALL>
 RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool want_uv, HitRec& rec) {
     const DPrim* pp = sc.prims + pi;
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);
@@ -419,10 +429,10 @@ RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool
     Ray wr; wr.o = r.o; wr.d = r.d;
     rec.p = ray_at(wr, t);
     V3 outward_obj, d_obj = r.d;
-    const int xf = meta.z;
+    const int xf = (F & FEAT_XFORM) ? meta.z : 0;
     float mc = 1.0f, ms = 0.0f;
     if (xf) { float4 m = __ldg(reinterpret_cast<const float4*>(sc.xforms + xf)); mc = m.x; ms = m.y; d_obj = mk(mc * r.d.x - ms * r.d.z, r.d.y, ms * r.d.x + mc * r.d.z); }
-    if (meta.x <= PRIM_MOVING_SPHERE) {
+    if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) {
         double cx, cy, cz, rad;
         load_prim_center(pp, meta.x, r.time, cx, cy, cz, rad);
         // one Newton step of f(t) = a t^2 + 2 half_b t + c in f64: t, the hit point and the normal then carry
@@ -545,25 +555,27 @@ RTW_DEV DMatRec load_mat(const DScene& sc, int mat) {
     DMatRec m; m.r = a.x; m.g = a.y; m.b = a.z; m.param = a.w; m.kind = b.x; m.tex = b.y;
     return m;
 }
+template <int F = FEAT_ALL>
 RTW_DEV bool mat_needs_uv(const DScene& sc, const DMatRec& m) {
-    if (m.tex < 0) return false;
+    if (!(F & FEAT_IMAGE) || m.tex < 0) return false;
     return __float_as_int(__ldg(&reinterpret_cast<const float4*>(sc.texs + m.tex)[1].w)) == TEX_IMAGE;
 }
+template <int F = FEAT_ALL>
 RTW_DEV V3 mat_color(const DScene& sc, const DMatRec& m, const HitRec& rec) {
     if (m.tex < 0) return mk(m.r, m.g, m.b);
-    return texture_value(sc, m.tex, rec.u, rec.v, rec.p);
+    return texture_value<F>(sc, m.tex, rec.u, rec.v, rec.p);
 }
 
 // Returns true when a scattered ray exists.  `emitted` is always written.
 // Lambertian, Metal and Isotropic all start with the same unit-ball rejection loop (src/math.rs:51-58): it is
 // hoisted to ONE call site so the lanes of a warp run it — and the Philox blocks behind it — together.
-template <class R>
+template <class R, int F = FEAT_ALL>
 RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const HitRec& rec, R& g, Ray& scattered, V3& attenuation, V3& emitted) {
     emitted = mk(0.f, 0.f, 0.f);
     scattered.o = rec.p; scattered.time = ray.time;
     const int kind = m.kind;
     if (kind == MAT_DIFFUSE_LIGHT) {                                                       // :20, :25-34 (both faces emit)
-        emitted = mat_color(sc, m, rec);
+        emitted = mat_color<F>(sc, m, rec);
         attenuation = mk(0.f, 0.f, 0.f);
         scattered.d = mk(0.f, 0.f, 0.f);
         return false;
@@ -597,7 +609,7 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
         V3 dir = rec.normal + normalize(ball);
         if (near_zero(dir)) dir = rec.normal;
         scattered.d = dir;
-        attenuation = mat_color(sc, m, rec);
+        attenuation = mat_color<F>(sc, m, rec);
         return true;
     }
     if (kind == MAT_METAL) {                                                               // :50-60
@@ -607,7 +619,7 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
         return dot(scattered.d, rec.normal) > 0.0f;
     }
     scattered.d = ball;                                                                    // Isotropic :84-87
-    attenuation = mat_color(sc, m, rec);
+    attenuation = mat_color<F>(sc, m, rec);
     return true;
 }
 
@@ -638,10 +650,11 @@ RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, in
 // Second half of one level of ray_color: media (list order, after the surfaces), miss -> background, otherwise
 // hit record + Material::emitted/scatter.  `tr`/(t_best, prim_best) = the segment's ray and its closest surface hit.
 // Returns true while the path continues; `add` = this level's radiance term (often 0).
+template <int F = FEAT_ALL>
 RTW_DEV bool path_finish(const DScene& sc, const DParams& prm, PathState& ps, const TRay& tr, float t_best, int prim_best, V3& add) {
     add = mk(0.f, 0.f, 0.f);
     int med_mat = -1; float med_t = 0.f;
-    for (int m = 0; m < sc.n_media; ++m) {
+    if (F & FEAT_MEDIA) for (int m = 0; m < sc.n_media; ++m) {
         float t; int mat;
         if (medium_hit(sc, m, tr, prm.t_min, t_best, ps.rng, t, mat)) { t_best = t; med_t = t; med_mat = mat; prim_best = -2; }
     }
@@ -650,16 +663,16 @@ RTW_DEV bool path_finish(const DScene& sc, const DParams& prm, PathState& ps, co
         return false;
     }
     HitRec rec; DMatRec m;
-    if (prim_best == -2) {
+    if ((F & FEAT_MEDIA) && prim_best == -2) {
         rec.t = med_t; rec.p = ray_at(ps.ray, med_t); rec.normal = mk(1.f, 0.f, 0.f); rec.front = 1; rec.mat = med_mat; rec.u = 0.f; rec.v = 0.f;
         m = load_mat(sc, med_mat);
     } else {
         int mat = __ldg(&sc.prims[prim_best].mat);
         m = load_mat(sc, mat);                                                             // :26
-        finalize_hit(sc, prim_best, t_best, tr, mat_needs_uv(sc, m), rec);
+        finalize_hit<F>(sc, prim_best, t_best, tr, mat_needs_uv<F>(sc, m), rec);
     }
     Ray scattered; V3 att, em;
-    bool cont = scatter(sc, m, ps.ray, rec, ps.rng, scattered, att, em);                  // :28-33
+    bool cont = scatter<PhiloxRng, F>(sc, m, ps.ray, rec, ps.rng, scattered, att, em);                  // :28-33
     add = ps.T * em;
     if (!cont) return false;
     ps.T = ps.T * att;

@@ -69,6 +69,7 @@ struct FlatScene {
     std::vector<uint8_t> image;
     double sah_cost = 0;
     int max_depth = 0;
+    int features = 0;                // FEAT_* bits (rtw_device.cuh) the scene needs: picks the kernel variant
 };
 
 // Flatten `roots` (world.hittables, or a single hittable for the test hooks).  Returns 0 or a negative
