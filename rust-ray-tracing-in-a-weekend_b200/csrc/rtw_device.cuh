@@ -95,6 +95,25 @@ struct PhiloxRng {
         uint32_t w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
         return (float)(w >> 8) * (1.0f / 16777216.0f);
     }
+    // Two / three CONSECUTIVE draws behind one inlined copy of the block function (every next() call site carries its
+    // own 70-instruction copy; the kernel is instruction-cache bound).  Same words as next() called 2 / 3 times.
+    // `single`: only the first draw is consumed (camera time, the last draw of bounce 0).
+    RTW_DEV void next2(float& x, float& y, bool single = false) {
+        const uint32_t i = draw & 3u;
+        const uint32_t ox = i == 1 ? w1 : (i == 2 ? w2 : w3), oy = i == 1 ? w2 : w3;
+        if (i == 0 || (i == 3 && !single)) philox4x32_10_rk((draw + 1) >> 2, bounce, pixel, sample, w0, w1, w2, w3);
+        const uint32_t wx = i == 0 ? w0 : ox, wy = i == 0 ? w1 : (i == 3 ? w0 : oy);
+        draw += single ? 1u : 2u;
+        x = (float)(wx >> 8) * (1.0f / 16777216.0f); y = (float)(wy >> 8) * (1.0f / 16777216.0f);
+    }
+    RTW_DEV void next3(float& x, float& y, float& z) {
+        const uint32_t i = draw & 3u;
+        const uint32_t ox = i == 1 ? w1 : (i == 2 ? w2 : w3), oy = i == 1 ? w2 : w3, oz = w3;
+        if (i != 1) philox4x32_10_rk((draw + 3) >> 2, bounce, pixel, sample, w0, w1, w2, w3);
+        const uint32_t wx = i == 0 ? w0 : ox, wy = i == 0 ? w1 : (i == 3 ? w0 : oy), wz = i == 0 ? w2 : (i == 1 ? oz : (i == 2 ? w0 : w1));
+        draw += 3;
+        x = (float)(wx >> 8) * (1.0f / 16777216.0f); y = (float)(wy >> 8) * (1.0f / 16777216.0f); z = (float)(wz >> 8) * (1.0f / 16777216.0f);
+    }
 };
 
 // explicit stream (parity hooks): `stride` f64 draws per item, consumed in order
@@ -102,13 +121,16 @@ struct StreamRng {
     const double* xi; int n; int draw;
     RTW_DEV void set_bounce(uint32_t) {}
     RTW_DEV float next() { float v = draw < n ? (float)xi[draw] : 0.5f; ++draw; return v; }
+    RTW_DEV void next2(float& x, float& y, bool single = false) { x = next(); y = single ? 0.5f : next(); }
+    RTW_DEV void next3(float& x, float& y, float& z) { x = next(); y = next(); z = next(); }
 };
 
 template <class R> RTW_DEV float rng_range(R& g, float a, float b) { return a + (b - a) * g.next(); }   // :273-276
 template <class R> RTW_DEV V3 random_in_unit_sphere(R& g) {                                               // :51-58, draw order x,y,z :43-49
     for (;;) {
-        float x = rng_range(g, -1.0f, 1.0f), y = rng_range(g, -1.0f, 1.0f), z = rng_range(g, -1.0f, 1.0f);
-        V3 p = mk(x, y, z);
+        float x, y, z;
+        g.next3(x, y, z);
+        V3 p = mk(-1.0f + 2.0f * x, -1.0f + 2.0f * y, -1.0f + 2.0f * z);                  // random_range(-1, 1) :273-276
         if (length_squared(p) < 1.0f) return p;
     }
 }
@@ -123,20 +145,30 @@ RTW_DEV V3 ray_at(const Ray& r, float t) { return mk(fmaf(t, r.d.x, r.o.x), fmaf
 // ------------------------------------------------------------------------------------------------
 // src/camera.rs:58-66 — get_ray.  Draw order: disk loop (x, y per iteration, src/math.rs:69-76), then time.
 // ------------------------------------------------------------------------------------------------
-template <class R> RTW_DEV Ray camera_get_ray(const DCamera& c, float s, float t, R& g) {
-    float rx, ry;
+// One loop, one next2() call site: pass 0 draws the pixel jitter (src/main.rs:518-519; skipped when the caller
+// supplies s, t), the next passes the lens-disk attempts, the last one the shutter time.
+template <bool JITTER, class R> RTW_DEV Ray camera_ray_loop(const DCamera& c, float s, float t, float px, float py, float wm1, float hm1, R& g) {
+    float rx = 0.f, ry = 0.f, tm = 0.f;
+    int phase = JITTER ? 0 : 1;
+#pragma unroll 1
     for (;;) {
-        rx = rng_range(g, -1.0f, 1.0f); ry = rng_range(g, -1.0f, 1.0f);
-        if (rx * rx + ry * ry < 1.0f) break;
+        float a, b;
+        g.next2(a, b, phase == 2);
+        if (JITTER && phase == 0) { s = (px + a) / wm1; t = (py + b) / hm1; phase = 1; }
+        else if (phase == 1) {
+            rx = -1.0f + 2.0f * a; ry = -1.0f + 2.0f * b;
+            if (rx * rx + ry * ry < 1.0f) phase = 2;
+        } else { tm = c.time0 + (c.time1 - c.time0) * a; break; }
     }
     rx *= c.lens_radius; ry *= c.lens_radius;
     V3 offset = mk(c.ux * rx + c.wx * ry, c.uy * rx + c.wy * ry, c.uz * rx + c.wz * ry);
     Ray r;
     r.o = mk(c.ox + offset.x, c.oy + offset.y, c.oz + offset.z);
     r.d = mk(c.lx + s * c.hx + t * c.vx - offset.x, c.ly + s * c.hy + t * c.vy - offset.y, c.lz + s * c.hz + t * c.vz - offset.z);
-    r.time = rng_range(g, c.time0, c.time1);
+    r.time = tm;
     return r;
 }
+template <class R> RTW_DEV Ray camera_get_ray(const DCamera& c, float s, float t, R& g) { return camera_ray_loop<false>(c, s, t, 0.f, 0.f, 1.f, 1.f, g); }
 
 // ------------------------------------------------------------------------------------------------
 // src/perlin.rs — noise (:32-68), perlin_interp (:70-94), turb (:96-108).  Smoothstep is applied twice and the
@@ -185,8 +217,13 @@ RTW_DEV V3 texture_value(const DScene& sc, int tex, float u, float v, V3 p) {
     int kind = __float_as_int(t1.w);
     if (kind == TEX_SOLID) return mk(t0.x, t0.y, t0.z);
     if (kind == TEX_CHECKER) {                                                             // :35-42
-        float sines = sinf(10.0f * p.x) * sinf(10.0f * p.y) * sinf(10.0f * p.z);
-        return sines < 0.0f ? mk(t1.x, t1.y, t1.z) : mk(t0.x, t0.y, t0.z);
+        // Only the SIGN of sin(10x)·sin(10y)·sin(10z) is used: sin(a) < 0 iff floor(a/pi) is odd, and the product is
+        // zero (-> even) only when a coordinate is 0.  Evaluated in f64 (three DMUL + F2I) so the cell boundaries sit
+        // where the f64 reference puts them; three inlined sinf() were 700 SASS instructions of this kernel.
+        const int odd = (__double2int_rd(10.0 * (double)p.x * 0.31830988618379067) ^ __double2int_rd(10.0 * (double)p.y * 0.31830988618379067) ^
+                         __double2int_rd(10.0 * (double)p.z * 0.31830988618379067)) & 1;
+        const bool zero = p.x == 0.0f || p.y == 0.0f || p.z == 0.0f;
+        return (odd && !zero) ? mk(t1.x, t1.y, t1.z) : mk(t0.x, t0.y, t0.z);
     }
     if (!(F & (FEAT_NOISE | FEAT_IMAGE))) return mk(t0.x, t0.y, t0.z);
     int4 ti = __ldg(reinterpret_cast<const int4*>(tp + 2));
@@ -485,20 +522,21 @@ template <class R>
 RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, float t_max, R& g, float& t_out, int& mat_out) {
     int4 md = __ldg(reinterpret_cast<const int4*>(sc.media + mi));
     const float inf = CUDART_INF_F;
-    float t1 = CUDART_NAN_F;
-    {   // boundary.hit(ray, -inf, inf) :422 — closest-so-far scan over the boundary prims (hit_hittables :43-55)
-        float hi = inf;
-        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, -inf, hi, -1); if (t == t) { hi = t; t1 = t; } }
+    // boundary.hit(ray, -inf, inf) :422, then boundary.hit(ray, rec1.t + 0.0001, inf) :423 — two closest-so-far scans
+    // over the boundary prims (hit_hittables :43-55) sharing ONE inlined copy of the primitive test
+    float t1 = 0.f, t2 = 0.f, lo = -inf;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        float hi = inf, found = CUDART_NAN_F;
+        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1); if (t == t) { hi = t; found = t; } }
+        if (!(found == found)) return false;
+        if (pass == 0) {
+            t1 = found;
+            // in f32 the +0.0001 vanishes once |t1| > 2048 (r = 5000 fog sphere): keep the probe strictly beyond t1
+            lo = t1 + 0.0001f;
+            if (!(lo > t1)) lo = nextafterf(t1, inf);
+        } else t2 = found;
     }
-    if (!(t1 == t1)) return false;
-    float t2 = CUDART_NAN_F;
-    {   // boundary.hit(ray, rec1.t + 0.0001, inf) :423
-        // in f32 the +0.0001 vanishes once |t1| > 2048 (r = 5000 fog sphere): keep the probe strictly beyond t1
-        float hi = inf, lo = t1 + 0.0001f;
-        if (!(lo > t1)) lo = nextafterf(t1, inf);
-        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1); if (t == t) { hi = t; t2 = t; } }
-    }
-    if (!(t2 == t2)) return false;
     if (t1 < t_min) t1 = t_min;
     if (t2 > t_max) t2 = t_max;
     if (t1 >= t2) return false;
@@ -640,9 +678,7 @@ struct PathState {
 
 RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, int s, PathState& ps) {   // :517-520
     ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)(y * prm.width + x), (uint32_t)s);
-    float u = ((float)x + ps.rng.next()) / ((float)prm.width - 1.0f);
-    float v = ((float)y + ps.rng.next()) / ((float)prm.height - 1.0f);
-    ps.ray = camera_get_ray(cam, u, v, ps.rng);
+    ps.ray = camera_ray_loop<true>(cam, 0.f, 0.f, (float)x, (float)y, (float)prm.width - 1.0f, (float)prm.height - 1.0f, ps.rng);
     ps.T = mk(1.f, 1.f, 1.f);
     ps.segment = 0; ps.last_prim = -1;
 }

@@ -1,0 +1,8 @@
+#!/bin/bash
+# A/B of two builds of the library: tools/ab.sh <libA> <libB> ...   (each: C1 bench line + config-like timings)
+mkdir -p gpurun_out
+for L in "$@"; do
+  T=$(basename $L .so)
+  RTW_LIB_PATH=$PWD/$L python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('[$T] C1', round(d['ms_per_step'],2), 'ms', round(d['value'],1), 'Mpaths/s')"
+  RTW_LIB_PATH=$PWD/$L RTW_TAG=$T python tools/exp_time2.py
+done 2>&1 | tee gpurun_out/ab.log
