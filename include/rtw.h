@@ -72,6 +72,7 @@ typedef struct rtw_render_params {
 
 #define RTW_FLAG_DEVICE_OUT 1   /* out_rgb_sum is a device pointer on the first device (no D2H) */
 #define RTW_FLAG_KERNEL_MEGA 2  /* force the one-path-per-lane megakernel */
+#define RTW_FLAG_NO_TILE_CULL 8 /* diagnostic: skip the per-tile candidate lists, primary rays traverse the BVH (same image) */
 #define RTW_FLAG_KERNEL_POOL 4  /* force the warp-pool (shared-memory wavefront) kernel; default: chosen by measurement */
 
 typedef struct rtw_stats {

@@ -41,8 +41,10 @@ extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
 #ifndef RTW_DEFAULT_POOL_MODE
 #define RTW_DEFAULT_POOL_MODE 2
 #endif
+// 7 CTAs = 28 warps per SM at 72 registers: measured best of 6 / 7 / 8 on every config once the kernel had been shrunk
+// (8 CTAs = 64 registers spill ~30 words per thread; 6 CTAs lose more latency hiding than the registers buy)
 #ifndef RTW_MIN_BLOCKS
-#define RTW_MIN_BLOCKS 8
+#define RTW_MIN_BLOCKS 7
 #endif
 
 template <int F>
@@ -72,8 +74,8 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
         const int n_items = prm.max_depth >= 1 ? npix * (s1 - s0) : 0;
         acc[warp][lane] = 0.f; acc[warp][lane + 32] = 0.f; acc[warp][lane + 64] = 0.f;
         // every primitive a primary ray of this tile can touch (-1: too many, traverse instead)
-        const int list_n = build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp],
-                                           reinterpret_cast<int*>(ring[warp][0]), lane);
+        const int list_n = prm.no_tile_cull ? -1 : build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp],
+                                                                   reinterpret_cast<int*>(ring[warp][0]), lane);
         __syncwarp();
         if (lane == 0) { if (list_n >= 0) atomicAdd(stats + 2, (unsigned long long)list_n); else atomicAdd(stats + 3, 1ull); }
         int next = 0, pix = 0;
@@ -557,6 +559,7 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     if (n_units >= 0xffffffffLL) return fail(RTW_ERR_INVALID_ARG, "too many work units");
     d.n_units = (uint32_t)n_units;
     d.accumulate = 1;
+    d.no_tile_cull = (p.flags & RTW_FLAG_NO_TILE_CULL) ? 1 : 0;
     return 0;
 }
 

@@ -122,6 +122,7 @@ struct DParams {
     int32_t chunks, chunk_spp;         // samples split into `chunks` units of `chunk_spp` per tile
     uint32_t n_units;
     int32_t accumulate;                // 1: atomicAdd into the framebuffer (several units or GPUs per pixel)
+    int32_t no_tile_cull;              // 1: primary rays traverse the BVH like all others (RTW_FLAG_NO_TILE_CULL)
 };
 
 #endif

@@ -565,6 +565,22 @@ def test_pool_kernel_equals_megakernel(pkg, gpu, name, W, H, spp):
     assert np.abs(mega - pool).max() <= 2e-4 * max(np.abs(mega).max(), 1.0)
 
 
+@pytest.mark.parametrize("name,W,H,spp", [("random_scene", 403, 227, 40), ("cornell_box", 150, 150, 40), ("final_scene", 160, 160, 40),
+                                          ("two_perlin_spheres", 200, 113, 40), ("simple_light", 200, 113, 40), ("earth", 200, 113, 40)])
+def test_tile_culling_is_conservative(pkg, gpu, name, W, H, spp):
+    """Primary rays only test their tile's candidate list (interval walk of the BVH with the tile's ray bundle).  With
+    RTW_FLAG_NO_TILE_CULL they traverse the BVH like every other ray: a list that missed a primitive would change the
+    first hit of some path, hence the ray count and the image.  Only the f32 order of the tile atomics may differ."""
+    sc, spec = pkg.scenes.build(gpu, name)
+    sc.commit(1, 0)
+    cam = spec.camera(gpu, W, H)
+    a, st0 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=11, flags=pkg.api.RTW_FLAG_KERNEL_MEGA))
+    b, st1 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=11,
+                                            flags=pkg.api.RTW_FLAG_KERNEL_MEGA | pkg.api.RTW_FLAG_NO_TILE_CULL))
+    assert st0["rays"] == st1["rays"]
+    assert np.abs(a - b).max() <= 1e-5 * max(np.abs(a).max(), 1.0)
+
+
 def test_write_color_bit_exact(pkg, gpu, orc):
     """write_color (src/math.rs:119-132): gamma 2, clamp, *256 truncation — byte-exact against the oracle."""
     import ctypes as C
