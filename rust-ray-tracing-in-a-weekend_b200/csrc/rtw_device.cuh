@@ -442,14 +442,13 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, t_min, t_best, e0);
             const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, t_min, t_best, e1);
             // straight-line child selection: nearer hit child next, the other one pushed
-            const bool second = h1 && (!h0 || e1 < e0);
+            const bool closer1 = e1 < e0;
+            const bool second = h1 & (!h0 | closer1);
             const int nearc = second ? ch.y : ch.x, farc = second ? ch.x : ch.y;
             const bool both = h0 && h1, none = !(h0 || h1);
-            if (both) *sp = farc;
-            sp += both ? 1 : 0;
-            const int top = sp[-1];                // one predictable local load per visit
-            node = none ? top : nearc;
-            sp -= none ? 1 : 0;
+            node = nearc;
+            if (both) { *sp = farc; ++sp; }
+            if (none) { --sp; node = *sp; }
 #if RTW_SPECULATIVE
             if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = sp[-1]; --sp; }   // postpone first leaf
             if (!__any_sync(__activemask(), searching)) break;
