@@ -66,9 +66,8 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= prm.n_units) break;
         ++units;
-        const int tile = (int)(unit / (unsigned)prm.chunks), chunk = (int)(unit % (unsigned)prm.chunks);
-        const int s0 = chunk * prm.chunk_spp;
-        const int s1 = min(prm.spp, s0 + prm.chunk_spp);
+        int tile, s0, s1;
+        decode_unit(prm, unit, tile, s0, s1);
         const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
         const int tw = min(8, prm.width - tx * 8), th = min(4, prm.height - ty * 4), npix = tw * th;     // ragged edge tiles
         const int n_items = prm.max_depth >= 1 ? npix * (s1 - s0) : 0;
@@ -242,9 +241,8 @@ render_pool_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict
         unit = __shfl_sync(0xffffffffu, unit, 0);
         if (unit >= prm.n_units) break;
         ++units;
-        const int tile = (int)(unit / (unsigned)prm.chunks), chunk = (int)(unit % (unsigned)prm.chunks);
-        const int s0 = chunk * prm.chunk_spp;
-        const int s1 = min(prm.spp, s0 + prm.chunk_spp);
+        int tile, s0, s1;
+        decode_unit(prm, unit, tile, s0, s1);
         const int tile_x0 = (tile % prm.tiles_x) * 8, tile_y0 = (tile / prm.tiles_x) * 4;
         const int tw = min(8, prm.width - tile_x0), th = min(4, prm.height - tile_y0), npix = tw * th;   // ragged edge tiles
         const int n_items = prm.max_depth >= 1 ? npix * (s1 - s0) : 0;
@@ -362,11 +360,10 @@ __global__ void aabb_kernel(int n, const double* __restrict__ bmin, const double
     if (i >= n) return;
     V3 ro = mk((float)o[3 * i], (float)o[3 * i + 1], (float)o[3 * i + 2]);
     V3 rd = mk((float)d[3 * i], (float)d[3 * i + 1], (float)d[3 * i + 2]);
-    V3 inv = mk(1.0f / rd.x, 1.0f / rd.y, 1.0f / rd.z);
-    V3 oi = mk(ro.x * inv.x, ro.y * inv.y, ro.z * inv.z);
-    float e;
+    V3 inv, oi; float slack, e;
+    slab_setup(ro, rd, inv, oi, slack);
     hit[i] = slab((float)bmin[3 * i], (float)bmax[3 * i], (float)bmin[3 * i + 1], (float)bmax[3 * i + 1], (float)bmin[3 * i + 2],
-                  (float)bmax[3 * i + 2], inv, oi, slab_slack(oi), t_min, t_max, e) ? 1 : 0;
+                  (float)bmax[3 * i + 2], inv, oi, slack, t_min, t_max, e) ? 1 : 0;
 }
 
 __global__ void scatter_kernel(DScene sc, int mat, int n, const double* __restrict__ ro, const double* __restrict__ rd, const double* __restrict__ rt,
@@ -544,18 +541,32 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     d.tiles_x = (p.width + 7) / 8; d.tiles_y = (p.height + 3) / 4;
     long long tiles = (long long)d.tiles_x * d.tiles_y;
     int chunk = p.samples_per_unit;
+    d.spp_a = p.spp;
     if (chunk <= 0) {
-        // aim for >= 16 units per resident warp, never below 32 samples per unit (in-unit regeneration tail)
-        long long want_units = 16LL * total_warps;
+        // Guided self-scheduling in two phases.  A: 80 % of the samples in units sized for ~24 per resident warp
+        // (>= 32 samples: per-unit cost = tile list + drain of the ring; much bigger units lose to the spread of tile
+        // costs, sky vs glass: 6 per warp measured 13 % slower).  B: the rest in units of 32 (16) samples, so the frame
+        // ends on SHORT units.  Measured C1 / final_scene: one size, 16 per warp 110.1 / 572 ms; this 106.7 / 535 ms.
+        // RTW_UNITS_PER_WARP / RTW_ONE_PHASE: tuning switches for tools/ab2.sh.
+        static const bool one_phase = std::getenv("RTW_ONE_PHASE") != nullptr;
+        static const char* wu = std::getenv("RTW_UNITS_PER_WARP");
+        const int spp_b = (p.spp >= 160 && !one_phase) ? p.spp / 5 : 0;
+        d.spp_a = p.spp - spp_b;
+        long long want_units = (wu ? atoll(wu) : 24LL) * total_warps;
         long long chunks = (want_units + tiles - 1) / tiles;
         if (chunks < 1) chunks = 1;
-        chunk = (int)((p.spp + chunks - 1) / chunks);
+        chunk = (int)((d.spp_a + chunks - 1) / chunks);
         if (chunk < 32) chunk = 32;
+        if (spp_b > 0) {
+            d.chunk_spp_b = chunk >= 64 ? 32 : 16;
+            d.chunks_b = (spp_b + d.chunk_spp_b - 1) / d.chunk_spp_b;
+        }
     }
-    if (chunk > p.spp) chunk = p.spp;
+    if (chunk > d.spp_a) chunk = d.spp_a;
     d.chunk_spp = chunk;
-    d.chunks = (p.spp + chunk - 1) / chunk;
-    long long n_units = tiles * d.chunks;
+    d.chunks = (d.spp_a + chunk - 1) / chunk;
+    d.n_units_a = (uint32_t)(tiles * d.chunks);
+    long long n_units = tiles * ((long long)d.chunks + d.chunks_b);
     if (n_units >= 0xffffffffLL) return fail(RTW_ERR_INVALID_ARG, "too many work units");
     d.n_units = (uint32_t)n_units;
     d.accumulate = 1;
@@ -927,7 +938,7 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     TRY(ensure_fb(s->local, r0.device, dev_out ? 1 : p->width, dev_out ? 1 : p->height));
     float* fb = dev_out ? out : s->local.fb();
     CUDA_TRY(cudaSetDevice(r0.device));
-    dp.accumulate = (n_rep > 1 || dp.chunks > 1) ? 1 : 0;
+    dp.accumulate = (n_rep > 1 || dp.chunks + dp.chunks_b > 1) ? 1 : 0;
     CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
     if (dp.accumulate) CUDA_TRY(cudaMemsetAsync(fb, 0, fb_bytes, r0.stream));
     if (n_rep > 1) CUDA_TRY(cudaStreamSynchronize(r0.stream));   // peers must see the zeroed buffers

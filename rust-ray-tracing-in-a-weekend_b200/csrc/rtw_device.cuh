@@ -35,6 +35,11 @@ RTW_DEV V3 operator*(float s, V3 a) { return mk(a.x * s, a.y * s, a.z * s); }
 RTW_DEV V3 operator*(V3 a, float s) { return mk(a.x * s, a.y * s, a.z * s); }
 RTW_DEV float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }       // :82-84
 RTW_DEV float length_squared(V3 a) { return dot(a, a); }                                    // :86-88
+// MUFU-backed sqrt / reciprocal (max relative error 2^-23, PTX ISA) for values that only SELECT a candidate: the IEEE
+// sequences behind sqrtf() and 1.0f/x cost ~10 instructions each plus an out-of-line slow path (85 SASS instructions
+// for the one sqrtf of sphere_root).  Accepted sphere hits are re-derived in f64 (finalize_hit), box tests are padded.
+RTW_DEV float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RTW_DEV float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 RTW_DEV V3 normalize(V3 v) { float inv = rsqrtf(length_squared(v)); return inv * v; }        // :102-104 ((1/len)*v, :260-266); MUFU.RSQ, 2 ulp
 RTW_DEV V3 reflect(V3 v, V3 n) { return v - (2.0f * dot(v, n)) * n; }                       // :106-108
 RTW_DEV V3 refract(V3 uv, V3 n, float etai_over_etat) {                                      // :110-117
@@ -175,7 +180,7 @@ template <bool JITTER, class R> RTW_DEV Ray camera_ray_loop(const DCamera& c, fl
     for (;;) {
         float a, b;
         g.next2(a, b, phase == 2);
-        if (JITTER && phase == 0) { s = (px + a) / wm1; t = (py + b) / hm1; phase = 1; }
+        if (JITTER && phase == 0) { s = __fdividef(px + a, wm1); t = __fdividef(py + b, hm1); phase = 1; }    // 2 ulp: sub-pixel jitter
         else if (phase == 1) {
             rx = -1.0f + 2.0f * a; ry = -1.0f + 2.0f * b;
             if (rx * rx + ry * ry < 1.0f) phase = 2;
@@ -294,11 +299,11 @@ struct TRay {
 RTW_DEV TRay make_tray(const Ray& r) {
     TRay t; t.o = r.o; t.d = r.d; t.time = r.time;
 #if RTW_LAZY_F64
-    t.inv_a = 1.0f / (float)t.ga();
+    t.inv_a = rcp_approx((float)t.ga());
 #else
     t.ox = r.o.x; t.oy = r.o.y; t.oz = r.o.z; t.dx = r.d.x; t.dy = r.d.y; t.dz = r.d.z;
     t.a = t.dx * t.dx + t.dy * t.dy + t.dz * t.dz;
-    t.inv_a = 1.0f / (float)t.a;
+    t.inv_a = rcp_approx((float)t.a);
 #endif
     return t;
 }
@@ -327,7 +332,7 @@ RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r,
     double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
     double disc = half_b * half_b - r.ga() * c;
     float discf = (float)disc, hb = (float)half_b, cf = (float)c;
-    float sq = sqrtf(fmaxf(discf, 0.0f));
+    float sq = sqrt_approx(fmaxf(discf, 0.0f));
     bool neg = hb < 0.0f;
     float q = neg ? sq - hb : -hb - sq;
     float tq = q * r.inv_a, tc = __fdividef(cf, q);
@@ -363,7 +368,7 @@ RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, floa
     const float ok = xy ? o.z : (yz ? o.x : o.y), dk = xy ? d.z : (yz ? d.x : d.y);
     const float oa = yz ? o.y : o.x, da = yz ? d.y : d.x;
     const float ob = xy ? o.y : o.z, db = xy ? d.y : d.z;
-    float t = (k - ok) / dk;
+    float t = __fdividef(k - ok, dk);               // MUFU.RCP + FMUL, 2 ulp (IEEE division: 10 instructions + slow path per test)
     float a = oa + t * da, b = ob + t * db;
     bool okk = t >= t_lo && t <= t_hi && !(a < ab.x || a > ab.y || b < ab.z || b > ab.w);
     return okk ? t : CUDART_NAN_F;
@@ -383,17 +388,24 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
 }
 
 // AABB::hit (src/aabb.rs:77-103) for the two children of a node, with precomputed 1/d and o/d.  Conservative: closed
-// interval, boxes rounded outward, and the exit distance padded by 2 ulp (Ize, "Robust BVH ray traversal") PLUS an
-// absolute slack of 4 ulp of max|o/d| — the fma form t = p*inv - o*inv carries the rounding of o*inv, which is not
+// interval, boxes rounded outward, and the exit distance padded by 5 ulp (Ize, "Robust BVH ray traversal": 2 ulp for
+// correctly rounded 1/d; 3 more for MUFU.RCP) PLUS an absolute slack of 4 ulp of max|o/d| — the fma form t = p*inv - o*inv carries the rounding of o*inv, which is not
 // relative to t when the origin is far from the box.  The f32 test can then never cull a primitive the f64 reference
 // would hit; the primitive tests decide.  `slack` is per ray (see slab_slack), folded into one FFMA.
 RTW_DEV float slab_slack(V3 oi) { return 2.384185791015625e-07f * fmaxf(fmaxf(fabsf(oi.x), fabsf(oi.y)), fabsf(oi.z)); }
+// Per-ray constants of the slab test.  1/d from MUFU.RCP (relative error <= 2^-23): the SAME inv feeds o*inv, so the
+// error is purely relative on every plane distance and is covered by widening Ize's 2-ulp exit padding to 5 ulp.
+RTW_DEV void slab_setup(V3 o, V3 d, V3& inv, V3& oi, float& slack) {
+    inv = mk(rcp_approx(d.x), rcp_approx(d.y), rcp_approx(d.z));
+    oi = mk(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    slack = slab_slack(oi);
+}
 RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
     float x0 = fmaf(mnx, inv.x, -oi.x), x1 = fmaf(mxx, inv.x, -oi.x);
     float y0 = fmaf(mny, inv.y, -oi.y), y1 = fmaf(mxy, inv.y, -oi.y);
     float z0 = fmaf(mnz, inv.z, -oi.z), z1 = fmaf(mxz, inv.z, -oi.z);
     float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
-    float tf = fmaf(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)), 1.0000004f, slack);
+    float tf = fmaf(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)), 1.0000006f, slack);
     t_enter = tn;
     return tn <= tf;
 }
@@ -423,10 +435,8 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
 #endif
                          ) {
     if (sc.n_bvh_prims == 0) return;
-    // exact 1/d: the 2-ulp padding of the slab test (Ize) assumes correctly rounded reciprocals
-    V3 inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-    V3 oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
-    const float slack = slab_slack(oi);
+    V3 inv, oi; float slack;
+    slab_setup(r.o, r.d, inv, oi, slack);
     int stack[RTW_STACK];
     stack[0] = RTW_SENTINEL;
     int* sp = stack + 1;                          // points at the next free entry
@@ -695,6 +705,22 @@ struct PathState {
 #endif
     PhiloxRng rng;
 };
+
+// Work unit -> (tile, sample range).  Units are handed out in index order from one counter: first the big phase-A
+// units, then the small phase-B ones (guided self-scheduling: the frame ends on short units, so the last warp finishes
+// at most one SHORT unit after the others instead of one long one).
+RTW_DEV void decode_unit(const DParams& prm, unsigned unit, int& tile, int& s0, int& s1) {
+    if (unit < prm.n_units_a) {
+        tile = (int)(unit / (unsigned)prm.chunks);
+        s0 = (int)(unit % (unsigned)prm.chunks) * prm.chunk_spp;
+        s1 = min(prm.spp_a, s0 + prm.chunk_spp);
+    } else {
+        const unsigned u = unit - prm.n_units_a;
+        tile = (int)(u / (unsigned)prm.chunks_b);
+        s0 = prm.spp_a + (int)(u % (unsigned)prm.chunks_b) * prm.chunk_spp_b;
+        s1 = min(prm.spp, s0 + prm.chunk_spp_b);
+    }
+}
 
 RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, int s, PathState& ps) {   // :517-520
     ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)(y * prm.width + x), (uint32_t)s);

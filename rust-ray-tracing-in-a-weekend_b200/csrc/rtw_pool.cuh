@@ -125,9 +125,7 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                     slot = P.trav[k];
                     Ray ray; ray.o = mk(P.ox[slot], P.oy[slot], P.oz[slot]); ray.d = mk(P.dx[slot], P.dy[slot], P.dz[slot]); ray.time = P.tm[slot];
                     r = make_tray(ray);
-                    inv = mk(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-                    oi = mk(r.o.x * inv.x, r.o.y * inv.y, r.o.z * inv.z);
-                    slack = slab_slack(oi);
+                    slab_setup(r.o, r.d, inv, oi, slack);
                     t_best = CUDART_INF_F; prim_best = -1; skip = P.last[slot];
                     sp = 1; leaf = 0; node = sc.n_bvh_prims ? 0 : RTW_SENTINEL;
                     active = true; ++rays;

@@ -119,8 +119,11 @@ struct DParams {
     float bg_r, bg_g, bg_b, t_min;
     uint32_t seed_lo, seed_hi;
     int32_t tiles_x, tiles_y;          // 8x4-pixel tiles
-    int32_t chunks, chunk_spp;         // samples split into `chunks` units of `chunk_spp` per tile
-    uint32_t n_units;
+    int32_t chunks, chunk_spp;         // phase A: samples [0, spp_a) of every tile in `chunks` units of `chunk_spp`
+    uint32_t n_units;                  // phase A + phase B
+    uint32_t n_units_a;                // = tiles * chunks
+    int32_t spp_a;                     // samples handled by phase A (= spp when there is no phase B)
+    int32_t chunks_b, chunk_spp_b;     // phase B: samples [spp_a, spp) in `chunks_b` small units (short end-of-frame tail)
     int32_t accumulate;                // 1: atomicAdd into the framebuffer (several units or GPUs per pixel)
     int32_t no_tile_cull;              // 1: primary rays traverse the BVH like all others (RTW_FLAG_NO_TILE_CULL)
 };

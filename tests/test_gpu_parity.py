@@ -521,6 +521,20 @@ def test_final_scene_full_config(pkg, gpu):
     assert np.abs(blk(full) / 10000 - blk(part) / 1000).max() <= 0.05 * blk(full).max() / 10000
 
 
+@pytest.mark.parametrize("W,H,spp,spu", [(37, 23, 160, 0), (101, 53, 163, 0), (64, 64, 500, 0), (1200, 800, 161, 0), (40, 20, 1000, 0), (37, 23, 163, 40)])
+def test_work_units_cover_every_sample_once(pkg, gpu, W, H, spp, spu):
+    """Work units = (tile, sample range) in two phases (big units, then short ones): with an empty world every
+    sample returns exactly the background (1, 2, 4), so each pixel sum must be spp * background EXACTLY (small integers
+    in f32) - a sample range covered twice or skipped shows up in every pixel of its tile."""
+    sc = pkg.Scene(gpu)
+    sc.commit(1, 0)
+    cam = gpu.camera_new((0, 0, 5), (0, 0, 0), (0, 1, 0), 40.0, W / H, 0.1, 5.0)
+    for flags in (pkg.api.RTW_FLAG_KERNEL_MEGA, pkg.api.RTW_FLAG_KERNEL_POOL):
+        img, st = sc.render(cam, pkg.make_params(W, H, spp, background=(1.0, 2.0, 4.0), samples_per_unit=spu, flags=flags))
+        assert st["rays"] == W * H * spp
+        assert (img == np.array([1.0, 2.0, 4.0], np.float32) * spp).all()
+
+
 def test_render_edge_cases(pkg, gpu, orc):
     # empty world: every sample returns the background (src/main.rs:37)
     sc = pkg.Scene(gpu)

@@ -7,7 +7,7 @@ for l in out:
     if "Function :" in l: on = sys.argv[2] in l
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if on and m: ins.append((int(m.group(1), 16), m.group(2).strip()))
-k = next(i for i, (a, t) in enumerate(ins) if "1.0000003576" in t and "FFMA" in t)
+k = next(i for i, (a, t) in enumerate(ins) if re.search(r"FFMA .*1\.00000[0-9]+", t))
 for j in range(k, len(ins)):
     m = re.search(r"BRA\s+(?:P\d, )?0x([0-9a-f]+)", ins[j][1])
     if m and int(m.group(1), 16) < ins[k][0]:
