@@ -509,11 +509,11 @@ RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool
         double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
         double td = (double)t;
         double f = (r.ga() * td + 2.0 * half_b) * td + c, fp = 2.0 * (r.ga() * td + half_b);
-        td -= (double)((float)f / (float)fp);
+        td -= (double)__fdividef((float)f, (float)fp);
         rec.t = (float)td;
         double px = fma(td, r.gdx(), r.gox()), py = fma(td, r.gdy(), r.goy()), pz = fma(td, r.gdz(), r.goz());
         rec.p = mk((float)px, (float)py, (float)pz);
-        float inv_r = 1.0f / (float)rad;
+        float inv_r = rcp_approx((float)rad);
         V3 ow = mk((float)(px - cx) * inv_r, (float)(py - cy) * inv_r, (float)(pz - cz) * inv_r);
         outward_obj = xf ? mk(mc * ow.x - ms * ow.z, ow.y, ms * ow.x + mc * ow.z) : ow;
         if (want_uv) sphere_uv(outward_obj, rec.u, rec.v);
@@ -526,8 +526,8 @@ RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool
         if (meta.x == PRIM_XY) { a = o.x + t * d.x; b = o.y + t * d.y; outward_obj = mk(0.f, 0.f, 1.f); }
         else if (meta.x == PRIM_XZ) { a = o.x + t * d.x; b = o.z + t * d.z; outward_obj = mk(0.f, 1.f, 0.f); }
         else { a = o.y + t * d.y; b = o.z + t * d.z; outward_obj = mk(1.f, 0.f, 0.f); }
-        rec.u = (a - ab.x) / (ab.y - ab.x);
-        rec.v = (b - ab.z) / (ab.w - ab.z);
+        rec.u = __fdividef(a - ab.x, ab.y - ab.x);
+        rec.v = __fdividef(b - ab.z, ab.w - ab.z);
     }
     set_face_normal(d_obj, outward_obj, rec.normal, rec.front);
     if (xf) {
@@ -571,11 +571,11 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     if (t2 > t_max) t2 = t_max;
     if (t1 >= t2) return false;
     if (t1 < 0.0f) t1 = 0.0f;
-    float ray_length = sqrtf(length_squared(r.d));
+    float ray_length = sqrt_approx(length_squared(r.d));
     float distance_inside_boundary = (t2 - t1) * ray_length;
     float hit_distance = __int_as_float(md.z) * logf(g.next());                            // :446 — the draw
     if (hit_distance > distance_inside_boundary) return false;
-    t_out = t1 + hit_distance / ray_length;
+    t_out = t1 + __fdividef(hit_distance, ray_length);
     mat_out = md.w;
     return true;
 }
@@ -610,7 +610,7 @@ RTW_DEV bool world_hit(const DScene& sc, const TRay& r, float t_min, float t_max
 // src/material.rs — emitted (:25-34), scatter (:15-23, :36-94)
 // ------------------------------------------------------------------------------------------------
 RTW_DEV float reflectance(float cosine, float ref_idx) {                                    // :89-94
-    float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+    float r0 = __fdividef(1.0f - ref_idx, 1.0f + ref_idx);
     r0 = r0 * r0;
     float x = 1.0f - cosine, x2 = x * x;
     return r0 + (1.0f - r0) * (x2 * x2 * x);                                               // powf(5.0)
@@ -652,7 +652,9 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
         // f64 island: near the critical angle 1 - |r_perp|^2 (src/math.rs:114) cancels to ~1e-5 and an f32 cos(theta)
         // (1e-7 absolute) would leave 1e-4 on the refracted direction.  B200: FP64 at half rate, 8 % of the hits.
         attenuation = mk(1.f, 1.f, 1.f);
-        const double ratio = rec.front ? 1.0 / (double)m.param : (double)m.param;
+        // 1 / ir: MUFU.RCP + one f64 Newton step (error 2^-46) instead of the f64 division sequence
+        const double ir = (double)m.param, ir_r = (double)rcp_approx(m.param);
+        const double ratio = rec.front ? ir_r * (2.0 - ir * ir_r) : ir;
         const double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z, nx = rec.normal.x, ny = rec.normal.y, nz = rec.normal.z;
         const double dd = dx * dx + dy * dy + dz * dz;
         double inv = (double)rsqrtf((float)dd);
@@ -667,7 +669,7 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
         } else {                                                                           // refract :110-117
             const double px = ratio * (ux + cos_theta * nx), py = ratio * (uy + cos_theta * ny), pz = ratio * (uz + cos_theta * nz);
             const double k = 1.0 - (px * px + py * py + pz * pz);
-            const double par = -(double)sqrtf((float)fabs(k));
+            const double par = -(double)sqrt_approx((float)fabs(k));
             scattered.d = mk((float)(px + par * nx), (float)(py + par * ny), (float)(pz + par * nz));
         }
         return true;
@@ -796,8 +798,10 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps, V3& 
 struct RayBounds { float ll[3], lh[3], wl[3], wh[3]; };
 
 RTW_DEV RayBounds tile_ray_bounds(const DCamera& c, const DParams& prm, int x0, int y0, int tw, int th) {
-    const float s_lo = (float)x0 / ((float)prm.width - 1.0f), s_hi = (float)(x0 + tw) / ((float)prm.width - 1.0f);
-    const float t_lo = (float)y0 / ((float)prm.height - 1.0f), t_hi = (float)(y0 + th) / ((float)prm.height - 1.0f);
+    // (2-ulp divisions: the window is padded by 2e-5 relative below)
+    const float iw = rcp_approx((float)prm.width - 1.0f), ih = rcp_approx((float)prm.height - 1.0f);
+    const float s_lo = (float)x0 * iw, s_hi = (float)(x0 + tw) * iw;
+    const float t_lo = (float)y0 * ih, t_hi = (float)(y0 + th) * ih;
     const float sc_ = 0.5f * (s_lo + s_hi), ds = 0.5f * (s_hi - s_lo), tc = 0.5f * (t_lo + t_hi), dt = 0.5f * (t_hi - t_lo);
     const float R = fabsf(c.lens_radius);
     const float o[3] = {c.ox, c.oy, c.oz}, l[3] = {c.lx, c.ly, c.lz}, h[3] = {c.hx, c.hy, c.hz}, v[3] = {c.vx, c.vy, c.vz};
@@ -819,7 +823,7 @@ RTW_DEV RayBounds tile_ray_bounds(const DCamera& c, const DParams& prm, int x0, 
 RTW_DEV void clip_linear(float x, float dx, float bound, bool le, float& a, float& b) {
     const float n = bound - x;
     if (dx == 0.0f) { if (le ? (n < 0.0f) : (n > 0.0f)) { a = 1.0f; b = 0.0f; } return; }
-    const float t = n / dx;
+    const float t = __fdividef(n, dx);              // 2 ulp, inside the 1e-5 slack of bounds_hit_box
     if ((dx > 0.0f) == le) b = fminf(b, t); else a = fmaxf(a, t);
 }
 
