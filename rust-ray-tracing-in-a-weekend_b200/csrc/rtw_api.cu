@@ -51,7 +51,7 @@ template <int F>
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
 render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
-    __shared__ float acc[RTW_WARPS][96];                  // per-warp tile accumulator (32 px x rgb)
+    __shared__ __align__(16) float acc[RTW_WARPS][96];    // per-warp tile accumulator (32 px x rgb)
     __shared__ float ring[RTW_WARPS][12][64];             // secondary-ray ring: o(3) d(3) time T(3) last_prim meta, 64 per warp
     __shared__ int tlist[RTW_WARPS][RTW_TILE_LIST];       // primitives the tile's primary rays can touch
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -204,15 +204,7 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
             } else if (work) alive = cont;
         }
         __syncwarp();
-        {   // tile -> framebuffer, row 0 = top (y = H-1 of src/main.rs:591)
-            const int x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
-            if (x < prm.width && y < prm.height) {
-                float* dst = fb + ((size_t)(prm.height - 1 - y) * prm.width + x) * 3;
-                const float r = acc[warp][lane * 3], g = acc[warp][lane * 3 + 1], b = acc[warp][lane * 3 + 2];
-                if (prm.accumulate) { atomicAdd_system(dst, r); atomicAdd_system(dst + 1, g); atomicAdd_system(dst + 2, b); }
-                else { dst[0] = r; dst[1] = g; dst[2] = b; }
-            }
-        }
+        flush_tile(prm, fb, acc[warp], tx, ty, tw, lane);
         __syncwarp();
     }
     // ray statistics: one atomic per warp
@@ -288,15 +280,7 @@ render_pool_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict
             shade_list<POOL, K_ISO>(P, lane, sc, prm, tile_x0, tile_y0);
             __syncwarp();
         }
-        {   // tile -> framebuffer, row 0 = top (y = H-1 of src/main.rs:591)
-            const int x = tile_x0 + (lane & 7), y = tile_y0 + (lane >> 3);
-            if (x < prm.width && y < prm.height) {
-                float* dst = fb + ((size_t)(prm.height - 1 - y) * prm.width + x) * 3;
-                const float r = P.acc[lane * 3], g = P.acc[lane * 3 + 1], b = P.acc[lane * 3 + 2];
-                if (prm.accumulate) { atomicAdd_system(dst, r); atomicAdd_system(dst + 1, g); atomicAdd_system(dst + 2, b); }
-                else { dst[0] = r; dst[1] = g; dst[2] = b; }
-            }
-        }
+        flush_tile(prm, fb, P.acc, tile_x0 >> 3, tile_y0 >> 2, tw, lane);
         __syncwarp();
     }
     for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);

@@ -36,7 +36,7 @@ struct PoolSmem {
     unsigned meta[POOL];                         // pix(5) | segment(6) << 5 | media draws(4) << 11 | sample(17) << 15
     unsigned char list[K_NKIND][POOL];
     unsigned char trav[POOL], freel[POOL];
-    float acc[96];
+    __align__(16) float acc[96];
     int cnt[8];
 };
 
