@@ -140,12 +140,31 @@ int rtw_scene_commit(rtw_scene*, int32_t n_gpus, int32_t first_device);
  * row-major H x W x 3 float, row 0 = TOP (= y = H-1 of src/main.rs:591). */
 int rtw_render(rtw_scene*, const rtw_camera*, const rtw_render_params*, float* out_rgb_sum, rtw_stats* stats);
 
+/* Progressive accumulation / resume with a progress callback: replaces the busy-poll progress thread
+ * (src/main.rs:557-582) and the all-or-nothing output (src/main.rs:591-596).
+ * Renders samples [first_sample, params->spp) in passes of `samples_per_pass` (0 = ten passes).  When first_sample > 0,
+ * inout_rgb_sum must hold the sums of samples [0, first_sample) on entry (the buffer of an earlier, interrupted call);
+ * it holds the sums of everything rendered so far whenever `progress` runs and on return.  The sample index is a
+ * coordinate of the Philox counter, so ANY split into passes or resumes yields the image of one rtw_render call
+ * (up to f32 summation order).  `progress` (may be NULL) returns non-zero to stop after the current pass: RTW_OK is
+ * returned and stats->paths says how far the render got.  RTW_FLAG_DEVICE_OUT is not supported here. */
+typedef int (*rtw_progress_fn)(int32_t samples_done, int32_t samples_total, const float* rgb_sum, void* user);
+int rtw_render_progressive(rtw_scene*, const rtw_camera*, const rtw_render_params*, int32_t first_sample,
+                           int32_t samples_per_pass, float* inout_rgb_sum, rtw_progress_fn progress, void* user,
+                           rtw_stats* stats);
+
 /* Page-locked host memory for out_rgb_sum: the D2H of the framebuffer then runs at PCIe speed (optional). */
 void* rtw_host_alloc(uint64_t bytes);
 void rtw_host_free(void* p);
 
 /* write_color (src/math.rs:119-132) on the device: sums -> 8-bit rgb, same row order. */
 int rtw_write_color(const float* rgb_sum, int32_t n_pixels, int32_t spp, uint8_t* out_rgb8);
+
+/* Output files (host only).  rtw_write_ppm: the P3 text the reference prints on stdout — header "P3\n{W} {H}\n255\n\n"
+ * (src/main.rs:472), one "r g b" line per pixel (src/math.rs:127-131), rows top to bottom (src/main.rs:591-596).
+ * rtw_write_png: the same pixels as an 8-bit RGB PNG (stored deflate blocks). */
+int rtw_write_ppm(const char* path, const uint8_t* rgb8, int32_t width, int32_t height);
+int rtw_write_png(const char* path, const uint8_t* rgb8, int32_t width, int32_t height);
 
 /* ---- multi-process (one rank per GPU) plumbing: CUDA IPC on the shared framebuffer + tile counter ---- */
 #define RTW_IPC_HANDLE_BYTES 160

@@ -182,6 +182,9 @@ class Lib:
             fp = C.POINTER(C.c_float)
             f("scene_commit").argtypes = [vp, C.c_int32, C.c_int32]
             f("render").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]
+            f("render_progressive").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_int32, C.c_int32, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+            f("render_progressive").restype = C.c_int
             f("write_color").argtypes = [fp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
             f("device_count").restype = C.c_int
             f("version").restype = C.c_char_p
@@ -261,6 +264,20 @@ def load_oracle():
     if "orc" not in _libs:
         _libs["orc"] = Lib(ORACLE_LIB_PATH, "orc_")
     return _libs["orc"]
+
+
+def write_ppm(lib, path, rgb8, width, height):
+    """rtw_write_ppm: the reference's P3 text output (src/main.rs:472, :591-596) as a file."""
+    a = np.ascontiguousarray(rgb8, np.uint8)
+    assert a.size == width * height * 3
+    lib.check(lib.f("write_ppm")(str(path).encode(), a.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int32(width), C.c_int32(height)))
+
+
+def write_png(lib, path, rgb8, width, height):
+    """rtw_write_png: 8-bit RGB PNG of the same pixels."""
+    a = np.ascontiguousarray(rgb8, np.uint8)
+    assert a.size == width * height * 3
+    lib.check(lib.f("write_png")(str(path).encode(), a.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int32(width), C.c_int32(height)))
 
 
 class Scene:
@@ -385,6 +402,23 @@ class Scene:
         st = Stats()
         self._c("render", C.byref(cam), C.byref(params), out.ctypes.data_as(C.c_void_p), C.byref(st))
         return out, st.as_dict()
+
+    def render_progressive(self, cam, params, first_sample=0, samples_per_pass=0, buf=None, progress=None):
+        """rtw_render_progressive: samples [first_sample, params.spp) in passes; `buf` carries the sums of the samples
+        below first_sample (resume).  progress(done, total, image_view) -> truthy to stop.  Returns (image, stats)."""
+        assert not self.lib.is_oracle
+        if buf is None:
+            assert first_sample == 0, "resuming needs the buffer of the interrupted render"
+            buf = np.zeros((params.height, params.width, 3), np.float32)
+        assert buf.dtype == np.float32 and buf.shape == (params.height, params.width, 3) and buf.flags.c_contiguous
+        FN = C.CFUNCTYPE(C.c_int, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p)
+        def _cb(done, total, _ptr, _user):
+            return 1 if (progress is not None and progress(done, total, buf)) else 0
+        cb = FN(_cb)
+        st = Stats()
+        self._c("render_progressive", C.byref(cam), C.byref(params), C.c_int32(first_sample), C.c_int32(samples_per_pass),
+                buf.ctypes.data_as(C.c_void_p), C.cast(cb, C.c_void_p), None, C.byref(st))
+        return buf, st.as_dict()
 
     def render_device(self, cam, params, dev_ptr):
         """rtw_render with RTW_FLAG_DEVICE_OUT: the sums stay in HBM at dev_ptr (no D2H)."""

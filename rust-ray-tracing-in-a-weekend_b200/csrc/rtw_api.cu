@@ -936,6 +936,58 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     return RTW_OK;
 }
 
+int rtw_render_progressive(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, int32_t first_sample, int32_t samples_per_pass,
+                           float* inout, rtw_progress_fn progress, void* user, rtw_stats* st) {
+    if (!s || !cam || !p || !inout) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "rtw_scene_commit has not been called since the last edit");
+    if (p->flags & RTW_FLAG_DEVICE_OUT) return fail(RTW_ERR_INVALID_ARG, "rtw_render_progressive works on a host buffer");
+    if (first_sample < 0 || first_sample > p->spp || samples_per_pass < 0) return fail(RTW_ERR_INVALID_ARG, "bad sample range");
+    double t0 = now_ms();
+    int n_rep = p->n_gpus > 0 ? p->n_gpus : (int)s->reps.size();
+    if (n_rep > (int)s->reps.size()) return fail(RTW_ERR_INVALID_ARG, "n_gpus exceeds the committed replicas");
+    int total_warps = 0;
+    for (int i = 0; i < n_rep; ++i) total_warps += s->reps[i].grid * RTW_WARPS;
+    if (st) { std::memset(st, 0, sizeof(*st)); fill_scene_stats(s, st); }
+    const int per_pass = samples_per_pass > 0 ? samples_per_pass : (p->spp + 9) / 10 > 0 ? (p->spp + 9) / 10 : 1;
+    Replica& r0 = s->reps[0];
+    const size_t fb_bytes = (size_t)p->width * p->height * 3 * sizeof(float);
+    TRY(ensure_fb(s->local, r0.device, p->width, p->height));
+    float* fb = s->local.fb();
+    CUDA_TRY(cudaSetDevice(r0.device));
+    // the device framebuffer carries the running sums across passes; a resume starts from the caller's checkpoint
+    if (first_sample > 0) { CUDA_TRY(cudaMemcpyAsync(fb, inout, fb_bytes, cudaMemcpyHostToDevice, r0.stream)); if (st) st->h2d_bytes += fb_bytes; }
+    else CUDA_TRY(cudaMemsetAsync(fb, 0, fb_bytes, r0.stream));
+    int done = first_sample;
+    double ms_render = 0; uint64_t rays = 0; uint64_t units[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int launches = 0;
+    if (done >= p->spp) { CUDA_TRY(cudaStreamSynchronize(r0.stream)); if (first_sample == 0) std::memset(inout, 0, fb_bytes); }
+    while (done < p->spp) {
+        rtw_render_params pass = *p;
+        pass.spp = p->spp - done < per_pass ? p->spp - done : per_pass;
+        DParams dp; TRY(make_params(pass, total_warps, dp));
+        dp.first_sample = done;
+        dp.accumulate = 1;
+        CUDA_TRY(cudaSetDevice(r0.device));
+        CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
+        CUDA_TRY(cudaStreamSynchronize(r0.stream));               // peers (and the next pass) must see counter + sums
+        rtw_stats ps; std::memset(&ps, 0, sizeof(ps));
+        TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, &ps, kernel_mode(p->flags)));
+        ms_render += ps.ms_render; rays += ps.rays; launches += ps.kernel_launches;
+        for (int i = 0; i < 8; ++i) units[i] += ps.units_per_device[i];
+        done += pass.spp;
+        CUDA_TRY(cudaSetDevice(r0.device));
+        CUDA_TRY(cudaMemcpy(inout, fb, fb_bytes, cudaMemcpyDeviceToHost));
+        if (st) st->d2h_bytes += fb_bytes;
+        if (progress && progress(done, p->spp, inout, user) != 0) break;
+    }
+    if (st) {
+        st->ms_render = ms_render; st->rays = rays; st->kernel_launches = launches; st->n_devices = n_rep;
+        for (int i = 0; i < 8; ++i) st->units_per_device[i] = units[i];
+        st->paths = (uint64_t)p->width * p->height * (uint64_t)(done - first_sample);
+        st->ms_total = now_ms() - t0;
+    }
+    return RTW_OK;
+}
+
 void* rtw_host_alloc(uint64_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) { cudaGetLastError(); fail(RTW_ERR_OOM, "cudaMallocHost failed"); return nullptr; }

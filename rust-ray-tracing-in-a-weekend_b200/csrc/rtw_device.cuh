@@ -722,6 +722,7 @@ RTW_DEV void decode_unit(const DParams& prm, unsigned unit, int& tile, int& s0, 
         s0 = prm.spp_a + (int)(u % (unsigned)prm.chunks_b) * prm.chunk_spp_b;
         s1 = min(prm.spp, s0 + prm.chunk_spp_b);
     }
+    s0 += prm.first_sample; s1 += prm.first_sample;      // progressive pass: the Philox sample coordinate is absolute
 }
 
 // Finished tile (32 pixels x rgb in shared memory, 16-byte aligned) -> framebuffer; row 0 of the image = top

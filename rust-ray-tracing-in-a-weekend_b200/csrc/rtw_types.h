@@ -126,6 +126,7 @@ struct DParams {
     int32_t chunks_b, chunk_spp_b;     // phase B: samples [spp_a, spp) in `chunks_b` small units (short end-of-frame tail)
     int32_t accumulate;                // 1: atomicAdd into the framebuffer (several units or GPUs per pixel)
     int32_t no_tile_cull;              // 1: primary rays traverse the BVH like all others (RTW_FLAG_NO_TILE_CULL)
+    int32_t first_sample;              // sample index of this launch's sample 0 (progressive passes / resume)
 };
 
 #endif

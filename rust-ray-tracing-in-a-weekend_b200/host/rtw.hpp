@@ -181,6 +181,21 @@ public:
         if (stats) *stats = st;
         return out;
     }
+    // The same render in passes with a progress callback (what the reference's progress thread reports, src/main.rs:557-582);
+    // `sums` may carry an interrupted render (then first_sample > 0).  progress(done, total, sums) -> true to stop.
+    template <class Progress>
+    void render_progressive(const Camera& cam, int width, int height, int spp, int max_depth, Color background, uint64_t seed,
+                            int first_sample, int samples_per_pass, std::vector<float>& sums, Progress progress, rtw_stats* stats = nullptr) {
+        rtw_render_params p{};
+        p.width = width; p.height = height; p.spp = spp; p.max_depth = max_depth;
+        p.background[0] = background.x; p.background[1] = background.y; p.background[2] = background.z;
+        p.t_min = 0.001; p.seed = seed;
+        sums.resize((size_t)width * height * 3);
+        rtw_stats st{};
+        auto tramp = [](int32_t done, int32_t total, const float* rgb, void* user) -> int { return (*static_cast<Progress*>(user))(done, total, rgb) ? 1 : 0; };
+        ok(rtw_render_progressive(s_, &cam.c, &p, first_sample, samples_per_pass, sums.data(), tramp, &progress, &st));
+        if (stats) *stats = st;
+    }
 
 private:
     rtw_scene* s_;

@@ -1,7 +1,9 @@
 // rtw_main.cpp — replacement for the reference's main() (src/main.rs:307-599) on top of the C++ mirror: pick a scene,
 // build World + Camera with the reference's constructors, flatten, render on the GPU(s), write_color, print the P3 image
 // byte-compatibly with src/main.rs:472 and :591-596.
-//   rtw_main --scene 0 --width 120 --height 80 --spp 16 [--gpus N] [--seed 1] [--earth earth.rgb] [--dry-run] > out.ppm
+//   rtw_main --scene 0 --width 120 --height 80 --spp 16 [--gpus N] [--seed 1] [--earth earth.rgb] [--passes K] [--png out.png] [--dry-run] > out.ppm
+//   --passes K: render in K passes and report "\rProgress: done/total samples" on stderr after each (the reference's progress
+//   thread, src/main.rs:557-582, busy-polls per-thread pixel counters instead)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -13,9 +15,9 @@
 extern "C" int rtw_debug_flatten(rtw_scene*, int32_t*, double*);
 
 int main(int argc, char** argv) {
-    int scene_id = 0, width = 0, height = 0, spp = 0, gpus = 1, dry = 0, max_depth = 50;     // max_depth: src/main.rs:310
+    int scene_id = 0, width = 0, height = 0, spp = 0, gpus = 1, dry = 0, passes = 0, max_depth = 50;     // max_depth: src/main.rs:310
     unsigned long long seed = 1;
-    std::string earth;
+    std::string earth, png;
     for (int i = 1; i < argc; ++i) {
         auto is = [&](const char* k) { return !strcmp(argv[i], k) && i + 1 < argc; };
         if (is("--scene")) scene_id = atoi(argv[++i]);
@@ -26,6 +28,8 @@ int main(int argc, char** argv) {
         else if (is("--seed")) seed = strtoull(argv[++i], nullptr, 10);
         else if (is("--depth")) max_depth = atoi(argv[++i]);
         else if (is("--earth")) earth = argv[++i];
+        else if (is("--passes")) passes = atoi(argv[++i]);
+        else if (is("--png")) png = argv[++i];
         else if (!strcmp(argv[i], "--dry-run")) dry = 1;
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
@@ -55,10 +59,19 @@ int main(int argc, char** argv) {
         auto t0 = std::chrono::steady_clock::now();
         be.commit(gpus, 0);
         rtw_stats st{};
-        std::vector<float> sums = be.render(cam, sd.image_width, sd.image_height, sd.samples_per_pixel, max_depth, sd.background, seed, &st);
+        std::vector<float> sums;
+        if (passes > 1) {
+            const int per_pass = (sd.samples_per_pixel + passes - 1) / passes;
+            be.render_progressive(cam, sd.image_width, sd.image_height, sd.samples_per_pixel, max_depth, sd.background, seed, 0, per_pass, sums,
+                                  [](int done, int total, const float*) { fprintf(stderr, "\rProgress: %d/%d samples", done, total); return false; }, &st);
+            fprintf(stderr, "\n");
+        } else {
+            sums = be.render(cam, sd.image_width, sd.image_height, sd.samples_per_pixel, max_depth, sd.background, seed, &st);
+        }
         const int n = sd.image_width * sd.image_height;
         std::vector<uint8_t> rgb((size_t)n * 3);
         if (rtw_write_color(sums.data(), n, sd.samples_per_pixel, rgb.data()) != RTW_OK) throw std::runtime_error(rtw_last_error());
+        if (!png.empty() && rtw_write_png(png.c_str(), rgb.data(), sd.image_width, sd.image_height) != RTW_OK) throw std::runtime_error("cannot write " + png);
         printf("P3\n%d %d\n255\n\n", sd.image_width, sd.image_height);              // println!("P3\n{} {}\n255\n") src/main.rs:472
         for (int i = 0; i < n; ++i) printf("%d %d %d\n", rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]);   // rows already top first (:591)
         double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

@@ -535,6 +535,36 @@ def test_work_units_cover_every_sample_once(pkg, gpu, W, H, spp, spu):
         assert (img == np.array([1.0, 2.0, 4.0], np.float32) * spp).all()
 
 
+@pytest.mark.parametrize("name", ["random_scene", "cornell_box_smoke"])
+def test_progressive_and_resume_equal_one_shot(pkg, gpu, name):
+    """rtw_render_progressive (replaces the progress thread src/main.rs:557-582 and the all-or-nothing output :591-596):
+    the sample index is a Philox counter coordinate, so passes of any size - and a render stopped by the callback and
+    resumed from its buffer - give the image of ONE rtw_render call up to f32 summation order, with the same ray count."""
+    sc, spec = pkg.scenes.build(gpu, name)
+    sc.commit(1, 0)
+    W, H, spp = 93, 61, 50
+    cam = spec.camera(gpu, W, H)
+    p = pkg.make_params(W, H, spp, background=spec.background, seed=9)
+    ref, st0 = sc.render(cam, p)
+    tol = 2e-5 * max(np.abs(ref).max(), 1.0)
+    seen = []
+    img, st1 = sc.render_progressive(cam, p, samples_per_pass=7, progress=lambda d, t, b: seen.append((d, t, float(b.sum()))) and False)
+    assert [d for d, _, _ in seen] == [7, 14, 21, 28, 35, 42, 49, 50] and all(t == spp for _, t, _ in seen)
+    assert all(b > a for (_, _, a), (_, _, b) in zip(seen, seen[1:]))          # the sums grow pass by pass
+    assert st1["rays"] == st0["rays"] and st1["paths"] == W * H * spp and st1["kernel_launches"] == 8
+    assert np.abs(img - ref).max() <= tol
+    # stop after 20 samples, then resume from the buffer
+    part, st2 = sc.render_progressive(cam, p, samples_per_pass=10, progress=lambda d, t, b: d >= 20)
+    assert st2["paths"] == W * H * 20
+    first20, _ = sc.render(cam, pkg.make_params(W, H, 20, background=spec.background, seed=9))
+    assert np.abs(part - first20).max() <= tol                                   # a prefix of the sample sequence
+    full, st3 = sc.render_progressive(cam, p, first_sample=20, samples_per_pass=0, buf=part.copy())
+    assert st3["paths"] == W * H * 30 and st2["rays"] + st3["rays"] == st0["rays"]
+    assert np.abs(full - ref).max() <= tol
+    with pytest.raises(pkg.RtwError):
+        sc.render_progressive(cam, p, first_sample=spp + 1, buf=part.copy())
+
+
 def test_render_edge_cases(pkg, gpu, orc):
     # empty world: every sample returns the background (src/main.rs:37)
     sc = pkg.Scene(gpu)
@@ -645,6 +675,18 @@ def test_cpp_mirror_main_matches_python_path(pkg, gpu, scene_id, name, tmp_path)
     gpu.check(gpu.f("write_color")(img.ctypes.data_as(C.POINTER(C.c_float)), W * H, spp, out.ctypes.data_as(C.POINTER(C.c_uint8))))
     diff = np.abs(vals - out.reshape(H, W, 3).astype(np.int64))
     assert diff.max() <= 1 and np.mean(diff > 0) < 0.01
+    # the same render in 4 passes with progress lines on stderr, and a PNG next to the P3 text
+    import struct, zlib
+    png = tmp_path / "o.png"
+    r2 = subprocess.run([exe, "--scene", str(scene_id), "--width", str(W), "--height", str(H), "--spp", str(spp), "--earth", str(earth),
+                         "--passes", "4", "--png", str(png)], capture_output=True, text=True, check=True)
+    assert "Progress: 4/16 samples" in r2.stderr and "Progress: 16/16 samples" in r2.stderr
+    vals2 = np.array(r2.stdout.split()[4:], dtype=np.int64).reshape(H, W, 3)
+    assert np.abs(vals2 - vals).max() <= 1 and np.mean(vals2 != vals) < 0.01
+    raw = png.read_bytes()
+    n_idat, = struct.unpack(">I", raw[33:37])
+    lines = np.frombuffer(zlib.decompress(raw[41:41 + n_idat]), np.uint8).reshape(H, 1 + 3 * W)
+    assert np.array_equal(lines[:, 1:].reshape(H, W, 3), vals2)
 
 
 def test_sweep_scene_parity_and_bulk_api(pkg, gpu, orc):

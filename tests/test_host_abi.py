@@ -178,3 +178,32 @@ def test_cpp_mirror_flattens_like_the_python_binding(pkg, rtw, name):
         assert got[k] == want[k], (k, got, want)
     r = subprocess.run([exe, "--scene", "9", "--dry-run"], capture_output=True, text=True)
     assert r.returncode == 1 and "Unsupported scene selected" in r.stderr          # src/main.rs:461-463, as an error not a panic
+
+
+def test_output_files_ppm_and_png(pkg, rtw, tmp_path):
+    """Output stage (host only): rtw_write_ppm reproduces the reference's stdout bytes — header
+    "P3\\n{W} {H}\\n255\\n\\n" (src/main.rs:472), one "r g b" line per pixel (src/math.rs:127-131), rows top to bottom —
+    and rtw_write_png stores the same pixels in a valid PNG (signature, chunk CRCs, zlib stream, filter-0 scanlines)."""
+    import struct, zlib
+    rs = np.random.RandomState(5)
+    for W, H in ((7, 5), (300, 131), (1, 1)):                    # 300x131x3 > 65535: several stored deflate blocks
+        img = rs.randint(0, 256, (H, W, 3)).astype(np.uint8)
+        ppm, png = tmp_path / f"a{W}.ppm", tmp_path / f"a{W}.png"
+        pkg.api.write_ppm(rtw, ppm, img, W, H)
+        pkg.api.write_png(rtw, png, img, W, H)
+        want = f"P3\n{W} {H}\n255\n\n" + "".join(f"{r} {g} {b}\n" for r, g, b in img.reshape(-1, 3))
+        assert ppm.read_text() == want
+        raw = png.read_bytes()
+        assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(raw):
+            n, = struct.unpack(">I", raw[pos:pos + 4]); typ = raw[pos + 4:pos + 8]; data = raw[pos + 8:pos + 8 + n]
+            crc, = struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])
+            assert zlib.crc32(typ + data) == crc
+            chunks.append((typ, data)); pos += 12 + n
+        assert [t for t, _ in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        assert struct.unpack(">IIBBBBB", chunks[0][1]) == (W, H, 8, 2, 0, 0, 0)
+        lines = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(H, 1 + 3 * W)
+        assert (lines[:, 0] == 0).all() and np.array_equal(lines[:, 1:].reshape(H, W, 3), img)
+    with pytest.raises(pkg.RtwError):
+        pkg.api.write_png(rtw, tmp_path / "no_such_dir" / "x.png", img, 1, 1)
