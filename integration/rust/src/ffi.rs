@@ -1,7 +1,7 @@
 // NOT COMPILED IN THIS REPO: rustc/cargo are absent from the build image.
 // Reviewed source of the Rust side of the drop-in; the same call sequence is exercised by host/rtw.hpp (C++) and api.py.
 #![allow(non_camel_case_types)]
-use std::os::raw::{c_char, c_double, c_int};
+use std::os::raw::{c_char, c_double, c_int, c_void};
 
 #[repr(C)] pub struct rtw_scene { _private: [u8; 0] }
 
@@ -54,4 +54,11 @@ extern "C" {
     pub fn rtw_scene_commit(s: *mut rtw_scene, n_gpus: i32, first_device: i32) -> c_int;
     pub fn rtw_render(s: *mut rtw_scene, cam: *const rtw_camera, p: *const rtw_render_params, out_rgb_sum: *mut f32, stats: *mut rtw_stats) -> c_int;
     pub fn rtw_write_color(rgb_sum: *const f32, n_pixels: i32, spp: i32, out_rgb8: *mut u8) -> c_int;
+    // progressive passes / resume + progress callback (replaces the progress thread, src/main.rs:557-582)
+    pub fn rtw_render_progressive(s: *mut rtw_scene, cam: *const rtw_camera, p: *const rtw_render_params, first_sample: i32, samples_per_pass: i32,
+                                  inout_rgb_sum: *mut f32, progress: Option<extern "C" fn(i32, i32, *const f32, *mut c_void) -> c_int>,
+                                  user: *mut c_void, stats: *mut rtw_stats) -> c_int;
+    // output files: the P3 text of src/main.rs:472 + :591-596, or a PNG of the same pixels
+    pub fn rtw_write_ppm(path: *const c_char, rgb8: *const u8, width: i32, height: i32) -> c_int;
+    pub fn rtw_write_png(path: *const c_char, rgb8: *const u8, width: i32, height: i32) -> c_int;
 }
