@@ -1,10 +1,12 @@
 // rtw_api.cu — kernels + the C ABI of include/rtw.h.
 //
-// Render = ONE persistent megakernel per GPU (render_kernel): every warp pulls work units (an 8x4-pixel
-// tile x a chunk of samples) from a single atomic counter that all GPUs share, keeps its 32 lanes busy with
-// in-warp path regeneration (ballot + prefix popcount), accumulates radiance per tile in shared memory and
-// adds the finished tile straight into the framebuffer on the first GPU (peer stores over NVLink — the
-// "gather" of src/main.rs:542-547 is fused into the kernel).  Replaces src/main.rs:497-589.
+// Render = ONE persistent megakernel per GPU (render_kernel<F>, F = the scene's feature set): every warp pulls work
+// units (an 8x4-pixel tile x a chunk of samples) from a single atomic counter that all GPUs share.  Per unit it culls
+// the BVH against the tile's primary-ray bundle, then alternates dense primary batches (32 camera paths tested against
+// the tile's candidate list) with secondary steps (one BVH-traversed segment per live lane, rays queued in a
+// shared-memory ring), accumulates radiance per tile in shared memory and adds the finished tile straight into the
+// framebuffer on the first GPU (peer atomics over NVLink — the "gather" of src/main.rs:542-547 is fused into the
+// kernel).  Replaces src/main.rs:497-589.  DESIGN.md 4.1 has the measurements behind each choice.
 #include <cuda_runtime.h>
 
 #include <chrono>
