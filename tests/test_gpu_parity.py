@@ -565,6 +565,17 @@ def test_progressive_and_resume_equal_one_shot(pkg, gpu, name):
         sc.render_progressive(cam, p, first_sample=spp + 1, buf=part.copy())
 
 
+def test_cuda_path_reproduces_the_reference_earth_image(pkg, gpu):
+    """The CUDA path against pixels the REFERENCE wrote (generated_images/earth.ppm via tests/golden/, see
+    test_oracle_kat.py): globe texture orientation, framing, shading level and gamma, through rtw_render."""
+    from test_oracle_kat import earth_reference_check
+    sc, spec = pkg.scenes.build(gpu, "earth")
+    sc.commit(1, 0)
+    cam = spec.camera(gpu, 400, 225)
+    img, _ = sc.render(cam, pkg.make_params(400, 225, 256, background=spec.background, seed=3))
+    earth_reference_check(pkg, cam, img.astype(np.float64), 256)
+
+
 def test_render_edge_cases(pkg, gpu, orc):
     # empty world: every sample returns the background (src/main.rs:37)
     sc = pkg.Scene(gpu)

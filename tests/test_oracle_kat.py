@@ -5,11 +5,14 @@ src/math.rs:292-294.  Everything else here is the reference FORMULA re-evaluated
 (different code shape than the C++ restatement) or a published known answer (Random123 Philox KATs).
 """
 import math
+import os
 
 import numpy as np
 import pytest
 
 from conftest import q24
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_sphere_uv_reference_table(orc):
@@ -371,3 +374,45 @@ def test_estimator_properties(pkg, orc):
         cam = orc.camera_new((0, 0, z), (0, 0, 0), (0, 1, 0), 40.0, 1.0, 0.0, 5.0)
         rgb, seg = sc.trace_paths(cam, p, [3], [4], [0])
         assert np.allclose(rgb[0], [4, 5, 6]) and seg[0] == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# The one reference OUTPUT that matches a HEAD scene: generated_images/earth.ppm (400x225, older commit: same globe,
+# same camera, gradient sky).  tests/golden/ref_earth_400x225_blocks5.npy = its 5x5 block means (tools/make_golden_earth.py).
+# ------------------------------------------------------------------------------------------------
+def earth_reference_check(pkg, cam, sums, spp):
+    """8-bit image like write_color (src/math.rs:119-132) -> 5x5 block means -> compare on the globe (analytic mask,
+    radius shrunk by 10 % to stay off the limb, where the old gradient sky shows through pixel coverage)."""
+    ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_earth_400x225_blocks5.npy"))
+    W, H = 400, 225
+    c8 = np.floor(np.clip(np.sqrt(np.clip(sums / spp, 0, None)), 0, 0.999) * 256)
+    blk = c8.reshape(45, 5, 80, 5, 3).mean((1, 3))
+    o, ll = np.array(list(cam.origin)), np.array(list(cam.lower_left_corner))
+    hz, vt = np.array(list(cam.horizontal)), np.array(list(cam.vertical))
+    ys, xs = np.mgrid[0:45, 0:80]
+    u, v = (xs * 5 + 2.5) / (W - 1), ((H - 1) - (ys * 5 + 2.5)) / (H - 1)
+    d = ll + u[..., None] * hz + v[..., None] * vt - o
+    a, hb, c = (d * d).sum(-1), (d * o).sum(-1), (o * o).sum() - (2.0 * 0.9) ** 2
+    mask = hb * hb - a * c > 0
+    assert 800 <= mask.sum() <= 1000                       # the globe covers ~ a quarter of the frame
+
+    def corr(p, q):
+        p, q = p - p.mean(), q - q.mean()
+        return float((p * q).sum() / np.sqrt((p * p).sum() * (q * q).sum()))
+    for ch in range(3):
+        assert corr(blk[mask][:, ch], ref[mask][:, ch]) >= 0.995, ch
+        # a wrong u or v orientation (src/math.rs:296-299, src/texture.rs:48-54) decorrelates completely
+        assert abs(corr(blk[:, ::-1][mask][:, ch], ref[mask][:, ch])) < 0.5
+        assert abs(corr(blk[::-1][mask][:, ch], ref[mask][:, ch])) < 0.5
+    # absolute level too: same texels, same albedo * sky transport, same gamma (measured 1.3 / 255)
+    assert np.abs(blk[mask] - ref[mask]).mean() <= 3.0
+
+
+def test_oracle_reproduces_the_reference_earth_image(pkg, orc):
+    """Pins sphere hit + normal, sphere_uv, image-texture addressing (and our JPEG decode against stb_image's), the
+    camera framing, Lambertian transport under the sky and write_color's gamma against pixels the reference itself wrote."""
+    sc, spec = pkg.scenes.build(orc, "earth")
+    cam = spec.camera(orc, 400, 225)
+    spp = 32
+    r = sc.render_oracle(cam, pkg.make_params(400, 225, spp, background=spec.background, seed=3), threads=0)
+    earth_reference_check(pkg, cam, r["sum"], spp)
