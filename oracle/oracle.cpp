@@ -8,10 +8,13 @@
 // path (librtw.so has no CPU fallback and never links this file).
 //
 // PARITY PINNING: the reference has no tests and cannot be compiled here (no rustc/cargo, `rand`
-// and `stb_image` not vendored).  The restatement is pinned to the only known answers the
-// reference holds — the sphere_uv table in src/math.rs:292-294 — plus closed-form values of the
-// reference formulas (tests/test_oracle_kat.py).  RNG (rand 0.8 thread_rng, OS-seeded) and JPEG
-// decode (stb_image) are third-party and unpinned: "parity unpinned" for those two, see DESIGN.md.
+// and `stb_image` not vendored).  The restatement is pinned to the known answers the reference
+// holds — the sphere_uv table in src/math.rs:292-294 and the one output image that matches a HEAD
+// scene, generated_images/earth.ppm (block means in tests/golden/ref_earth_400x225_blocks5.npy:
+// correlation 0.999, |delta| 1.3/255 on the globe) — plus closed-form values of the reference
+// formulas (tests/test_oracle_kat.py).  RNG (rand 0.8 thread_rng, OS-seeded) is third-party and
+// unpinned ("parity unpinned": only the distributions carry over); JPEG decode (stb_image) is
+// pinned only through that image.  See DESIGN.md section 2.
 //
 // Deliberate departures (none changes a distribution):
 //  * random_double() is replaced by an injectable stream: either an explicit array of U[0,1)
