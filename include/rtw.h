@@ -59,8 +59,8 @@ typedef struct rtw_camera {
 /* Everything the reference hard-codes in main() (src/main.rs:309-312, :25, :316-459). */
 typedef struct rtw_render_params {
     int32_t width, height;      /* explicit; aspect = width/height (not src/main.rs:467) */
-    int32_t spp;                /* samples per pixel (all of them; no spp/thread_count truncation) */
-    int32_t max_depth;          /* 50 in the reference (src/main.rs:310) */
+    int32_t spp;                /* samples per pixel (all of them; no spp/thread_count truncation); <= 1048576 */
+    int32_t max_depth;          /* 50 in the reference (src/main.rs:310); <= 63 */
     double background[3];       /* constant miss colour (src/main.rs:37) */
     double t_min;               /* 0.001 (src/main.rs:25), ray-parameter units */
     uint64_t seed;              /* Philox key; counter = (draw block, bounce, pixel, sample) */

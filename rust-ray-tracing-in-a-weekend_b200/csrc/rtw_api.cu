@@ -132,7 +132,7 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
                         ps.last_prim = __float_as_int(rg[640]);
                         const int meta = __float_as_int(rg[704]);
                         pix = meta & 31;
-                        ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)(meta >> 11));
+                        ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)meta >> 11);
                         ps.segment = (meta >> 5) & 63;
                         alive = true;
                     }
@@ -519,6 +519,8 @@ DCamera to_dcamera(const rtw_camera& c) {
 
 int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     if (p.width < 2 || p.height < 2 || p.spp < 1 || p.max_depth < 0) return fail(RTW_ERR_INVALID_ARG, "bad render params");
+    // a queued ray packs pixel(5) | segment(6) | sample(21) into one word (the pool kernel: sample(17), checked at launch)
+    if (p.spp > (1 << 20) || p.max_depth > 63) return fail(RTW_ERR_INVALID_ARG, "spp <= 1048576 and max_depth <= 63");
     std::memset(&d, 0, sizeof(d));
     d.width = p.width; d.height = p.height; d.spp = p.spp; d.max_depth = p.max_depth;
     d.bg_r = (float)p.background[0]; d.bg_g = (float)p.background[1]; d.bg_b = (float)p.background[2];
@@ -621,6 +623,7 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         CUDA_TRY(cudaMemcpyToSymbolAsync(c_philox_rk, rk, sizeof(rk), 0, cudaMemcpyHostToDevice, r.stream));
         CUDA_TRY(cudaMemsetAsync(r.stats, 0, 32, r.stream));
         CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
+        if (mode >= 1 && dp.first_sample + dp.spp > (1 << 17)) return fail(RTW_ERR_INVALID_ARG, "the pool kernel packs the sample index into 17 bits: spp <= 131072");
         switch (mode) {
         case 1: TRY(launch_pool<64>(r, 0, dc, dp, counter, fb)); break;
         case 2: TRY(launch_pool<128>(r, 1, dc, dp, counter, fb)); break;

@@ -599,6 +599,15 @@ def test_render_edge_cases(pkg, gpu, orc):
     assert img.shape == (2, 2, 3) and st["paths"] == 4
     with pytest.raises(pkg.RtwError):
         a.render(camg, pkg.make_params(1, 1, 1))
+    # a queued ray packs segment (6 bits) and sample index (21 bits; pool kernel 17): out-of-range requests are refused
+    for bad in (dict(max_depth=64), dict(spp=(1 << 20) + 1)):
+        kw = dict(spp=1, max_depth=50); kw.update(bad)
+        with pytest.raises(pkg.RtwError):
+            a.render(camg, pkg.make_params(33, 17, kw["spp"], max_depth=kw["max_depth"]))
+    with pytest.raises(pkg.RtwError):
+        a.render(camg, pkg.make_params(33, 17, (1 << 17) + 1, flags=pkg.api.RTW_FLAG_KERNEL_POOL))
+    img, _ = a.render(camg, pkg.make_params(33, 17, 2, max_depth=63))
+    assert np.isfinite(img).all()
     # editing the scene after commit must be re-committed
     a.push(a.sphere(1, (0, 0, 0), 1.0))
     with pytest.raises(pkg.RtwError) as e:
