@@ -324,7 +324,7 @@ RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float time
 // then the numerically stable root pair in f32 (q = -(half_b + sign(half_b) sqrt(disc)); roots q/a and c/q).
 // Branch-free: a warp processes 32 different leaves, an early-out would only add divergence.
 // Returns the accepted root or NaN.
-RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi, bool self) {
+RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi, bool self, float* far_root = nullptr) {
     double cx, cy, cz, rad;
     load_prim_center(pp, type, r.time, cx, cy, cz, rad);
     double ocx = r.gox() - cx, ocy = r.goy() - cy, ocz = r.goz() - cz;
@@ -344,6 +344,7 @@ RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r,
     // coordinate quantum and the root can exceed t_min for grazing directions.  Exact geometry: the root at the
     // origin is c/q (c ~ 0); only the other one, q/a, can be a real hit.
     if (self) root = tq;
+    if (far_root) *far_root = discf >= 0.0f ? t_far : CUDART_NAN_F;       // the other crossing (ConstantMedium boundary)
     bool ok = discf >= 0.0f && root >= t_lo && root <= t_hi;
     return ok ? root : CUDART_NAN_F;
 }
@@ -377,10 +378,10 @@ RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, floa
 // Any primitive: accepted root in [t_lo, t_hi] or NaN.  `skip` = primitive the ray starts on (-1: none): a planar
 // rect cannot be re-hit by a ray leaving it (exact geometry; the reference's f64 gets t ~ 1e-13 < t_min).
 template <int F = FEAT_ALL>
-RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip) {
+RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip, float* far_root = nullptr) {
     const DPrim* pp = sc.prims + pi;
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
-    if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip);
+    if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip, far_root);
     if (pi == skip) return CUDART_NAN_F;
     V3 o, d;
     xform_ray(sc, meta.z, r, o, d);           // xform 0 is the identity: no branch, one instruction stream
@@ -554,17 +555,21 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     const float inf = CUDART_INF_F;
     // boundary.hit(ray, -inf, inf) :422, then boundary.hit(ray, rec1.t + 0.0001, inf) :423 — two closest-so-far scans
     // over the boundary prims (hit_hittables :43-55) sharing ONE inlined copy of the primitive test
-    float t1 = 0.f, t2 = 0.f, lo = -inf;
+    // A boundary made of ONE sphere (final_scene's two media): its second crossing comes out of the same discriminant
+    // — the first probe returns the near root, the second probe can only return the far one — so one test serves both.
+    const bool one_sphere = md.y == 1 && __ldg(reinterpret_cast<const int*>(sc.prims + md.x) + 16) <= PRIM_MOVING_SPHERE;
+    float t1 = 0.f, t2 = 0.f, lo = -inf, far_root = CUDART_NAN_F;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         float hi = inf, found = CUDART_NAN_F;
-        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1); if (t == t) { hi = t; found = t; } }
+        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1, &far_root); if (t == t) { hi = t; found = t; } }
         if (!(found == found)) return false;
         if (pass == 0) {
             t1 = found;
             // in f32 the +0.0001 vanishes once |t1| > 2048 (r = 5000 fog sphere): keep the probe strictly beyond t1
             lo = t1 + 0.0001f;
             if (!(lo > t1)) lo = nextafterf(t1, inf);
+            if (one_sphere) { if (!(far_root >= lo)) return false; t2 = far_root; break; }
         } else t2 = found;
     }
     if (t1 < t_min) t1 = t_min;
