@@ -153,6 +153,7 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
             if (work) {
                 tr = make_tray(ps.ray);
                 if (primary && list_n >= 0) {
+#pragma unroll 1
                     for (int i = 0; i < list_n; ++i) {
                         const int pi = tlist[warp][i];
                         const float t = prim_root<F>(sc, pi, tr, prm.t_min, t_best, -1);
@@ -636,10 +637,11 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
             RTW_TRY_VARIANT(0)                                         // spheres, solid / checker         (C1, two_spheres)
             RTW_TRY_VARIANT(FEAT_NOISE)                                // + Perlin                         (two_perlin_spheres)
             RTW_TRY_VARIANT(FEAT_IMAGE)                                // + image                          (earth)
-            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM)                    // rects, boxes, instances          (cornell_box)
-            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM | FEAT_NOISE)       //                                  (simple_light)
-            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM | FEAT_MEDIA)       // + media                          (cornell_box_smoke)
-            RTW_TRY_VARIANT(FEAT_ALL)                                  //                                  (final_scene)
+            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM | FEAT_RXFORM)                // rects, boxes, instances (cornell_box)
+            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM | FEAT_RXFORM | FEAT_NOISE)   //                         (simple_light)
+            RTW_TRY_VARIANT(FEAT_RECT | FEAT_XFORM | FEAT_RXFORM | FEAT_MEDIA)   // + media                 (cornell_box_smoke)
+            RTW_TRY_VARIANT(FEAT_ALL & ~FEAT_RXFORM)                             // all, rects not instanced (final_scene)
+            RTW_TRY_VARIANT(FEAT_ALL)
 #undef RTW_TRY_VARIANT
         }
         }

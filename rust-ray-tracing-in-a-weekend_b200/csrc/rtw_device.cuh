@@ -19,7 +19,9 @@ namespace rtwd {
 // Scene features a kernel instantiation must support.  The render kernel is compiled twice: FEAT_ALL and a lean
 // variant for scenes made of (moving) spheres with solid / checker textures only (book-1: config 1) — the full
 // kernel is 90 KB of SASS and the instruction cache is the first thing it runs out of (ncu: stall_no_instruction).
-enum { FEAT_RECT = 1, FEAT_XFORM = 2, FEAT_MEDIA = 4, FEAT_NOISE = 8, FEAT_IMAGE = 16, FEAT_ALL = 31 };
+// FEAT_XFORM: some primitive sits under Translate / RotateY (hit records replay the wrapper chain); FEAT_RXFORM: some RECT
+// does, so rect tests must move the ray into object space (final_scene: only its baked spheres are instanced).
+enum { FEAT_RECT = 1, FEAT_XFORM = 2, FEAT_MEDIA = 4, FEAT_NOISE = 8, FEAT_IMAGE = 16, FEAT_RXFORM = 32, FEAT_ALL = 63 };
 #define RTW_PI_F 3.14159265358979323846f
 
 // ------------------------------------------------------------------------------------------------
@@ -383,8 +385,8 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
     if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip, far_root);
     if (pi == skip) return CUDART_NAN_F;
-    V3 o, d;
-    xform_ray(sc, meta.z, r, o, d);           // xform 0 is the identity: no branch, one instruction stream
+    V3 o = r.o, d = r.d;
+    if (F & FEAT_RXFORM) xform_ray(sc, meta.z, r, o, d);      // xform 0 is the identity: no branch, one instruction stream
     return rect_root(pp, meta.x, o, d, t_lo, t_hi);
 }
 
@@ -470,6 +472,7 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
         }
         while (leaf < 0) {
             int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
+#pragma unroll 1                                    // one copy of the primitive tests (the compiler unrolls by 2 when the body is small)
             for (int i = 0; i < count; ++i) {
                 RTW_DBG_PRIM();
                 float t = prim_root<F>(sc, first + i, r, t_min, t_best, skip);
@@ -562,6 +565,7 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         float hi = inf, found = CUDART_NAN_F;
+#pragma unroll 1
         for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1, &far_root); if (t == t) { hi = t; found = t; } }
         if (!(found == found)) return false;
         if (pass == 0) {

@@ -456,9 +456,9 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
     lap("emit nodes");
     out.max_depth = b.max_depth;
     out.n_bvh_prims = n;
-    // feature bits (must match the FEAT_* enum of rtw_device.cuh): RECT 1, XFORM 2, MEDIA 4, NOISE 8, IMAGE 16
-    for (const DPrim& p : fl.bvh_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= 2; }
-    for (const DPrim& p : fl.boundary_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= 2; }
+    // feature bits (must match the FEAT_* enum of rtw_device.cuh): RECT 1, XFORM 2, MEDIA 4, NOISE 8, IMAGE 16, RXFORM 32 (an instanced RECT)
+    for (const DPrim& p : fl.bvh_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= p.type >= PRIM_XY ? 2 | 32 : 2; }
+    for (const DPrim& p : fl.boundary_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= p.type >= PRIM_XY ? 2 | 32 : 2; }
     if (!out.media.empty()) out.features |= 4;
     for (const DTex& t : out.texs) { if (t.kind == TEX_NOISE) out.features |= 8; if (t.kind == TEX_IMAGE) out.features |= 16; }
     // boundary prims follow; shift media ranges
