@@ -16,9 +16,10 @@ namespace rtwd {
 
 #define RTW_DEV __device__ __forceinline__
 
-// Scene features a kernel instantiation must support.  The render kernel is compiled twice: FEAT_ALL and a lean
-// variant for scenes made of (moving) spheres with solid / checker textures only (book-1: config 1) — the full
-// kernel is 90 KB of SASS and the instruction cache is the first thing it runs out of (ncu: stall_no_instruction).
+// Scene features a kernel instantiation must support.  The render kernel is compiled in 8 variants (launch_all picks
+// the smallest superset of what the scene uses): the all-features kernel is 64 KB of SASS, the one for (moving) spheres
+// with solid / checker textures (book-1: config 1) 34 KB, and the instruction cache (L1.5 = 32 KB per SM) is the first
+// thing a megakernel runs out of (ncu: stall_no_instruction).
 // FEAT_XFORM: some primitive sits under Translate / RotateY (hit records replay the wrapper chain); FEAT_RXFORM: some RECT
 // does, so rect tests must move the ray into object space (final_scene: only its baked spheres are instanced).
 enum { FEAT_RECT = 1, FEAT_XFORM = 2, FEAT_MEDIA = 4, FEAT_NOISE = 8, FEAT_IMAGE = 16, FEAT_RXFORM = 32, FEAT_ALL = 63 };
