@@ -380,14 +380,21 @@ RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, floa
 
 // Any primitive: accepted root in [t_lo, t_hi] or NaN.  `skip` = primitive the ray starts on (-1: none): a planar
 // rect cannot be re-hit by a ray leaving it (exact geometry; the reference's f64 gets t ~ 1e-13 < t_min).
+// object-space ray of the last instance transform used: the faces of a Box share one (ConstantMedium boundary scans)
+struct XfCache { int xf; V3 o, d; };
 template <int F = FEAT_ALL>
-RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip, float* far_root = nullptr) {
+RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip, float* far_root = nullptr, XfCache* xc = nullptr) {
     const DPrim* pp = sc.prims + pi;
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
     if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip, far_root);
     if (pi == skip) return CUDART_NAN_F;
     V3 o = r.o, d = r.d;
-    if (F & FEAT_RXFORM) xform_ray(sc, meta.z, r, o, d);      // xform 0 is the identity: no branch, one instruction stream
+    if (F & FEAT_RXFORM) {
+        if (xc) {                                              // all lanes scan the same boundary: the branch is uniform
+            if (xc->xf != meta.z) { xform_ray(sc, meta.z, r, xc->o, xc->d); xc->xf = meta.z; }
+            o = xc->o; d = xc->d;
+        } else xform_ray(sc, meta.z, r, o, d);                 // xform 0 is the identity: no branch, one instruction stream
+    }
     return rect_root(pp, meta.x, o, d, t_lo, t_hi);
 }
 
@@ -563,11 +570,12 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     // — the first probe returns the near root, the second probe can only return the far one — so one test serves both.
     const bool one_sphere = md.y == 1 && __ldg(reinterpret_cast<const int*>(sc.prims + md.x) + 16) <= PRIM_MOVING_SPHERE;
     float t1 = 0.f, t2 = 0.f, lo = -inf, far_root = CUDART_NAN_F;
+    XfCache xc; xc.xf = -1; xc.o = r.o; xc.d = r.d;        // 6 faces x 2 probes of a rotated Box: one transform instead of 12
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         float hi = inf, found = CUDART_NAN_F;
 #pragma unroll 1
-        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1, &far_root); if (t == t) { hi = t; found = t; } }
+        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1, &far_root, &xc); if (t == t) { hi = t; found = t; } }
         if (!(found == found)) return false;
         if (pass == 0) {
             t1 = found;
