@@ -571,11 +571,23 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     const bool one_sphere = md.y == 1 && __ldg(reinterpret_cast<const int*>(sc.prims + md.x) + 16) <= PRIM_MOVING_SPHERE;
     float t1 = 0.f, t2 = 0.f, lo = -inf, far_root = CUDART_NAN_F;
     XfCache xc; xc.xf = -1; xc.o = r.o; xc.d = r.d;        // 6 faces x 2 probes of a rotated Box: one transform instead of 12
+    // Small boundaries (a Box: 6 faces) are intersected ONCE: the first scan keeps every face's root, the second scan
+    // (same faces, range [t1 + 0.0001, inf)) re-reads them — the same values hit_hittables would compute again.
+    float ts[8];
+    const bool keep = md.y <= 8;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         float hi = inf, found = CUDART_NAN_F;
 #pragma unroll 1
-        for (int i = 0; i < md.y; ++i) { float t = prim_root(sc, md.x + i, r, lo, hi, -1, &far_root, &xc); if (t == t) { hi = t; found = t; } }
+        for (int i = 0; i < md.y; ++i) {
+            float t;
+            if (keep && pass == 1) t = ts[i];
+            else {
+                t = prim_root(sc, md.x + i, r, keep ? -inf : lo, keep ? inf : hi, -1, &far_root, &xc);
+                if (keep) ts[i] = t;
+            }
+            if (t >= lo && t <= hi) { hi = t; found = t; }          // closest-so-far (hit_hittables :43-55); NaN fails
+        }
         if (!(found == found)) return false;
         if (pass == 0) {
             t1 = found;
