@@ -1,3 +1,6 @@
+"""Path-level parity diagnosis for one scene: 200 k individual (pixel, sample) paths traced by the CUDA path
+(rtw_trace_paths) and by the oracle with the same Philox keys; prints the share of identical paths and the segment-count
+histogram of the ones that diverge.  Usage: diag_paths2.py [scene]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, rtw_pkg
