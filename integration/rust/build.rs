@@ -10,7 +10,7 @@ fn main() {
         .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
                "-Xcompiler", "-fPIC", "-shared", "-o"])
         .arg(&lib)
-        .arg(csrc.join("rtw_api.cu")).arg(csrc.join("scene_host.cpp"))
+        .arg(csrc.join("rtw_api.cu")).arg(csrc.join("scene_host.cpp")).arg(csrc.join("image_out.cpp"))
         .arg("-lcudart")
         .status().expect("nvcc not found");
     assert!(st.success(), "nvcc failed");
