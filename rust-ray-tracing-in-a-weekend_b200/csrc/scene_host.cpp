@@ -203,6 +203,23 @@ struct Flattener {
 inline float down(double v) { float f = (float)v; if ((double)f > v) f = std::nextafterf(f, -INFINITY); return std::nextafterf(f, -INFINITY); }
 inline float up(double v) { float f = (float)v; if ((double)f < v) f = std::nextafterf(f, INFINITY); return std::nextafterf(f, INFINITY); }
 
+// ---- fork-join over index ranges (the 1 M - 16 M sphere sweep: every O(n) pass of flatten runs on all cores) -------
+static int worker_count() {             // RTW_BUILD_THREADS=1 forces the serial builder (tests compare the two)
+    if (const char* e = getenv("RTW_BUILD_THREADS")) return std::max(1, std::min(64, atoi(e)));
+    unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min<unsigned>(hw ? hw : 1, 32);
+}
+// fn(chunk, begin, end) on up to worker_count() threads; returns the number of chunks used (1 = ran inline)
+template <class Fn> static int parallel_chunks(size_t n, size_t min_per_chunk, Fn fn) {
+    const int t = (int)std::min<size_t>((size_t)worker_count(), std::max<size_t>(1, n / std::max<size_t>(1, min_per_chunk)));
+    if (t <= 1) { fn(0, (size_t)0, n); return 1; }
+    std::vector<std::thread> th;
+    for (int i = 1; i < t; ++i) th.emplace_back([&fn, i, t, n]() { fn(i, n * (size_t)i / t, n * (size_t)(i + 1) / t); });
+    fn(0, (size_t)0, n / t);
+    for (auto& x : th) x.join();
+    return t;
+}
+
 struct FBox {
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     void grow(const FBox& b) { for (int i = 0; i < 3; ++i) { mn[i] = std::min(mn[i], b.mn[i]); mx[i] = std::max(mx[i], b.mx[i]); } }
@@ -218,44 +235,64 @@ struct BuildNode { FBox box; int left = -1, right = -1; int first = 0, count = 0
 struct BuildTask { int node, first, count, depth; };
 
 struct Builder {
-    std::vector<Item> items;
+    std::vector<Item> items, tmp;          // tmp: scratch of the out-of-place parallel partition (top levels only)
     std::vector<BuildNode> nodes;
     int max_depth = 0;
     static constexpr int NBINS = 16;
+    static constexpr int PAR_MIN = 1 << 18;               // nodes with at least this many items are processed by all threads
     static int MAX_LEAF;
     static double C_TRAV, C_ISECT;
 
     explicit Builder(const std::vector<Box3>& b) {
         items.resize(b.size());
-        for (size_t i = 0; i < b.size(); ++i) {
-            for (int a = 0; a < 3; ++a) { items[i].b.mn[a] = down(b[i].mn[a]); items[i].b.mx[a] = up(b[i].mx[a]); }
-            items[i].id = (int)i;
-        }
+        parallel_chunks(b.size(), 1 << 16, [&](int, size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i) {
+                for (int a = 0; a < 3; ++a) { items[i].b.mn[a] = down(b[i].mn[a]); items[i].b.mx[a] = up(b[i].mx[a]); }
+                items[i].id = (int)i;
+            }
+        });
     }
     static void centroid(const Item& it, float c[3]) { for (int a = 0; a < 3; ++a) c[a] = 0.5f * (it.b.mn[a] + it.b.mx[a]); }
+    struct Bounds { FBox box, cbox; void add(const Item& it) { float c[3]; centroid(it, c); box.grow(it.b); cbox.grow_pt(c); }
+                    void merge(const Bounds& o) { box.grow(o.box); cbox.grow(o.cbox); } };
+    struct Bins { FBox bb[3][NBINS]; int bc[3][NBINS] = {}; };
 
-    // Top-down binned SAH.  With `tasks` set, subtrees of at most `cutoff` prims are not built but recorded, so that
-    // they can be built by worker threads afterwards (disjoint item ranges, private node vectors).
-    int build(std::vector<BuildNode>& out, int first, int count, int depth, int& depth_max, std::vector<BuildTask>* tasks, int cutoff) {
+    Bounds range_bounds(int first, int count, bool par) {
+        Bounds r;
+        if (!par) { for (int i = first; i < first + count; ++i) r.add(items[i]); return r; }
+        std::vector<Bounds> part(worker_count());
+        const int used = parallel_chunks((size_t)count, 1 << 16, [&](int c, size_t i0, size_t i1) { Bounds loc; for (size_t i = i0; i < i1; ++i) loc.add(items[first + i]); part[c] = loc; });   // locals: no false sharing
+        for (int c = 0; c < used; ++c) r.merge(part[c]);
+        return r;
+    }
+
+    // Top-down binned SAH.  `bd` = bounds of the range (handed down by the parent, which measured both halves while it
+    // partitioned them: one pass over the items per level instead of two).  With `tasks` set, subtrees of at most
+    // `cutoff` prims are not built but recorded, so that worker threads can build them afterwards (disjoint item
+    // ranges, private node vectors); the levels above them stream their items with all threads (bins per thread,
+    // out-of-place partition by prefix sums).
+    int build(std::vector<BuildNode>& out, int first, int count, int depth, int& depth_max, std::vector<BuildTask>* tasks, int cutoff, const Bounds& bd) {
         depth_max = std::max(depth_max, depth);
         int me = (int)out.size();
         out.emplace_back();
-        out[me].first = first; out[me].count = count;
+        out[me].first = first; out[me].count = count; out[me].box = bd.box;
         if (tasks && depth > 0 && count <= cutoff && count > MAX_LEAF) { tasks->push_back(BuildTask{me, first, count, depth}); return me; }
-        FBox box, cbox;
-        for (int i = first; i < first + count; ++i) { float c[3]; centroid(items[i], c); box.grow(items[i].b); cbox.grow_pt(c); }
-        out[me].box = box;
         if (count <= 1) return me;
-        // one pass fills the bins of all three axes
-        FBox bb[3][NBINS]; int bc[3][NBINS] = {};
+        const bool par = tasks != nullptr && count >= PAR_MIN;
+        const FBox& box = bd.box; const FBox& cbox = bd.cbox;
         float lo[3], scale[3];
         for (int a = 0; a < 3; ++a) { lo[a] = cbox.mn[a]; float ext = cbox.mx[a] - cbox.mn[a]; scale[a] = ext > 0 ? NBINS / ext : 0.f; }
-        for (int i = first; i < first + count; ++i) {
-            float c[3]; centroid(items[i], c);
-            for (int a = 0; a < 3; ++a) {
-                int k = std::min(NBINS - 1, std::max(0, (int)((c[a] - lo[a]) * scale[a])));
-                bb[a][k].grow(items[i].b); bc[a][k]++;
-            }
+        auto bin_of = [&](const Item& it, int a) { float c = 0.5f * (it.b.mn[a] + it.b.mx[a]); return std::min(NBINS - 1, std::max(0, (int)((c - lo[a]) * scale[a]))); };
+        // one pass fills the bins of all three axes
+        Bins bins;
+        auto fill = [&](Bins& B, size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i) { const Item& it = items[first + i]; for (int a = 0; a < 3; ++a) { int k = bin_of(it, a); B.bb[a][k].grow(it.b); B.bc[a][k]++; } }
+        };
+        if (!par) fill(bins, 0, (size_t)count);
+        else {
+            std::vector<Bins> part(worker_count());
+            const int used = parallel_chunks((size_t)count, 1 << 16, [&](int c, size_t i0, size_t i1) { Bins loc; fill(loc, i0, i1); part[c] = loc; });
+            for (int c = 0; c < used; ++c) for (int a = 0; a < 3; ++a) for (int k = 0; k < NBINS; ++k) if (part[c].bc[a][k]) { bins.bb[a][k].grow(part[c].bb[a][k]); bins.bc[a][k] += part[c].bc[a][k]; }
         }
         double best_cost = 1e300; int best_axis = -1, best_bin = -1;
         double parent_area = std::max(box.area(), 1e-300);
@@ -263,9 +300,9 @@ struct Builder {
             if (!(scale[a] > 0)) continue;
             double la[NBINS], ra[NBINS]; int lc[NBINS], rc[NBINS];
             FBox acc; int n = 0;
-            for (int k = 0; k < NBINS; ++k) { if (bc[a][k]) acc.grow(bb[a][k]); n += bc[a][k]; la[k] = acc.area(); lc[k] = n; }
+            for (int k = 0; k < NBINS; ++k) { if (bins.bc[a][k]) acc.grow(bins.bb[a][k]); n += bins.bc[a][k]; la[k] = acc.area(); lc[k] = n; }
             acc = FBox(); n = 0;
-            for (int k = NBINS - 1; k >= 0; --k) { if (bc[a][k]) acc.grow(bb[a][k]); n += bc[a][k]; ra[k] = acc.area(); rc[k] = n; }
+            for (int k = NBINS - 1; k >= 0; --k) { if (bins.bc[a][k]) acc.grow(bins.bb[a][k]); n += bins.bc[a][k]; ra[k] = acc.area(); rc[k] = n; }
             for (int k = 0; k < NBINS - 1; ++k) {
                 if (lc[k] == 0 || rc[k + 1] == 0) continue;
                 double cost = C_TRAV + C_ISECT * (la[k] * lc[k] + ra[k + 1] * rc[k + 1]) / parent_area;
@@ -274,32 +311,67 @@ struct Builder {
         }
         double leaf_cost = C_ISECT * count;
         if (count <= MAX_LEAF && (best_axis < 0 || leaf_cost <= best_cost)) return me;
-        int mid;
-        if (best_axis < 0) {
-            mid = first + count / 2;       // coincident centroids: split by index
-        } else {
-            const int ax = best_axis; const float l0 = lo[ax], sc = scale[ax];
-            auto it = std::partition(items.begin() + first, items.begin() + first + count, [&](const Item& p) {
-                float c = 0.5f * (p.b.mn[ax] + p.b.mx[ax]);
-                int k = std::min(NBINS - 1, std::max(0, (int)((c - l0) * sc)));
-                return k <= best_bin;
-            });
-            mid = (int)(it - items.begin());
-            if (mid == first || mid == first + count) mid = first + count / 2;
+        int mid = first + count / 2;
+        Bounds bl, br;
+        bool measured = false;
+        if (best_axis >= 0) {
+            const int ax = best_axis;
+            if (!par) {
+                // Hoare partition that measures both halves on the way (each item classified exactly once)
+                int i = first, j = first + count - 1;
+                for (;;) {
+                    while (i <= j && bin_of(items[i], ax) <= best_bin) { bl.add(items[i]); ++i; }
+                    while (i <= j && bin_of(items[j], ax) > best_bin) { br.add(items[j]); --j; }
+                    if (i >= j) break;
+                    std::swap(items[i], items[j]);
+                    bl.add(items[i]); br.add(items[j]);
+                    ++i; --j;
+                }
+                mid = i; measured = true;
+            } else {
+                // out of place: per-chunk counts -> prefix sums -> scatter -> copy back (stable, all threads)
+                const int T = worker_count();
+                std::vector<int> nl(T, 0), nr(T, 0);
+                std::vector<Bounds> pl(T), pr(T);
+                const int used = parallel_chunks((size_t)count, 1 << 16, [&](int c, size_t i0, size_t i1) {
+                    int a = 0, b = 0; Bounds la, lb;
+                    for (size_t i = i0; i < i1; ++i) { const Item& it = items[first + i]; if (bin_of(it, ax) <= best_bin) { ++a; la.add(it); } else { ++b; lb.add(it); } }
+                    nl[c] = a; nr[c] = b; pl[c] = la; pr[c] = lb;
+                });
+                int n_left = 0; for (int c = 0; c < used; ++c) n_left += nl[c];
+                std::vector<int> ol(used, 0), orr(used, 0);
+                for (int c = 1; c < used; ++c) { ol[c] = ol[c - 1] + nl[c - 1]; orr[c] = orr[c - 1] + nr[c - 1]; }
+                if (tmp.size() < items.size()) tmp.resize(items.size());
+                parallel_chunks((size_t)count, 1 << 16, [&](int c, size_t i0, size_t i1) {   // same chunking as above (same n, same threshold)
+                    int wl = first + ol[c], wr = first + n_left + orr[c];
+                    for (size_t i = i0; i < i1; ++i) { const Item& it = items[first + i]; if (bin_of(it, ax) <= best_bin) tmp[wl++] = it; else tmp[wr++] = it; }
+                });
+                parallel_chunks((size_t)count, 1 << 16, [&](int, size_t i0, size_t i1) { std::memcpy(&items[first + i0], &tmp[first + i0], (i1 - i0) * sizeof(Item)); });
+                for (int c = 0; c < used; ++c) { bl.merge(pl[c]); br.merge(pr[c]); }
+                mid = first + n_left; measured = true;
+            }
+            if (mid == first || mid == first + count) { mid = first + count / 2; measured = false; }
         }
-        int l = build(out, first, mid - first, depth + 1, depth_max, tasks, cutoff);
-        int r = build(out, mid, first + count - mid, depth + 1, depth_max, tasks, cutoff);
+        if (!measured) {                   // coincident centroids / degenerate split: halves by index, measured separately
+            bl = range_bounds(first, mid - first, par); br = range_bounds(mid, first + count - mid, par);
+        }
+        int l = build(out, first, mid - first, depth + 1, depth_max, tasks, cutoff, bl);
+        int r = build(out, mid, first + count - mid, depth + 1, depth_max, tasks, cutoff, br);
         out[me].left = l; out[me].right = r;
         return me;
     }
 
     void build_all(int n) {
         nodes.reserve(2 * (size_t)n);
-        unsigned hw = std::thread::hardware_concurrency();
-        int n_threads = (int)std::min<unsigned>(hw ? hw : 1, 32);
-        if (n < (1 << 16) || n_threads < 2) { build(nodes, 0, n, 0, max_depth, nullptr, 0); return; }
+        const int n_threads = worker_count();
+        const Bounds root = range_bounds(0, n, n >= PAR_MIN && n_threads > 1);
+        if (n < (1 << 16) || n_threads < 2) { build(nodes, 0, n, 0, max_depth, nullptr, 0, root); return; }
         std::vector<BuildTask> tasks;
-        build(nodes, 0, n, 0, max_depth, &tasks, std::max(1024, n / (8 * n_threads)));
+        const bool timing = getenv("RTW_TIMING") != nullptr;
+        auto tp0 = std::chrono::steady_clock::now();
+        build(nodes, 0, n, 0, max_depth, &tasks, std::max(1024, n / (8 * n_threads)), root);
+        if (timing) fprintf(stderr, "[build] top levels (%zu tasks, %d threads) %.3f s\n", tasks.size(), n_threads, std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
+        std::vector<Item>().swap(tmp);
         std::vector<std::vector<BuildNode>> sub(tasks.size());
         std::vector<int> sub_depth(tasks.size(), 0);
         std::atomic<size_t> next(0);
@@ -308,21 +380,37 @@ struct Builder {
                 size_t t = next.fetch_add(1);
                 if (t >= tasks.size()) break;
                 sub[t].reserve(2 * (size_t)tasks[t].count);
-                build(sub[t], tasks[t].first, tasks[t].count, tasks[t].depth, sub_depth[t], nullptr, 0);
+                // the placeholder kept the range's box; the centroid bounds are re-measured here (one pass per task)
+                Bounds m; for (int i = tasks[t].first; i < tasks[t].first + tasks[t].count; ++i) m.add(items[i]);
+                build(sub[t], tasks[t].first, tasks[t].count, tasks[t].depth, sub_depth[t], nullptr, 0, m);
             }
         };
         std::vector<std::thread> th;
         for (int i = 1; i < n_threads; ++i) th.emplace_back(worker);
         worker();
         for (auto& t : th) t.join();
-        for (size_t t = 0; t < tasks.size(); ++t) {            // splice: local root replaces the placeholder
-            max_depth = std::max(max_depth, sub_depth[t]);
-            const int off = (int)nodes.size() - 1;             // local index c >= 1  ->  off + c
-            auto remap = [&](BuildNode b) { if (b.left >= 0) { b.left += off; b.right += off; } return b; };
-            nodes[tasks[t].node] = remap(sub[t][0]);
-            for (size_t c = 1; c < sub[t].size(); ++c) nodes.push_back(remap(sub[t][c]));
-            std::vector<BuildNode>().swap(sub[t]);
-        }
+        if (timing) fprintf(stderr, "[build] subtrees %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count());
+        // splice: every task's local root replaces its placeholder, its other nodes go to a precomputed slice of `nodes`
+        std::vector<int> off(tasks.size());
+        size_t total = nodes.size();
+        for (size_t t = 0; t < tasks.size(); ++t) { max_depth = std::max(max_depth, sub_depth[t]); off[t] = (int)total - 1; total += sub[t].size() - 1; }   // local index c >= 1 -> off + c
+        nodes.resize(total);
+        next = 0;
+        auto splice = [&]() {
+            for (;;) {
+                size_t t = next.fetch_add(1);
+                if (t >= tasks.size()) break;
+                const int o = off[t];
+                auto remap = [o](BuildNode b) { if (b.left >= 0) { b.left += o; b.right += o; } return b; };
+                nodes[tasks[t].node] = remap(sub[t][0]);
+                for (size_t c = 1; c < sub[t].size(); ++c) nodes[(size_t)o + c] = remap(sub[t][c]);
+                std::vector<BuildNode>().swap(sub[t]);
+            }
+        };
+        th.clear();
+        for (int i = 1; i < n_threads; ++i) th.emplace_back(splice);
+        splice();
+        for (auto& t : th) t.join();
     }
 };
 
@@ -396,16 +484,20 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         if (rc) return rc;
     }
     if (&roots == &g.world) {           // bulk spheres belong to the world, not to a single-hittable view
-        fl.bvh_prims.reserve(fl.bvh_prims.size() + g.bulk.size());
-        fl.bvh_boxes.reserve(fl.bvh_boxes.size() + g.bulk.size());
-        for (const BulkSphere& b : g.bulk) {
-            DPrim p; std::memset(&p, 0, sizeof(p));
-            p.s.cx = b.c[0]; p.s.cy = b.c[1]; p.s.cz = b.c[2]; p.s.r = b.r; p.type = PRIM_SPHERE; p.mat = b.mat - 1;
-            double ar = std::fabs(b.r);
-            Box3 bx; double lo[3] = {b.c[0] - ar, b.c[1] - ar, b.c[2] - ar}, hi[3] = {b.c[0] + ar, b.c[1] + ar, b.c[2] + ar};
-            bx.grow(lo); bx.grow(hi);
-            fl.bvh_prims.push_back(p); fl.bvh_boxes.push_back(bx);
-        }
+        const size_t base = fl.bvh_prims.size();
+        fl.bvh_prims.resize(base + g.bulk.size());
+        fl.bvh_boxes.resize(base + g.bulk.size());
+        parallel_chunks(g.bulk.size(), 1 << 16, [&](int, size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i) {
+                const BulkSphere& b = g.bulk[i];
+                DPrim p; std::memset(&p, 0, sizeof(p));
+                p.s.cx = b.c[0]; p.s.cy = b.c[1]; p.s.cz = b.c[2]; p.s.r = b.r; p.type = PRIM_SPHERE; p.mat = b.mat - 1;
+                double ar = std::fabs(b.r);
+                Box3 bx; double lo[3] = {b.c[0] - ar, b.c[1] - ar, b.c[2] - ar}, hi[3] = {b.c[0] + ar, b.c[1] + ar, b.c[2] + ar};
+                bx.grow(lo); bx.grow(hi);
+                fl.bvh_prims[base + i] = p; fl.bvh_boxes[base + i] = bx;
+            }
+        });
     }
     lap("emit");
     pack_materials(g, out);
@@ -428,7 +520,7 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         lap("build");
         // leaf order
         out.prims.resize(n);
-        for (int i = 0; i < n; ++i) out.prims[i] = fl.bvh_prims[b.items[i].id];
+        parallel_chunks((size_t)n, 1 << 16, [&](int, size_t i0, size_t i1) { for (size_t i = i0; i < i1; ++i) out.prims[i] = fl.bvh_prims[b.items[i].id]; });
         if (b.nodes[0].left < 0) {     // the whole scene is one leaf
             // one leaf: both slots point at it (tested twice, like the reference's duplicated single-object
             // leaves, src/hittable.rs:96-98); an "empty" slot cannot be encoded with min/max slabs
@@ -437,22 +529,32 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
             out.nodes.push_back(root);
         } else {
             // inner build nodes -> DNode indices (pre-order)
-            std::vector<int> dn(b.nodes.size(), -1);
-            int cnt = 0;
-            for (size_t i = 0; i < b.nodes.size(); ++i) if (b.nodes[i].left >= 0) dn[i] = cnt++;
+            const size_t nb = b.nodes.size();
+            std::vector<int> dn(nb, -1);
+            std::vector<int> part_cnt(worker_count() + 1, 0);
+            const int used = parallel_chunks(nb, 1 << 16, [&](int c, size_t i0, size_t i1) { int k = 0; for (size_t i = i0; i < i1; ++i) k += b.nodes[i].left >= 0; part_cnt[c + 1] = k; });
+            for (int c = 0; c < used; ++c) part_cnt[c + 1] += part_cnt[c];
+            const int cnt = part_cnt[used];
+            parallel_chunks(nb, 1 << 16, [&](int c, size_t i0, size_t i1) { int k = part_cnt[c]; for (size_t i = i0; i < i1; ++i) if (b.nodes[i].left >= 0) dn[i] = k++; });
             out.nodes.resize(cnt);
-            double sah = 0, root_area = std::max(b.nodes[0].box.area(), 1e-300);
-            for (size_t i = 0; i < b.nodes.size(); ++i) {
-                const BuildNode& bn = b.nodes[i];
-                if (bn.left < 0) { sah += Builder::C_ISECT * bn.count * bn.box.area() / root_area; continue; }
-                sah += Builder::C_TRAV * bn.box.area() / root_area;
-                DNode d; std::memset(&d, 0, sizeof(d));
-                const BuildNode& l = b.nodes[bn.left]; const BuildNode& r = b.nodes[bn.right];
-                set_child_box(d, 0, &l.box); set_child_box(d, 1, &r.box);
-                d.child0 = l.left >= 0 ? dn[bn.left] : leaf_code(l.first, l.count);
-                d.child1 = r.left >= 0 ? dn[bn.right] : leaf_code(r.first, r.count);
-                out.nodes[dn[i]] = d;
-            }
+            const double root_area = std::max(b.nodes[0].box.area(), 1e-300);
+            std::vector<double> part_sah(worker_count(), 0.0);
+            parallel_chunks(nb, 1 << 16, [&](int c, size_t i0, size_t i1) {
+                double sah = 0;
+                for (size_t i = i0; i < i1; ++i) {
+                    const BuildNode& bn = b.nodes[i];
+                    if (bn.left < 0) { sah += Builder::C_ISECT * bn.count * bn.box.area() / root_area; continue; }
+                    sah += Builder::C_TRAV * bn.box.area() / root_area;
+                    DNode d; std::memset(&d, 0, sizeof(d));
+                    const BuildNode& l = b.nodes[bn.left]; const BuildNode& r = b.nodes[bn.right];
+                    set_child_box(d, 0, &l.box); set_child_box(d, 1, &r.box);
+                    d.child0 = l.left >= 0 ? dn[bn.left] : leaf_code(l.first, l.count);
+                    d.child1 = r.left >= 0 ? dn[bn.right] : leaf_code(r.first, r.count);
+                    out.nodes[dn[i]] = d;
+                }
+                part_sah[c] = sah;
+            });
+            double sah = 0; for (double v : part_sah) sah += v;
             out.sah_cost = sah;
         }
     }

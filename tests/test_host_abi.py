@@ -207,3 +207,22 @@ def test_output_files_ppm_and_png(pkg, rtw, tmp_path):
         assert (lines[:, 0] == 0).all() and np.array_equal(lines[:, 1:].reshape(H, W, 3), img)
     with pytest.raises(pkg.RtwError):
         pkg.api.write_png(rtw, tmp_path / "no_such_dir" / "x.png", img, 1, 1)
+
+
+def test_parallel_bvh_build_equals_serial(pkg, rtw, monkeypatch):
+    """The host SAH builder streams the top levels of big scenes with all threads (per-thread bins, out-of-place
+    partition by prefix sums) and builds the subtrees below as tasks.  Same tree as the serial builder: same node
+    count, depth and SAH cost, and the structural validation (every primitive once, inside all its ancestors) passes."""
+    n = 300_000                                    # above the 2^18 threshold of the all-threads path
+    out = {}
+    for mode, threads in (("serial", "1"), ("parallel", "4"), ("parallel8", "8")):
+        monkeypatch.setenv("RTW_BUILD_THREADS", threads)
+        sc = pkg.Scene(rtw)
+        pkg.scenes.sweep_scene(sc, n, seed=11)
+        out[mode] = sc.debug_flatten()             # flatten + BVH + validate_bvh
+        sc.close()
+    for mode in ("parallel", "parallel8"):
+        for k in ("prims", "nodes", "depth"):
+            assert out[mode][k] == out["serial"][k], (mode, k)
+        assert abs(out[mode]["sah"] - out["serial"]["sah"]) <= 1e-9 * out["serial"]["sah"]
+    assert out["serial"]["nodes"] == n - 1
