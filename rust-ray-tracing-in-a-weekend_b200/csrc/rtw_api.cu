@@ -466,7 +466,10 @@ void free_replicas(rtw_scene* s) {
 }
 
 // pack FlatScene into one host blob; offsets -> DScene (device pointers filled per replica)
-struct Packed { std::vector<uint8_t> bytes; size_t o_nodes, o_prims, o_xf, o_media, o_mats, o_texs, o_perlin, o_image; };
+struct Packed { std::vector<uint8_t> bytes; size_t total = 0, o_nodes, o_prims, o_xf, o_media, o_mats, o_texs, o_perlin, o_image; };
+// Up to this size the scene is staged in one host blob and uploaded with ONE copy (C1: 100 KB, latency matters);
+// beyond it (the 1 M - 16 M sphere sweep: 0.15 - 2.4 GB) zero-filling and filling a second host copy costs ~1 s.
+static const size_t kBlobStageLimit = 64u << 20;
 void pack(const rtw::FlatScene& f, Packed& p) {
     size_t off = 0;
     auto place = [&](size_t n) { size_t o = off; off = align_up(off + std::max<size_t>(n, 16), 256); return o; };
@@ -478,6 +481,8 @@ void pack(const rtw::FlatScene& f, Packed& p) {
     p.o_texs = place(f.texs.size() * sizeof(DTex));
     p.o_perlin = place(f.perlin.size());
     p.o_image = place(f.image.size());
+    p.total = off;
+    if (off > kBlobStageLimit) return;        // big scene: sections are uploaded straight from their vectors (upload())
     p.bytes.assign(off, 0);
     auto cp = [&](size_t o, const void* src, size_t n) { if (n) std::memcpy(p.bytes.data() + o, src, n); };
     cp(p.o_nodes, f.nodes.data(), f.nodes.size() * sizeof(DNode));
@@ -488,6 +493,20 @@ void pack(const rtw::FlatScene& f, Packed& p) {
     cp(p.o_texs, f.texs.data(), f.texs.size() * sizeof(DTex));
     cp(p.o_perlin, f.perlin.data(), f.perlin.size());
     cp(p.o_image, f.image.data(), f.image.size());
+}
+cudaError_t upload(const rtw::FlatScene& f, const Packed& p, uint8_t* dst, cudaStream_t st) {
+    if (!p.bytes.empty()) return cudaMemcpyAsync(dst, p.bytes.data(), p.bytes.size(), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaSuccess;
+    auto cp = [&](size_t o, const void* src, size_t n) { if (n && e == cudaSuccess) e = cudaMemcpyAsync(dst + o, src, n, cudaMemcpyHostToDevice, st); };
+    cp(p.o_nodes, f.nodes.data(), f.nodes.size() * sizeof(DNode));
+    cp(p.o_prims, f.prims.data(), f.prims.size() * sizeof(DPrim));
+    cp(p.o_xf, f.xforms.data(), f.xforms.size() * sizeof(DXform));
+    cp(p.o_media, f.media.data(), f.media.size() * sizeof(DMedium));
+    cp(p.o_mats, f.mats.data(), f.mats.size() * sizeof(DMat));
+    cp(p.o_texs, f.texs.data(), f.texs.size() * sizeof(DTex));
+    cp(p.o_perlin, f.perlin.data(), f.perlin.size());
+    cp(p.o_image, f.image.data(), f.image.size());
+    return e;
 }
 DScene bind(const rtw::FlatScene& f, const Packed& p, uint8_t* base) {
     DScene d;
@@ -899,12 +918,12 @@ int rtw_scene_commit(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
                 cudaGetLastError();
             }
         }
-        if (r.blob_bytes < pk.bytes.size()) {
+        if (r.blob_bytes < pk.total) {
             if (r.blob) { CUDA_TRY(cudaFree(r.blob)); r.blob = nullptr; }
-            CUDA_TRY(cudaMalloc(&r.blob, pk.bytes.size())); r.blob_bytes = pk.bytes.size();
+            CUDA_TRY(cudaMalloc(&r.blob, pk.total)); r.blob_bytes = pk.total;
         }
-        CUDA_TRY(cudaMemcpyAsync(r.blob, pk.bytes.data(), pk.bytes.size(), cudaMemcpyHostToDevice, r.stream));
-        s->h2d_commit += pk.bytes.size();
+        CUDA_TRY(upload(s->flat, pk, r.blob, r.stream));
+        s->h2d_commit += pk.total;
         r.ds = bind(s->flat, pk, r.blob);
     }
     for (Replica& r : s->reps) { CUDA_TRY(cudaSetDevice(r.device)); CUDA_TRY(cudaStreamSynchronize(r.stream)); }
@@ -1119,8 +1138,9 @@ static int make_view(rtw_scene* s, int target, View& v) {
     int rc = rtw::flatten(s->g, std::vector<int>{target}, f, err);
     if (rc) return fail(rc, err);
     Packed pk; pack(f, pk);
-    CUDA_TRY(cudaMalloc(&v.blob, pk.bytes.size())); v.owned = true;
-    CUDA_TRY(cudaMemcpy(v.blob, pk.bytes.data(), pk.bytes.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&v.blob, pk.total)); v.owned = true;
+    CUDA_TRY(upload(f, pk, v.blob, 0));
+    CUDA_TRY(cudaStreamSynchronize(0));
     v.ds = bind(f, pk, v.blob);
     return 0;
 }
