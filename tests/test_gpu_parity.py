@@ -645,6 +645,33 @@ def test_tile_culling_is_conservative(pkg, gpu, name, W, H, spp):
     assert np.abs(a - b).max() <= 1e-5 * max(np.abs(a).max(), 1.0)
 
 
+@pytest.mark.parametrize("name,extent", [("random_scene", 12.0), ("cornell_box", 500.0), ("final_scene", 500.0)])
+def test_tile_culling_with_random_cameras(pkg, gpu, name, extent):
+    """Same check as above with cameras the scenes were not designed for: inside the scene, looking anywhere, narrow
+    and wide fields of view, pinhole to very large apertures, near and far focus planes, tilted up vectors - the
+    interval walk over the tile's ray bundle (lens box -> focus window) must stay a superset in all of them."""
+    sc, spec = pkg.scenes.build(gpu, name)
+    sc.commit(1, 0)
+    rs = np.random.RandomState(17)
+    centre = np.array(spec.look_at, float)
+    W, H, spp = 120, 67, 12
+    for k in range(10):
+        look_from = centre + rs.uniform(-extent, extent, 3) * (0.2 if k % 3 == 0 else 1.0)
+        look_at = centre + rs.uniform(-extent, extent, 3) * 0.5
+        vup = (0.0, 1.0, 0.0) if k % 2 == 0 else tuple(rs.uniform(-1, 1, 3))
+        vfov = float(rs.choice([5.0, 20.0, 40.0, 90.0, 140.0]))
+        aperture = float(rs.choice([0.0, 0.1, 2.0, 0.3 * extent]))
+        focus = float(rs.choice([0.05 * extent, extent, 10.0 * extent]))
+        cam = gpu.camera_new(tuple(look_from), tuple(look_at), vup, vfov, W / H, aperture, focus, 0.0, 1.0)
+        p0 = pkg.make_params(W, H, spp, background=(0.7, 0.8, 1.0), seed=100 + k, flags=pkg.api.RTW_FLAG_KERNEL_MEGA)
+        p1 = pkg.make_params(W, H, spp, background=(0.7, 0.8, 1.0), seed=100 + k,
+                             flags=pkg.api.RTW_FLAG_KERNEL_MEGA | pkg.api.RTW_FLAG_NO_TILE_CULL)
+        a, st0 = sc.render(cam, p0)
+        b, st1 = sc.render(cam, p1)
+        assert st0["rays"] == st1["rays"], (name, k, st0["rays"], st1["rays"])
+        assert np.abs(a - b).max() <= 1e-5 * max(np.abs(a).max(), 1.0), (name, k)
+
+
 def test_write_color_bit_exact(pkg, gpu, orc):
     """write_color (src/math.rs:119-132): gamma 2, clamp, *256 truncation — byte-exact against the oracle."""
     import ctypes as C
