@@ -311,15 +311,14 @@ RTW_DEV TRay make_tray(const Ray& r) {
     return t;
 }
 
-RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float time, double& cx, double& cy, double& cz, double& r) {
+RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float inv_dt, float time, double& cx, double& cy, double& cz, double& r) {
     const double2* q = reinterpret_cast<const double2*>(pp);
     double2 c01 = __ldg(q), c23 = __ldg(q + 1);
     cx = c01.x; cy = c01.y; cz = c23.x; r = c23.y;
     if (type == PRIM_MOVING_SPHERE) {                                                      // get_center_at_time :556-558
-        double2 d01 = __ldg(q + 2), d2t = __ldg(q + 3);
-        float2 tt = *reinterpret_cast<const float2*>(&d2t.y);
-        double s = (double)((time - tt.x) * tt.y);
-        cx = fma(s, d01.x, cx); cy = fma(s, d01.y, cy); cz = fma(s, d2t.x, cz);
+        const float4 mv = __ldg(reinterpret_cast<const float4*>(pp) + 2);                  // centre1 - centre0, time0
+        double s = (double)((time - mv.w) * inv_dt);
+        cx = fma(s, (double)mv.x, cx); cy = fma(s, (double)mv.y, cy); cz = fma(s, (double)mv.z, cz);
     }
 }
 
@@ -327,9 +326,9 @@ RTW_DEV void load_prim_center(const DPrim* __restrict__ pp, int type, float time
 // then the numerically stable root pair in f32 (q = -(half_b + sign(half_b) sqrt(disc)); roots q/a and c/q).
 // Branch-free: a warp processes 32 different leaves, an early-out would only add divergence.
 // Returns the accepted root or NaN.
-RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, const TRay& r, float t_lo, float t_hi, bool self, float* far_root = nullptr) {
+RTW_DEV float sphere_root(const DPrim* __restrict__ pp, int type, float inv_dt, const TRay& r, float t_lo, float t_hi, bool self, float* far_root = nullptr) {
     double cx, cy, cz, rad;
-    load_prim_center(pp, type, r.time, cx, cy, cz, rad);
+    load_prim_center(pp, type, inv_dt, r.time, cx, cy, cz, rad);
     double ocx = r.gox() - cx, ocy = r.goy() - cy, ocz = r.goz() - cz;
     double half_b = ocx * r.gdx() + ocy * r.gdy() + ocz * r.gdz();
     double c = ocx * ocx + ocy * ocy + ocz * ocz - rad * rad;
@@ -385,8 +384,8 @@ struct XfCache { int xf; V3 o, d; };
 template <int F = FEAT_ALL>
 RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip, float* far_root = nullptr, XfCache* xc = nullptr) {
     const DPrim* pp = sc.prims + pi;
-    int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);      // type, mat, xform, pad
-    if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, r, t_lo, t_hi, pi == skip, far_root);
+    int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 3);      // type, mat, xform, 1/dt (moving sphere)
+    if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, __int_as_float(meta.w), r, t_lo, t_hi, pi == skip, far_root);
     if (pi == skip) return CUDART_NAN_F;
     V3 o = r.o, d = r.d;
     if (F & FEAT_RXFORM) {
@@ -503,7 +502,7 @@ RTW_DEV void set_face_normal(V3 dir, V3 outward, V3& normal, int& front) {
 template <int F = FEAT_ALL>
 RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool want_uv, HitRec& rec) {
     const DPrim* pp = sc.prims + pi;
-    int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 4);
+    int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 3);
     rec.t = t; rec.mat = meta.y; rec.u = 0.0f; rec.v = 0.0f;
     Ray wr; wr.o = r.o; wr.d = r.d;
     rec.p = ray_at(wr, t);
@@ -513,7 +512,7 @@ RTW_DEV void finalize_hit(const DScene& sc, int pi, float t, const TRay& r, bool
     if (xf) { float4 m = __ldg(reinterpret_cast<const float4*>(sc.xforms + xf)); mc = m.x; ms = m.y; d_obj = mk(mc * r.d.x - ms * r.d.z, r.d.y, ms * r.d.x + mc * r.d.z); }
     if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) {
         double cx, cy, cz, rad;
-        load_prim_center(pp, meta.x, r.time, cx, cy, cz, rad);
+        load_prim_center(pp, meta.x, __int_as_float(meta.w), r.time, cx, cy, cz, rad);
         // one Newton step of f(t) = a t^2 + 2 half_b t + c in f64: t, the hit point and the normal then carry
         // the reference's precision (an f32 t alone leaves |t d| * 1e-7 / r ~ 1e-5 of error on small far spheres)
         double ocx = r.gox() - cx, ocy = r.goy() - cy, ocz = r.goz() - cz;
@@ -568,7 +567,7 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     // over the boundary prims (hit_hittables :43-55) sharing ONE inlined copy of the primitive test
     // A boundary made of ONE sphere (final_scene's two media): its second crossing comes out of the same discriminant
     // — the first probe returns the near root, the second probe can only return the far one — so one test serves both.
-    const bool one_sphere = md.y == 1 && __ldg(reinterpret_cast<const int*>(sc.prims + md.x) + 16) <= PRIM_MOVING_SPHERE;
+    const bool one_sphere = md.y == 1 && __ldg(reinterpret_cast<const int*>(sc.prims + md.x) + 12) <= PRIM_MOVING_SPHERE;
     float t1 = 0.f, t2 = 0.f, lo = -inf, far_root = CUDART_NAN_F;
     XfCache xc; xc.xf = -1; xc.o = r.o; xc.d = r.d;        // 6 faces x 2 probes of a rotated Box: one transform instead of 12
     // Small boundaries (a Box: 6 faces) are intersected ONCE: the first scan keeps every face's root, the second scan

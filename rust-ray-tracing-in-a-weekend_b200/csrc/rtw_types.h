@@ -5,7 +5,7 @@
 // scene is flattened once per commit into index-linked 16-byte-aligned records in ONE device blob:
 //
 //   nodes   : 64 B  binary BVH nodes holding BOTH children's boxes (4 x LDG.128 per visit)
-//   prims   : 80 B  records (5 x 16 B).  BVH-referenced prims first (leaf order), medium boundaries after
+//   prims   : 64 B  records (4 x 16 B).  BVH-referenced prims first (leaf order), medium boundaries after
 //   xforms  : composed Translate/RotateY chains (src/hittable.rs:232-247, :386-415)
 //   media   : ConstantMedium table (src/hittable.rs:417-473)
 //   mats    : 32 B  materials, solid-colour textures inlined
@@ -32,20 +32,23 @@ enum : int32_t {
 enum : int32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
 enum : int32_t { TEX_SOLID = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3 };
 
-// 80 B.  Spheres keep centre/radius in f64: the discriminant is evaluated in f64 on the device (B200 runs
-// FP64 at half the FP32 rate), which removes the |oc|^2 - r^2 cancellation of the r = 1000 ground sphere.
+// 64 B = two 32-byte sectors, both used by every test (an 80-byte record left one sector in 2.5 unused in the L1 lines
+// it occupied).  Spheres keep centre/radius in f64: the discriminant is evaluated in f64 on the device (B200 runs
+// FP64 at half the FP32 rate), which removes the |oc|^2 - r^2 cancellation of the r = 1000 ground sphere.  The motion
+// vector of a MovingSphere is f32 (|centre1 - centre0| < 1 in the reference's scenes: 3e-8 absolute).
 struct RTW_ALIGN(16) DPrim {
     union {
         struct { double cx, cy, cz, r; } s;       // sphere: centre at time0 (world space, xform baked), radius
         struct { float a0, a1, b0, b1, k, pad0, pad1, pad2; } q;   // rect (object space)
     };
-    double dcx, dcy, dcz;                         // moving sphere: centre1 - centre0
-    float t0, inv_dt;                             // moving sphere: time0, 1/(time1-time0)
+    float dcx, dcy, dcz;                          // moving sphere: centre1 - centre0
+    float t0;                                     // moving sphere: time0
     int32_t type;                                 // PRIM_*
     int32_t mat;                                  // 0-based material index (reference handle - 1)
     int32_t xform;                                // 0 = identity, else index into xforms
-    int32_t pad;
+    float inv_dt;                                 // moving sphere: 1/(time1-time0)
 };
+static_assert(sizeof(DPrim) == 64, "DPrim is two sectors");
 
 // Aila–Laine style node: both children's slabs live in the parent.
 struct RTW_ALIGN(16) DNode {

@@ -126,11 +126,14 @@ struct Flattener {
         if (h.kind == H_MOVING_SPHERE) {
             double dc[3] = {h.c1.x - h.c0.x, h.c1.y - h.c0.y, h.c1.z - h.c0.z}, dcw[3];
             to_world_vec(m, dc, dcw);
-            p.dcx = dcw[0]; p.dcy = dcw[1]; p.dcz = dcw[2];
+            p.dcx = (float)dcw[0]; p.dcy = (float)dcw[1]; p.dcz = (float)dcw[2];
             p.t0 = (float)h.time0; p.inv_dt = (float)(1.0 / (h.time1 - h.time0));
             p.type = PRIM_MOVING_SPHERE;
-            // box over the sphere's own [time0, time1] (the MovingSphere arm shadows the arguments, hittable.rs:480-482)
-            double lo1[3] = {lo[0] + dcw[0], lo[1] + dcw[1], lo[2] + dcw[2]}, hi1[3] = {hi[0] + dcw[0], hi[1] + dcw[1], hi[2] + dcw[2]};
+            // box over the sphere's own [time0, time1] (the MovingSphere arm shadows the arguments, hittable.rs:480-482),
+            // spanned by BOTH the f64 motion vector and the f32 one the device moves the centre with
+            const double dcf[3] = {(double)p.dcx, (double)p.dcy, (double)p.dcz};
+            double lo1[3], hi1[3];
+            for (int a = 0; a < 3; ++a) { lo1[a] = lo[a] + std::min(dcw[a], dcf[a]); hi1[a] = hi[a] + std::max(dcw[a], dcf[a]); }
             b.grow(lo1); b.grow(hi1);
         } else p.type = PRIM_SPHERE;
         p.mat = h.mat - 1;

@@ -23,7 +23,7 @@ for n in sizes:
     rec = dict(n_spheres=n, gpus=gpus, spp=spp, build_scene_s=round(t1 - t0, 2), commit_s=round(t2 - t1, 2), ms_render=round(best["ms_render"], 2),
                mpaths_s=round(best["paths"] / best["ms_render"] / 1e3, 1), mrays_s=round(best["rays"] / best["ms_render"] / 1e3, 1),
                rays_per_path=round(best["rays"] / best["paths"], 3), nodes=best["n_nodes"], image_mean=float(img.mean() / spp),
-               scene_bytes=best["n_nodes"] * 64 + best["n_prims"] * 80)
+               scene_bytes=best["n_nodes"] * 64 + best["n_prims"] * 64)
     out.append(rec); print(json.dumps(rec), flush=True)
     sc.close()
 os.makedirs("gpurun_out", exist_ok=True)
