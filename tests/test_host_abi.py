@@ -226,3 +226,66 @@ def test_parallel_bvh_build_equals_serial(pkg, rtw, monkeypatch):
             assert out[mode][k] == out["serial"][k], (mode, k)
         assert abs(out[mode]["sah"] - out["serial"]["sah"]) <= 1e-9 * out["serial"]["sah"]
     assert out["serial"]["nodes"] == n - 1
+
+
+def test_flatten_random_scene_graphs(pkg, rtw):
+    """Random compositions of the reference's Hittable variants (src/hittable.rs:29-41): spheres, moving spheres,
+    rects, boxes, Translate / RotateY wrappers up to the supported depth, BvhNodes of mixed members, media over
+    spheres and (instanced) boxes.  Flatten must account for every surface primitive (a Box is 6 rects), count media,
+    and produce a BVH that passes the structural validation; deeper wrapper chains are refused with
+    RTW_ERR_UNSUPPORTED_NESTING, never mis-flattened."""
+    rs = np.random.RandomState(2024)
+    for trial in range(40):
+        sc = pkg.Scene(rtw)
+        mat = sc.lambertian(sc.tex_solid((0.5, 0.5, 0.5)))
+        iso = sc.isotropic(sc.tex_solid((1.0, 1.0, 1.0)))
+        n_surface = n_boundary = n_media = 0
+        too_deep = False
+
+        def leaf():
+            k = rs.randint(5)
+            c = tuple(rs.uniform(-50, 50, 3))
+            if k == 0:
+                return sc.sphere(mat, c, float(rs.uniform(0.1, 5))), 1
+            if k == 1:
+                return sc.moving_sphere(mat, c, tuple(np.array(c) + rs.uniform(-1, 1, 3)), 0.0, 1.0, float(rs.uniform(0.1, 3))), 1
+            if k == 2:
+                a0, b0 = rs.uniform(-50, 40, 2)
+                f = [sc.xy_rect, sc.xz_rect, sc.yz_rect][rs.randint(3)]
+                return f(mat, a0, a0 + rs.uniform(1, 10), b0, b0 + rs.uniform(1, 10), float(rs.uniform(-50, 50))), 1
+            lo = rs.uniform(-50, 40, 3)
+            return sc.box(tuple(lo), tuple(lo + rs.uniform(1, 10, 3)), mat), 6
+
+        def wrap(h, depth):
+            for _ in range(depth):
+                h = sc.translate(h, tuple(rs.uniform(-5, 5, 3))) if rs.randint(2) else sc.rotate_y(float(rs.uniform(-90, 90)), h)
+            return h
+
+        for _ in range(rs.randint(1, 12)):
+            kind = rs.randint(4)
+            depth = int(rs.choice([0, 0, 1, 2, 4, 5]))
+            if kind == 0:                                            # wrapped leaf
+                h, n = leaf()
+                too_deep |= depth > 4
+                sc.push(wrap(h, depth)); n_surface += n
+            elif kind == 1:                                          # BvhNode of leaves, possibly wrapped as a whole
+                members = [leaf() for _ in range(rs.randint(1, 9))]
+                node = sc.bvh_node([m[0] for m in members], 0.0, 1.0)
+                too_deep |= depth > 4
+                sc.push(wrap(node, depth)); n_surface += sum(m[1] for m in members)
+            elif kind == 2:                                          # medium over a sphere or an instanced box
+                h, n = leaf()
+                d = min(depth, 4)
+                sc.push(sc.constant_medium(wrap(h, d), float(rs.uniform(0.001, 0.5)), iso)); n_boundary += n; n_media += 1
+            else:
+                h, n = leaf()
+                sc.push(h); n_surface += n
+        if too_deep:
+            with pytest.raises(pkg.RtwError) as e:
+                sc.debug_flatten()
+            assert e.value.code == -2
+        else:
+            d = sc.debug_flatten()                                   # flatten + BVH + validate_bvh
+            assert d["bvh_prims"] == n_surface and d["prims"] == n_surface + n_boundary and d["media"] == n_media, trial
+            assert d["nodes"] == max(1, n_surface - 1)               # one primitive per leaf
+        sc.close()
