@@ -289,3 +289,30 @@ def test_flatten_random_scene_graphs(pkg, rtw):
             assert d["bvh_prims"] == n_surface and d["prims"] == n_surface + n_boundary and d["media"] == n_media, trial
             assert d["nodes"] == max(1, n_surface - 1)               # one primitive per leaf
         sc.close()
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/rtw.h is the drop-in boundary: it must compile as C99 (what a Rust bindgen / cgo / ctypes user sees) and
+    as C++, with no CUDA, torch or C++ types in any signature."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "rtw.h")
+    for args in (["gcc", "-std=c99", "-pedantic", "-x", "c"], ["g++", "-std=c++17", "-x", "c++"]):
+        r = subprocess.run(args + ["-Wall", "-Wextra", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(hdr).read()
+    for banned in ("torch", "std::", "cudaStream", "at::Tensor", "#include <cuda"):
+        assert banned not in text, banned
+    # a C program can drive the host-only entry points
+    src = tmp_path / "t.c"
+    src.write_text('#include "rtw.h"\n#include <stdio.h>\nint main(void){ unsigned char px[6]={1,2,3,4,5,6};'
+                   ' rtw_scene* s = rtw_scene_new(); double c[3]={0,0,0}; int t = rtw_tex_solid(s,c); int m = rtw_mat_lambertian(s,t);'
+                   ' int h = rtw_sphere(s,m,c,1.0); int rc = rtw_world_push(s,h); rtw_scene_free(s);'
+                   ' printf("%d %d %d %d %d\\n", t>=0, m>=1, h>=0, rc, rtw_write_ppm("o.ppm", px, 2, 1)); return 0; }\n')
+    exe = tmp_path / "t"
+    lib_dir = os.path.join(ROOT, "rust-ray-tracing-in-a-weekend_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir, "-lrtw",
+                        f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 0 and r.stdout.split() == ["1", "1", "1", "0", "0"], (r.stdout, r.stderr)
+    assert (tmp_path / "o.ppm").read_text() == "P3\n2 1\n255\n\n1 2 3\n4 5 6\n"
