@@ -111,7 +111,8 @@ def run_reference(args, m):
     line = {"impl": "reference", "metric": "Mpaths/s, 1200x800 500spp depth 50 (book-1 random spheres)", "value": val, "unit": "Mpaths/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": val / README_MPATHS, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "book-1 random_scene 1200x800 500spp depth 50 (bounded sample per step)", "sample": sample},
+            "config": {"workload": f"book-1 random_scene (seed 1, 485 spheres) {W}x{H} {SPP}spp depth {DEPTH}", "paths_per_step": W * H * SPP,
+                       "sample": sample + " - each step is a bounded sample of the workload, throughput is spp-independent"},
             "cpu_baseline": {"value": val, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "extrapolated_full_render_s": W * H * SPP / (val * 1e6)}
