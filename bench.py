@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 import rtw_pkg  # noqa: E402
+from oracle.binding import load_oracle  # noqa: E402  (cpu_baseline / reference arm only: the checker, never the product)
 
 SCENE, W, H, SPP, DEPTH = "random_scene", 1200, 800, 500, 50
 README_MPATHS = 480.0 / 4200.0          # README.md:6 — 1 h 10 min on 10 CPU threads (older commit of the scene)
@@ -82,7 +83,7 @@ class ClockSampler:
 def cpu_baseline(m, threads=0, budget_s=12.0, impl_steps=None):
     """The reference's own algorithm on the host cores: f64, FLAT world list (src/main.rs:25 / hittable.rs:43-55),
     all threads, same scene/camera/depth, reduced spp (throughput is spp-independent)."""
-    orc = m.api.load_oracle()
+    orc = load_oracle()
     sc, spec = m.scenes.build(orc, SCENE, wrap_bvh=False)
     cores = int(orc.f("hardware_threads")()) if threads <= 0 else threads
     # calibrate on a 1/16-area image, 1 spp

@@ -21,6 +21,9 @@
  *    a thread-local message.
  *  - all scene inputs are f64 like the reference; the device path computes in
  *    f32 with f64 islands (see DESIGN.md "Precision").
+ *  - every constructor rejects non-finite numbers and the degenerate values the
+ *    reference would turn into NaN pixels (radius 0, density 0, time0 == time1,
+ *    ir 0, look_from == look_at) with RTW_ERR_INVALID_ARG.
  *  - there is NO CPU fallback: without a CUDA device rtw_scene_commit fails
  *    with RTW_ERR_NO_DEVICE.
  */
@@ -123,6 +126,9 @@ int rtw_yz_rect(rtw_scene*, int mat, double y0, double y1, double z0, double z1,
 int rtw_box(rtw_scene*, const double min[3], const double max[3], int mat);           /* new_box :132-145 */
 int rtw_translate(rtw_scene*, int child, const double offset[3]);                     /* Translate :38 */
 int rtw_rotate_y(rtw_scene*, double angle_deg, int child);                            /* new_rotate_y :147-199 */
+/* RotateY as the reference STORES it (sin_theta, cos_theta; src/hittable.rs:39): for hosts that walk an existing
+ * Hittable tree — no round trip of the angle through atan2 */
+int rtw_rotate_y_sincos(rtw_scene*, double sin_theta, double cos_theta, int child);
 int rtw_constant_medium(rtw_scene*, int child, double density, int phase_mat);        /* :201-207 */
 int rtw_bvh_node(rtw_scene*, const int32_t* children, int32_t n, double time0, double time1); /* :77-130 */
 int rtw_world_push(rtw_scene*, int hittable);                                         /* world.hittables.push */

@@ -3,7 +3,7 @@
 Only what the render hot path needs lives here:
   csrc/      hand-written CUDA (sm_100a) + the C ABI of include/rtw.h  -> librtw.so
   host/      C++ mirror of the reference's constructor surface (flatten -> C ABI)
-  api.py     ctypes binding of the C ABI (and of the oracle twin, for tests only)
+  api.py     ctypes binding of the C ABI
   scenes.py  the reference's scene functions restated as seeded input generators
 """
 from . import api, scenes  # noqa: F401

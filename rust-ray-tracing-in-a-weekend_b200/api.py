@@ -1,10 +1,11 @@
-"""ctypes binding of the C ABI in include/rtw.h (librtw.so) and of its oracle twin (liboracle.so).
+"""ctypes binding of the C ABI in include/rtw.h (librtw.so).
 
 This is the reference-side binding a maintainer would write (the Python analogue of the Rust
 `extern "C"` block shown in INTEGRATION.md): a scene is built with the reference's constructors
 (src/hittable.rs:29-41, src/material.rs:6-12, src/texture.rs:4-9, src/camera.rs:18-56), committed,
-and rendered.  The same `Scene` class drives either library because the oracle exports the same
-signatures under the `orc_` prefix; the oracle is only ever loaded by tests/, smoke() and bench.py.
+and rendered.  `Lib` binds any library that exports this ABI under a symbol prefix; the package itself only ever
+loads librtw.so.  (The test suite's CPU checker exports the same signatures under its own prefix; its loader lives
+with it, outside this package — nothing here imports it or can reach it.)
 
 librtw.so has NO CPU fallback: `load_rtw()` raises if the CUDA library is missing.
 """
@@ -17,7 +18,6 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 
 RTW_LIB_PATH = os.environ.get("RTW_LIB_PATH") or os.path.join(_HERE, "librtw.so")   # override: kernel experiments only
-ORACLE_LIB_PATH = os.path.join(_ROOT, "oracle", "liboracle.so")
 
 RTW_IPC_HANDLE_BYTES = 160
 RTW_FLAG_DEVICE_OUT = 1
@@ -65,19 +65,6 @@ class Stats(C.Structure):
         return d
 
 
-class OrcCounters(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("paths", "rays", "aabb", "sphere", "sphere_accept", "moving", "rect",
-                                           "rect_accept", "translate", "rotate", "medium")] + \
-               [("scatter", C.c_uint64 * 5), ("tex", C.c_uint64 * 4), ("accum", C.c_uint64), ("draws", C.c_uint64)]
-
-    def as_dict(self):
-        d = {}
-        for name, _ in self._fields_:
-            v = getattr(self, name)
-            d[name] = list(v) if hasattr(v, "__len__") else v
-        return d
-
-
 def make_params(width, height, spp, max_depth=50, background=(0.7, 0.8, 1.0), t_min=0.001, seed=1, n_gpus=0,
                 samples_per_unit=0, flags=0):
     p = RenderParams()
@@ -104,7 +91,8 @@ def _p(a, t=C.c_double):
 
 
 class Lib:
-    """One loaded library + symbol prefix ('rtw_' for the CUDA product, 'orc_' for the oracle)."""
+    """One loaded library exporting the include/rtw.h ABI under a symbol prefix ('rtw_' = the CUDA product)."""
+    scene_cls = None          # subclasses may name a Scene subclass with extra, library-specific calls
 
     def __init__(self, path, prefix):
         if not os.path.exists(path):
@@ -112,8 +100,8 @@ class Lib:
                            "There is no CPU fallback for the render path.")
         self.path, self.prefix = path, prefix
         self.dll = C.CDLL(path)
-        self.is_oracle = prefix == "orc_"
         self._sig()
+        self._sig_extra()
 
     def f(self, name):
         return getattr(self.dll, self.prefix + name)
@@ -165,41 +153,35 @@ class Lib:
                                       ip, dp, dp, dp, dp, dp, ip]
         f("test_texture").argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, dp]
         f("trace_paths").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_int32, ip, ip, ip, dp, ip]
-        if self.is_oracle:
-            f("render").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_int32, dp, dp,
-                                    C.POINTER(OrcCounters), dp]
-            f("write_color").argtypes = [dp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
-            f("scene_set_media_deferred").argtypes = [vp, C.c_int]
-            f("scene_set_build_seed").argtypes = [vp, C.c_uint64]
-            f("bounding_box").argtypes = [vp, C.c_int, C.c_double, C.c_double, dp, dp]
-            f("sphere_uv").argtypes = [C.c_int32, dp, dp, dp]
-            f("reflectance").argtypes = [C.c_int32, dp, dp, dp]
-            f("refract").argtypes = [dp, dp, C.c_double, dp]
-            f("reflect").argtypes = [dp, dp, dp]
-            f("perlin_noise").argtypes = [vp, C.c_int, C.c_int32, dp, dp, dp]
-            f("world_clear").argtypes = [vp]
-        else:
-            fp = C.POINTER(C.c_float)
-            f("scene_commit").argtypes = [vp, C.c_int32, C.c_int32]
-            f("render").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]
-            f("render_progressive").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_int32, C.c_int32, C.c_void_p,
-                                                C.c_void_p, C.c_void_p, C.POINTER(Stats)]
-            f("render_progressive").restype = C.c_int
-            f("write_color").argtypes = [fp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
-            f("device_count").restype = C.c_int
-            f("version").restype = C.c_char_p
-            u8p = C.POINTER(C.c_uint8)
-            f("shared_create").argtypes = [vp, C.c_int32, C.c_int32, u8p]
-            f("shared_open").argtypes = [vp, C.c_int32, C.c_int32, u8p]
-            f("shared_reset").argtypes = [vp]
-            f("render_shared").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.POINTER(Stats)]
-            f("shared_read").argtypes = [vp, fp]
-            f("shared_close").argtypes = [vp]
-            f("host_alloc").argtypes = [C.c_uint64]
-            f("host_alloc").restype = C.c_void_p
-            f("host_free").argtypes = [C.c_void_p]
-            f("host_free").restype = None
-            f("debug_flatten").argtypes = [vp, ip, dp]
+
+    def _sig_extra(self):
+        """Entry points beyond the constructors / parity hooks: the product's commit, render, IPC and output calls."""
+        f = self.f
+        vp, ip, dp = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)
+        fp = C.POINTER(C.c_float)
+        f("scene_commit").argtypes = [vp, C.c_int32, C.c_int32]
+        f("render").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_void_p, C.POINTER(Stats)]
+        f("render_progressive").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_int32, C.c_int32, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.POINTER(Stats)]
+        f("render_progressive").restype = C.c_int
+        f("write_color").argtypes = [fp, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
+        f("device_count").restype = C.c_int
+        f("version").restype = C.c_char_p
+        u8p = C.POINTER(C.c_uint8)
+        f("shared_create").argtypes = [vp, C.c_int32, C.c_int32, u8p]
+        f("shared_open").argtypes = [vp, C.c_int32, C.c_int32, u8p]
+        f("shared_reset").argtypes = [vp]
+        f("render_shared").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.POINTER(Stats)]
+        f("shared_read").argtypes = [vp, fp]
+        f("shared_close").argtypes = [vp]
+        f("host_alloc").argtypes = [C.c_uint64]
+        f("host_alloc").restype = C.c_void_p
+        f("host_free").argtypes = [C.c_void_p]
+        f("host_free").restype = None
+        f("debug_flatten").argtypes = [vp, ip, dp]
+        f("debug_flatten2").argtypes = [vp, ip, dp]
+        f("rotate_y_sincos").argtypes = [vp, C.c_double, C.c_double, C.c_int]
+        f("rotate_y_sincos").restype = C.c_int
 
     def check(self, rc):
         if rc < 0:
@@ -216,7 +198,7 @@ class Lib:
     def pinned_image(self, height, width):
         """H x W x 3 float32 array in page-locked host memory (rtw_host_alloc); falls back to pageable memory."""
         n = height * width * 3
-        p = self.f("host_alloc")(n * 4) if not self.is_oracle else None
+        p = self.f("host_alloc")(n * 4) if self.has("host_alloc") else None
         if not p:
             return np.zeros((height, width, 3), np.float32)
         buf = (C.c_float * n).from_address(p)
@@ -259,13 +241,6 @@ def load_rtw():
     return _libs["rtw"]
 
 
-def load_oracle():
-    """The CPU oracle — test infrastructure only (tests/, smoke(), bench.py cpu_baseline)."""
-    if "orc" not in _libs:
-        _libs["orc"] = Lib(ORACLE_LIB_PATH, "orc_")
-    return _libs["orc"]
-
-
 def write_ppm(lib, path, rgb8, width, height):
     """rtw_write_ppm: the reference's P3 text output (src/main.rs:472, :591-596) as a file."""
     a = np.ascontiguousarray(rgb8, np.uint8)
@@ -282,6 +257,9 @@ def write_png(lib, path, rgb8, width, height):
 
 class Scene:
     """= reference `World` (src/main.rs:40-50): materials + hittables, built through the C ABI."""
+
+    def __new__(cls, lib):
+        return object.__new__(lib.scene_cls if cls is Scene and lib.scene_cls else cls)
 
     def __init__(self, lib):
         self.lib = lib
@@ -368,6 +346,10 @@ class Scene:
     def rotate_y(self, angle_deg, child):
         return self._c("rotate_y", float(angle_deg), child)
 
+    def rotate_y_sincos(self, sin_theta, cos_theta, child):
+        """RotateY as the reference stores it (src/hittable.rs:39); product ABI only."""
+        return self._c("rotate_y_sincos", float(sin_theta), float(cos_theta), child)
+
     def constant_medium(self, child, density, phase_mat):
         return self._c("constant_medium", child, float(density), phase_mat)
 
@@ -386,17 +368,16 @@ class Scene:
 
     def debug_flatten(self):
         """Host-only: flatten + structural BVH validation (no device needed)."""
-        counts = np.zeros(8, np.int32)
+        counts = np.zeros(16, np.int32)
         sah = C.c_double(0)
-        self._c("debug_flatten", _p(counts, C.c_int32), C.byref(sah))
-        keys = ("prims", "bvh_prims", "nodes", "xforms", "media", "mats", "texs", "depth")
+        self._c("debug_flatten2", _p(counts, C.c_int32), C.byref(sah))
+        keys = ("prims", "bvh_prims", "nodes", "xforms", "media", "mats", "texs", "depth", "dedup")
         d = dict(zip(keys, (int(x) for x in counts)))
         d["sah"] = sah.value
         return d
 
     def render(self, cam, params, out=None):
         """rtw_render: per-pixel radiance SUM, H x W x 3 float32, row 0 = top.  Returns (image, stats dict)."""
-        assert not self.lib.is_oracle
         if out is None:
             out = np.zeros((params.height, params.width, 3), np.float32)
         st = Stats()
@@ -406,7 +387,6 @@ class Scene:
     def render_progressive(self, cam, params, first_sample=0, samples_per_pass=0, buf=None, progress=None):
         """rtw_render_progressive: samples [first_sample, params.spp) in passes; `buf` carries the sums of the samples
         below first_sample (resume).  progress(done, total, image_view) -> truthy to stop.  Returns (image, stats)."""
-        assert not self.lib.is_oracle
         if buf is None:
             assert first_sample == 0, "resuming needs the buffer of the interrupted render"
             buf = np.zeros((params.height, params.width, 3), np.float32)
@@ -426,23 +406,7 @@ class Scene:
         self._c("render", C.byref(cam), C.byref(params), C.c_void_p(dev_ptr), C.byref(st))
         return st.as_dict()
 
-    # --- oracle only
-    def render_oracle(self, cam, params, threads=0, counters=False, sumsq=False):
-        assert self.lib.is_oracle
-        H, W = params.height, params.width
-        out = np.zeros((H, W, 3))
-        sq = np.zeros((H, W, 3)) if sumsq else None
-        cnt = OrcCounters() if counters else None
-        secs = C.c_double(0)
-        self._c("render", C.byref(cam), C.byref(params), threads, _p(out), _p(sq),
-                C.byref(cnt) if counters else None, C.byref(secs))
-        return dict(sum=out, sumsq=sq, counters=cnt.as_dict() if counters else None, seconds=secs.value)
-
-    def set_media_deferred(self, on):
-        assert self.lib.is_oracle
-        self._c("scene_set_media_deferred", 1 if on else 0)
-
-    # --- parity hooks (both)
+    # --- parity hooks
     def test_hit(self, target, origin, direction, time=None, t_min=0.001, t_max=float("inf"), xi=None):
         o, d = _f64(origin), _f64(direction)
         n = len(o)

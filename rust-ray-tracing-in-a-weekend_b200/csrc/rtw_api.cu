@@ -10,10 +10,10 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -51,7 +51,7 @@ extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
 
 template <int F>
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
-render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
+render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
     __shared__ __align__(16) float acc[RTW_WARPS][96];    // per-warp tile accumulator (32 px x rgb)
     __shared__ float ring[RTW_WARPS][12][64];             // secondary-ray ring: o(3) d(3) time T(3) last_prim meta, 64 per warp
@@ -62,6 +62,8 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
 #ifdef RTW_INSTRUMENT
     unsigned long long dbg[6] = {0, 0, 0, 0, 0, 0};
 #endif
+    PathState ps;
+    ps.rng.bind(prm);                                          // key schedule: a constant-bank address, set once
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
@@ -82,7 +84,6 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
         int next = 0, pix = 0;
         int ring_head = 0, ring_count = 0;                     // warp-uniform
         bool alive = false;
-        PathState ps;
         // Each iteration of this loop is EITHER a primary batch or a secondary step; both run the SAME copy of the
         // closest-hit and shading code (two inlined copies doubled the kernel to 145 KB and cost 40 % in i-cache misses).
         //  primary batch : taken when the ring cannot serve the lanes that need a path.  All 32 lanes queue their
@@ -117,7 +118,7 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
                     const int pl = idx % npix, sample = s0 + idx / npix;
                     const int px = pl % tw, py = pl / tw;
                     wpix = py * 8 + px;
-                    path_begin(cam, prm, tx * 8 + px, ty * 4 + py, sample, ps);
+                    path_begin(cam, prm, tx * 8 + px, ty * 4 + py, sample, ps, true);
                     ps.segment = 1;
                     ps.rng.set_bounce(1u);
                     work = true;
@@ -132,7 +133,7 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
                         ps.last_prim = __float_as_int(rg[640]);
                         const int meta = __float_as_int(rg[704]);
                         pix = meta & 31;
-                        ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)meta >> 11);
+                        ps.rng.start((uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)meta >> 11);
                         ps.segment = (meta >> 5) & 63;
                         alive = true;
                     }
@@ -222,7 +223,7 @@ render_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ un
 // render_kernel — only the scheduling of the four stages differs.
 template <int POOL>
 __global__ void __launch_bounds__(RTW_BLOCK)
-render_pool_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
+render_pool_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
                    unsigned long long* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char pool_raw[];
     PoolSmem<POOL>* pools = reinterpret_cast<PoolSmem<POOL>*>(pool_raw);
@@ -291,7 +292,7 @@ render_pool_kernel(DScene sc, DCamera cam, DParams prm, unsigned int* __restrict
 }
 
 // per-path radiance with the render's Philox keys (parity hook rtw_trace_paths)
-__global__ void trace_paths_kernel(DScene sc, DCamera cam, DParams prm, int n, const int* __restrict__ px, const int* __restrict__ py,
+__global__ void trace_paths_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ DParams prm, int n, const int* __restrict__ px, const int* __restrict__ py,
                                    const int* __restrict__ smp, double* __restrict__ out_rgb, int* __restrict__ out_seg) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -412,6 +413,12 @@ int fail(int code, const std::string& m) { g_err = m; return code; }
     } while (0)
 
 #define TRY(x) do { int rc_ = (x); if (rc_ < 0) return rc_; } while (0)
+
+// The reference computes with whatever it is given and renders NaN pixels (or panics); across the ABI the contract is
+// a status code: every constructor rejects non-finite numbers and the degenerate values that divide by zero later.
+bool fin(double v) { return std::isfinite(v); }
+bool fin3(const double* a) { return a && fin(a[0]) && fin(a[1]) && fin(a[2]); }
+template <class... T> bool fin_all(T... v) { bool ok = true; for (double x : {(double)v...}) ok = ok && fin(x); return ok; }
 
 struct Replica {
     int device = -1;
@@ -541,11 +548,13 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     if (p.width < 2 || p.height < 2 || p.spp < 1 || p.max_depth < 0) return fail(RTW_ERR_INVALID_ARG, "bad render params");
     // a queued ray packs pixel(5) | segment(6) | sample(21) into one word (the pool kernel: sample(17), checked at launch)
     if (p.spp > (1 << 20) || p.max_depth > 63) return fail(RTW_ERR_INVALID_ARG, "spp <= 1048576 and max_depth <= 63");
+    if (!fin_all(p.background[0], p.background[1], p.background[2], p.t_min)) return fail(RTW_ERR_INVALID_ARG, "non-finite background / t_min");
     std::memset(&d, 0, sizeof(d));
     d.width = p.width; d.height = p.height; d.spp = p.spp; d.max_depth = p.max_depth;
     d.bg_r = (float)p.background[0]; d.bg_g = (float)p.background[1]; d.bg_b = (float)p.background[2];
     d.t_min = (float)p.t_min;
     d.seed_lo = (uint32_t)p.seed; d.seed_hi = (uint32_t)(p.seed >> 32);
+    for (int k = 0; k < 10; ++k) { d.philox_rk[2 * k] = d.seed_lo + 0x9E3779B9u * (uint32_t)k; d.philox_rk[2 * k + 1] = d.seed_hi + 0xBB67AE85u * (uint32_t)k; }
     d.tiles_x = (p.width + 7) / 8; d.tiles_y = (p.height + 3) / 4;
     long long tiles = (long long)d.tiles_x * d.tiles_y;
     int chunk = p.samples_per_unit;
@@ -628,22 +637,21 @@ int launch_pool(Replica& r, int slot, const DCamera& dc, const DParams& dp, unsi
 }
 
 // Launch the render kernel on replicas [0, n) against (counter, fb); sync; fill stats.
-// The Philox key schedule lives in a __constant__ symbol: renders of one process are serialised on this mutex
-// (rtw_render is blocking anyway), so concurrent host threads with different seeds cannot interleave set + launch.
-std::mutex g_launch_mutex;
-
+// Everything a launch needs (scene pointers, camera, the Philox key schedule) travels in its kernel parameters: renders
+// on different scene handles share no mutable state and may run concurrently from different host threads.
 int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp, unsigned int* counter, float* fb, rtw_stats* st, int mode) {
-    std::lock_guard<std::mutex> lock(g_launch_mutex);
+    // MovingSphere boxes in the BVH cover the spheres' own [time0, time1] (as the reference's BvhNode boxes do); a ray
+    // time outside that interval could be culled where the reference's flat world list would still hit: refuse it.
+    if (std::min(cam->time0, cam->time1) < s->flat.mov_t0 || std::max(cam->time0, cam->time1) > s->flat.mov_t1)
+        return fail(RTW_ERR_INVALID_ARG, "camera shutter [time0, time1] exceeds the [time0, time1] of a MovingSphere in the scene");
     DCamera dc = to_dcamera(*cam);
-    uint32_t rk[20];
-    for (int k = 0; k < 10; ++k) { rk[2 * k] = dp.seed_lo + 0x9E3779B9u * (uint32_t)k; rk[2 * k + 1] = dp.seed_hi + 0xBB67AE85u * (uint32_t)k; }
     for (int i = 0; i < n_rep; ++i) {
         Replica& r = s->reps[i];
         CUDA_TRY(cudaSetDevice(r.device));
-        CUDA_TRY(cudaMemcpyToSymbolAsync(c_philox_rk, rk, sizeof(rk), 0, cudaMemcpyHostToDevice, r.stream));
         CUDA_TRY(cudaMemsetAsync(r.stats, 0, 32, r.stream));
         CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
         if (mode >= 1 && dp.first_sample + dp.spp > (1 << 17)) return fail(RTW_ERR_INVALID_ARG, "the pool kernel packs the sample index into 17 bits: spp <= 131072");
+        if (mode >= 1 && s->flat.media.size() > 15) return fail(RTW_ERR_INVALID_ARG, "the pool kernel packs the media draw count into 4 bits: at most 15 media");
         switch (mode) {
         case 1: TRY(launch_pool<64>(r, 0, dc, dp, counter, fb)); break;
         case 2: TRY(launch_pool<128>(r, 1, dc, dp, counter, fb)); break;
@@ -747,15 +755,19 @@ void rtw_scene_free(rtw_scene* s) {
 
 int rtw_tex_solid(rtw_scene* s, const double rgb[3]) {
     if (!s || !rgb) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!fin3(rgb)) return fail(RTW_ERR_INVALID_ARG, "non-finite colour");
     rtw::HTexture t; t.kind = TEX_SOLID; std::memcpy(t.c0, rgb, 24); s->g.textures.push_back(t); return (int)s->g.textures.size() - 1;
 }
 int rtw_tex_checker(rtw_scene* s, const double even[3], const double odd[3]) {
     if (!s || !even || !odd) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!fin3(even) || !fin3(odd)) return fail(RTW_ERR_INVALID_ARG, "non-finite colour");
     rtw::HTexture t; t.kind = TEX_CHECKER; std::memcpy(t.c0, even, 24); std::memcpy(t.c1, odd, 24);
     s->g.textures.push_back(t); return (int)s->g.textures.size() - 1;
 }
 int rtw_tex_noise(rtw_scene* s, const double* ranvec, const int32_t* px, const int32_t* py, const int32_t* pz, double scale) {
     if (!s || !ranvec || !px || !py || !pz) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!fin(scale)) return fail(RTW_ERR_INVALID_ARG, "non-finite noise scale");
+    for (int i = 0; i < 768; ++i) if (!fin(ranvec[i])) return fail(RTW_ERR_INVALID_ARG, "non-finite perlin gradient");
     rtw::HTexture t; t.kind = TEX_NOISE; t.scale = scale;
     t.ranvec.assign(ranvec, ranvec + 768);
     t.perm.assign(px, px + 256); t.perm.insert(t.perm.end(), py, py + 256); t.perm.insert(t.perm.end(), pz, pz + 256);
@@ -774,10 +786,12 @@ int rtw_mat_lambertian(rtw_scene* s, int tex) {
 }
 int rtw_mat_metal(rtw_scene* s, const double albedo[3], double fuzz) {
     if (!s || !albedo) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!fin3(albedo) || !fin(fuzz)) return fail(RTW_ERR_INVALID_ARG, "non-finite metal parameters");
     rtw::HMaterial m; m.kind = MAT_METAL; std::memcpy(m.albedo, albedo, 24); m.fuzz = fuzz; return push_mat(s, m);
 }
 int rtw_mat_dielectric(rtw_scene* s, double ir) {
     if (!s) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!fin(ir) || ir == 0.0) return fail(RTW_ERR_INVALID_ARG, "index of refraction must be finite and non-zero");
     rtw::HMaterial m; m.kind = MAT_DIELECTRIC; m.ir = ir; return push_mat(s, m);
 }
 int rtw_mat_diffuse_light(rtw_scene* s, int tex) {
@@ -791,11 +805,15 @@ int rtw_mat_isotropic(rtw_scene* s, int tex) {
 
 int rtw_sphere(rtw_scene* s, int mat, const double c[3], double r) {
     if (!mat_ok(s, mat) || !c) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    if (!fin3(c) || !fin(r) || r == 0.0) return fail(RTW_ERR_INVALID_ARG, "sphere centre / radius must be finite, radius non-zero");
     rtw::HNode h; h.kind = rtw::H_SPHERE; h.mat = mat; h.c0 = v3(c); h.radius = r; return push_node(s, h);
 }
 int rtw_sphere_batch(rtw_scene* s, int32_t n, const int32_t* mats, const double* centers, const double* radii) {
     if (!s || n <= 0 || !mats || !centers || !radii) return fail(RTW_ERR_INVALID_ARG, "bad argument");
     for (int i = 0; i < n; ++i) if (!mat_ok(s, mats[i])) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    for (int i = 0; i < n; ++i)
+        if (!fin_all(centers[3 * i], centers[3 * i + 1], centers[3 * i + 2], radii[i]) || radii[i] == 0.0)
+            return fail(RTW_ERR_INVALID_ARG, "sphere centre / radius must be finite, radius non-zero");
     size_t base = s->g.bulk.size();
     s->g.bulk.resize(base + (size_t)n);
     for (int i = 0; i < n; ++i) {
@@ -807,11 +825,14 @@ int rtw_sphere_batch(rtw_scene* s, int32_t n, const int32_t* mats, const double*
 }
 int rtw_moving_sphere(rtw_scene* s, int mat, const double c0[3], const double c1[3], double t0, double t1, double r) {
     if (!mat_ok(s, mat) || !c0 || !c1) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    if (!fin3(c0) || !fin3(c1) || !fin_all(t0, t1, r) || r == 0.0) return fail(RTW_ERR_INVALID_ARG, "moving sphere parameters must be finite, radius non-zero");
+    if (t0 == t1) return fail(RTW_ERR_INVALID_ARG, "moving sphere needs time0 != time1 (centre(t) divides by time1 - time0)");
     rtw::HNode h; h.kind = rtw::H_MOVING_SPHERE; h.mat = mat; h.c0 = v3(c0); h.c1 = v3(c1); h.time0 = t0; h.time1 = t1; h.radius = r;
     return push_node(s, h);
 }
 static int push_rect(rtw_scene* s, int kind, int mat, double a0, double a1, double b0, double b1, double k) {
     if (!mat_ok(s, mat)) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    if (!fin_all(a0, a1, b0, b1, k)) return fail(RTW_ERR_INVALID_ARG, "non-finite rect coordinates");
     rtw::HNode h; h.kind = kind; h.mat = mat; h.a0 = a0; h.a1 = a1; h.b0 = b0; h.b1 = b1; h.k = k; return push_node(s, h);
 }
 int rtw_xy_rect(rtw_scene* s, int mat, double x0, double x1, double y0, double y1, double k) { return push_rect(s, rtw::H_XY, mat, x0, x1, y0, y1, k); }
@@ -819,6 +840,7 @@ int rtw_xz_rect(rtw_scene* s, int mat, double x0, double x1, double z0, double z
 int rtw_yz_rect(rtw_scene* s, int mat, double y0, double y1, double z0, double z1, double k) { return push_rect(s, rtw::H_YZ, mat, y0, y1, z0, z1, k); }
 int rtw_box(rtw_scene* s, const double mn[3], const double mx[3], int mat) {           // new_box src/hittable.rs:132-145
     if (!mat_ok(s, mat) || !mn || !mx) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    if (!fin3(mn) || !fin3(mx)) return fail(RTW_ERR_INVALID_ARG, "non-finite box corners");
     rtw::HNode h; h.kind = rtw::H_BOX; h.mat = mat; h.bmin = v3(mn); h.bmax = v3(mx);
     h.children.push_back(rtw_xy_rect(s, mat, mn[0], mx[0], mn[1], mx[1], mx[2]));
     h.children.push_back(rtw_xy_rect(s, mat, mn[0], mx[0], mn[1], mx[1], mn[2]));
@@ -830,22 +852,35 @@ int rtw_box(rtw_scene* s, const double mn[3], const double mx[3], int mat) {    
 }
 int rtw_translate(rtw_scene* s, int child, const double offset[3]) {
     if (!node_ok(s, child) || !offset) return fail(RTW_ERR_INVALID_ARG, "bad child id");
+    if (!fin3(offset)) return fail(RTW_ERR_INVALID_ARG, "non-finite offset");
     rtw::HNode h; h.kind = rtw::H_TRANSLATE; h.child = child; h.offset = v3(offset); return push_node(s, h);
 }
 int rtw_rotate_y(rtw_scene* s, double angle_deg, int child) {                           // new_rotate_y src/hittable.rs:147-152
     if (!node_ok(s, child)) return fail(RTW_ERR_INVALID_ARG, "bad child id");
+    if (!fin(angle_deg)) return fail(RTW_ERR_INVALID_ARG, "non-finite angle");
     rtw::HNode h; h.kind = rtw::H_ROTATE_Y; h.child = child; h.angle_deg = angle_deg;
     double radians = angle_deg * 3.1415926535897932385 / 180.0;
     h.sin_theta = std::sin(radians); h.cos_theta = std::cos(radians);
     return push_node(s, h);
 }
+// A reference RotateY stores sin_theta / cos_theta, not the angle (src/hittable.rs:39): a host that walks an existing
+// Hittable tree hands those two numbers over unchanged instead of round-tripping them through atan2.
+int rtw_rotate_y_sincos(rtw_scene* s, double sin_theta, double cos_theta, int child) {
+    if (!node_ok(s, child)) return fail(RTW_ERR_INVALID_ARG, "bad child id");
+    if (!fin_all(sin_theta, cos_theta)) return fail(RTW_ERR_INVALID_ARG, "non-finite sin / cos");
+    rtw::HNode h; h.kind = rtw::H_ROTATE_Y; h.child = child; h.sin_theta = sin_theta; h.cos_theta = cos_theta;
+    h.angle_deg = std::atan2(sin_theta, cos_theta) * 180.0 / 3.1415926535897932385;
+    return push_node(s, h);
+}
 int rtw_constant_medium(rtw_scene* s, int child, double density, int phase_mat) {      // src/hittable.rs:201-207
     if (!node_ok(s, child)) return fail(RTW_ERR_INVALID_ARG, "bad child id");
     if (!mat_ok(s, phase_mat)) return fail(RTW_ERR_INVALID_ARG, "bad material handle");
+    if (!fin(density) || density == 0.0) return fail(RTW_ERR_INVALID_ARG, "medium density must be finite and non-zero (-1/density, src/hittable.rs:205)");
     rtw::HNode h; h.kind = rtw::H_MEDIUM; h.child = child; h.mat = phase_mat; h.density = density; return push_node(s, h);
 }
 int rtw_bvh_node(rtw_scene* s, const int32_t* children, int32_t n, double t0, double t1) {
     if (!s || !children || n <= 0) return fail(RTW_ERR_INVALID_ARG, "empty BvhNode");
+    if (!fin_all(t0, t1)) return fail(RTW_ERR_INVALID_ARG, "non-finite time range");
     rtw::HNode h; h.kind = rtw::H_BVH_NODE; h.time0 = t0; h.time1 = t1;
     for (int i = 0; i < n; ++i) { if (!node_ok(s, children[i])) return fail(RTW_ERR_INVALID_ARG, "bad child id"); h.children.push_back(children[i]); }
     return push_node(s, h);
@@ -858,6 +893,8 @@ int rtw_world_push(rtw_scene* s, int id) {
 int rtw_camera_new(const double look_from[3], const double look_at[3], const double vup[3], double vfov, double aspect,
                    double aperture, double focus_dist, double time0, double time1, rtw_camera* out) {   // src/camera.rs:18-56
     if (!look_from || !look_at || !vup || !out) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    if (!fin3(look_from) || !fin3(look_at) || !fin3(vup) || !fin_all(vfov, aspect, aperture, focus_dist, time0, time1))
+        return fail(RTW_ERR_INVALID_ARG, "non-finite camera parameters");
     auto sub = [](const double* a, const double* b, double* r) { for (int i = 0; i < 3; ++i) r[i] = a[i] - b[i]; };
     auto norm = [](double* v) { double inv = 1.0 / std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); for (int i = 0; i < 3; ++i) v[i] = inv * v[i]; };
     auto cross = [](const double* u, const double* v, double* r) { r[0] = u[1] * v[2] - u[2] * v[1]; r[1] = u[2] * v[0] - u[0] * v[2]; r[2] = u[0] * v[1] - u[1] * v[0]; };
@@ -876,11 +913,21 @@ int rtw_camera_new(const double look_from[3], const double look_at[3], const dou
         out->u[i] = u[i]; out->v[i] = v[i]; out->w[i] = w[i];
     }
     out->lens_radius = aperture * 0.5; out->time0 = time0; out->time1 = time1;
+    for (int i = 0; i < 3; ++i)      // look_from == look_at, vup parallel to the view direction, vfov = 180: the reference divides by 0
+        if (!fin_all(out->horizontal[i], out->vertical[i], out->lower_left_corner[i], out->u[i], out->v[i], out->w[i]))
+            return fail(RTW_ERR_INVALID_ARG, "degenerate camera (look_from == look_at, vup parallel to the view axis, or vfov out of range)");
     return RTW_OK;
 }
 
+static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device);
 int rtw_scene_commit(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     if (!s) return fail(RTW_ERR_INVALID_ARG, "null scene");
+    s->committed = false;          // a commit that fails part-way leaves the scene uncommitted and without replicas:
+    const int rc = commit_impl(s, n_gpus, first_device);      // no later render can launch on a half-built replica
+    if (rc < 0) { std::string keep = g_err; free_replicas(s); cudaGetLastError(); g_err = keep; }
+    return rc;
+}
+static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     TRY(need_device());
     int ndev = rtw_device_count();
     if (n_gpus <= 0) n_gpus = ndev - first_device;
@@ -968,6 +1015,8 @@ int rtw_render_progressive(rtw_scene* s, const rtw_camera* cam, const rtw_render
     if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "rtw_scene_commit has not been called since the last edit");
     if (p->flags & RTW_FLAG_DEVICE_OUT) return fail(RTW_ERR_INVALID_ARG, "rtw_render_progressive works on a host buffer");
     if (first_sample < 0 || first_sample > p->spp || samples_per_pass < 0) return fail(RTW_ERR_INVALID_ARG, "bad sample range");
+    // the ABSOLUTE sample index is a Philox counter coordinate and travels in 21 bits of a queued ray (17 in the pool kernel)
+    if (p->spp > (1 << 20)) return fail(RTW_ERR_INVALID_ARG, "spp <= 1048576");
     double t0 = now_ms();
     int n_rep = p->n_gpus > 0 ? p->n_gpus : (int)s->reps.size();
     if (n_rep > (int)s->reps.size()) return fail(RTW_ERR_INVALID_ARG, "n_gpus exceeds the committed replicas");
@@ -1073,6 +1122,7 @@ int rtw_shared_reset(rtw_scene* s) {
 }
 int rtw_render_shared(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, rtw_stats* st) {
     if (!s || !cam || !p || !s->shared.base) return fail(RTW_ERR_INVALID_ARG, "no shared framebuffer");
+    if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "rtw_scene_commit has not been called since the last edit");
     if (p->width != s->shared.width || p->height != s->shared.height) return fail(RTW_ERR_INVALID_ARG, "size mismatch");
     double t0 = now_ms();
     int world = p->n_gpus > 0 ? p->n_gpus : 1;    // ranks taking part (sizes the work units)
@@ -1211,11 +1261,9 @@ int rtw_trace_paths(rtw_scene* s, const rtw_camera* cam, const rtw_render_params
     if (!s || !cam || !p || n <= 0 || !px || !py || !smp || !out_rgb || !out_seg) return fail(RTW_ERR_INVALID_ARG, "bad argument");
     TRY(need_device());
     View vw; TRY(make_view(s, -1, vw));
+    if (std::min(cam->time0, cam->time1) < s->flat.mov_t0 || std::max(cam->time0, cam->time1) > s->flat.mov_t1)
+        return fail(RTW_ERR_INVALID_ARG, "camera shutter [time0, time1] exceeds the [time0, time1] of a MovingSphere in the scene");
     DParams dp; TRY(make_params(*p, 1, dp));
-    uint32_t rk[20];
-    for (int k = 0; k < 10; ++k) { rk[2 * k] = dp.seed_lo + 0x9E3779B9u * (uint32_t)k; rk[2 * k + 1] = dp.seed_hi + 0xBB67AE85u * (uint32_t)k; }
-    std::lock_guard<std::mutex> lock(g_launch_mutex);
-    CUDA_TRY(cudaMemcpyToSymbol(c_philox_rk, rk, sizeof(rk)));
     Scratch sc; int *d_x, *d_y, *d_s, *d_seg; double* d_rgb;
     TRY(sc.up(px, n, d_x)); TRY(sc.up(py, n, d_y)); TRY(sc.up(smp, n, d_s)); TRY(sc.up((double*)nullptr, 3 * (size_t)n, d_rgb)); TRY(sc.up((int*)nullptr, n, d_seg));
     trace_paths_kernel<<<(n + 127) / 128, 128>>>(vw.ds, to_dcamera(*cam), dp, n, d_x, d_y, d_s, d_rgb, d_seg);
@@ -1235,6 +1283,20 @@ int rtw_debug_flatten(rtw_scene* s, int32_t* out_counts /* prims, bvh_prims, nod
         out_counts[0] = (int)f.prims.size(); out_counts[1] = f.n_bvh_prims; out_counts[2] = (int)f.nodes.size(); out_counts[3] = (int)f.xforms.size();
         out_counts[4] = (int)f.media.size(); out_counts[5] = (int)f.mats.size(); out_counts[6] = (int)f.texs.size(); out_counts[7] = f.max_depth;
     }
+    if (out_sah) *out_sah = f.sah_cost;
+    return RTW_OK;
+}
+// same, with room to grow: out_counts[16] = the 8 above, [8] BvhNode members dropped as clones of an earlier member
+int rtw_debug_flatten2(rtw_scene* s, int32_t* out_counts, double* out_sah) {
+    if (!s || !out_counts) return fail(RTW_ERR_INVALID_ARG, "null argument");
+    rtw::FlatScene f; std::string err;
+    int rc = rtw::flatten(s->g, s->g.world, f, err);
+    if (rc) return fail(rc, err);
+    if (!rtw::validate_bvh(f, err)) return fail(RTW_ERR_INVALID_ARG, "invalid BVH: " + err);
+    std::memset(out_counts, 0, 16 * sizeof(int32_t));
+    out_counts[0] = (int)f.prims.size(); out_counts[1] = f.n_bvh_prims; out_counts[2] = (int)f.nodes.size(); out_counts[3] = (int)f.xforms.size();
+    out_counts[4] = (int)f.media.size(); out_counts[5] = (int)f.mats.size(); out_counts[6] = (int)f.texs.size(); out_counts[7] = f.max_depth;
+    out_counts[8] = f.n_dedup;
     if (out_sah) *out_sah = f.sah_cost;
     return RTW_OK;
 }

@@ -66,15 +66,15 @@ RTW_DEV void sphere_uv(V3 p, float& u, float& v) {                              
     u = (ang[1] + RTW_PI_F) * (1.0f / (2.0f * RTW_PI_F));
     v = ang[0] * (1.0f / RTW_PI_F);
 }
-// sinf for bounded arguments: Cody-Waite reduction by pi/2 in three FMAs + the usual minimax pair, WITHOUT the
-// Payne-Hanek path sinf carries for |x| > 1e5 (150 instructions).  Used for the marble phase scale*z + 10*turb, a
-// function of scene coordinates; beyond 1e5 an f32 phase has lost the sine anyway (ulp 0.008).  |err| < 1.5e-7.
-RTW_DEV float sin_bounded(float x) {
-    const float k = rintf(x * 0.636619772f);
-    const int q = __float2int_rn(k);
-    float r = fmaf(k, -1.57079601e+00f, x);
-    r = fmaf(k, -3.13916473e-07f, r);
-    r = fmaf(k, -5.39030253e-15f, r);
+// sin for bounded arguments: reduction by pi/2 + the usual f32 minimax pair, WITHOUT the Payne-Hanek path sinf carries
+// for |x| > 1e5 (150 instructions).  Used for the marble phase scale*z + 10*turb, a function of scene coordinates.
+// |err| < 1.5e-7 up to |x| ~ 1e9.
+// The phase arrives in f64 and is reduced in f64 (one DFMA against pi/2 and its tail): at |x| ~ 200 an f32 phase is
+// already quantised to 1.5e-5 — the whole 1e-5 budget of the texture value.
+RTW_DEV float sin_bounded(double x) {
+    const double kd = rint(x * 0.63661977236758134);
+    const int q = __double2int_rn(kd);
+    const float r = (float)fma(kd, -6.123233995736766e-17, fma(kd, -1.5707963267948966, x));
     const float s = r * r;
     const float sn = fmaf(fmaf(fmaf(-1.95152959e-4f, s, 8.33216087e-3f), s, -1.66666546e-1f), s * r, r);
     const float cs = fmaf(fmaf(fmaf(fmaf(2.44331571e-5f, s, -1.38873163e-3f), s, 4.16666457e-2f), s, -0.5f), s, 1.0f);
@@ -98,28 +98,32 @@ RTW_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-// The key is the same for every block of a launch: its 10-round schedule sits in constant memory (c_philox_rk, set
-// per launch from the seed) and feeds the LOP3s directly — 20 integer adds fewer per block than bumping the key.
-__constant__ uint32_t c_philox_rk[20];
-RTW_DEV void philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+// The key is the same for every block of a launch: its 10-round schedule travels in the kernel parameters
+// (DParams::philox_rk, filled per launch from the seed by make_params; kernel parameters live in the constant bank) and
+// feeds the LOP3s directly — 20 integer adds fewer per block than bumping the key.  Nothing is shared between
+// launches, so renders of different scenes / seeds never serialise on a symbol.
+RTW_DEV void philox4x32_10_rk(const uint32_t* __restrict__ rk, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                               uint32_t& o0, uint32_t& o1, uint32_t& o2, uint32_t& o3) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ c_philox_rk[2 * r]; c1 = lo1; c2 = hi0 ^ c3 ^ c_philox_rk[2 * r + 1]; c3 = lo0;
+        c0 = hi1 ^ c1 ^ rk[2 * r]; c1 = lo1; c2 = hi0 ^ c3 ^ rk[2 * r + 1]; c3 = lo0;
     }
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
 struct PhiloxRng {
-    uint32_t pixel, sample, bounce, draw;          // the key (seed) lives in c_philox_rk
+    uint32_t pixel, sample, bounce, draw;
     uint32_t w0, w1, w2, w3;
-    RTW_DEV void init(uint32_t, uint32_t, uint32_t px, uint32_t s) { pixel = px; sample = s; bounce = 0; draw = 0; }
+    const uint32_t* rk;                            // the launch's key schedule: &prm.philox_rk[0] of a __grid_constant__ DParams
+    RTW_DEV void bind(const DParams& prm) { rk = prm.philox_rk; }
+    RTW_DEV void start(uint32_t px, uint32_t s) { pixel = px; sample = s; bounce = 0; draw = 0; }      // after bind()
+    RTW_DEV void init(const DParams& prm, uint32_t px, uint32_t s) { bind(prm); start(px, s); }
     RTW_DEV void set_bounce(uint32_t b) { bounce = b; draw = 0; }
     RTW_DEV float next() {                               // random_double()
         uint32_t i = draw & 3u;
-        if (i == 0) philox4x32_10_rk(draw >> 2, bounce, pixel, sample, w0, w1, w2, w3);
+        if (i == 0) philox4x32_10_rk(rk, draw >> 2, bounce, pixel, sample, w0, w1, w2, w3);
         ++draw;
         uint32_t w = i == 0 ? w0 : (i == 1 ? w1 : (i == 2 ? w2 : w3));
         return (float)(w >> 8) * (1.0f / 16777216.0f);
@@ -130,7 +134,7 @@ struct PhiloxRng {
     RTW_DEV void next2(float& x, float& y, bool single = false) {
         const uint32_t i = draw & 3u;
         const uint32_t ox = i == 1 ? w1 : (i == 2 ? w2 : w3), oy = i == 1 ? w2 : w3;
-        if (i == 0 || (i == 3 && !single)) philox4x32_10_rk((draw + 1) >> 2, bounce, pixel, sample, w0, w1, w2, w3);
+        if (i == 0 || (i == 3 && !single)) philox4x32_10_rk(rk, (draw + 1) >> 2, bounce, pixel, sample, w0, w1, w2, w3);
         const uint32_t wx = i == 0 ? w0 : ox, wy = i == 0 ? w1 : (i == 3 ? w0 : oy);
         draw += single ? 1u : 2u;
         x = (float)(wx >> 8) * (1.0f / 16777216.0f); y = (float)(wy >> 8) * (1.0f / 16777216.0f);
@@ -138,7 +142,7 @@ struct PhiloxRng {
     RTW_DEV void next3(float& x, float& y, float& z) {
         const uint32_t i = draw & 3u;
         const uint32_t ox = i == 1 ? w1 : (i == 2 ? w2 : w3), oy = i == 1 ? w2 : w3, oz = w3;
-        if (i != 1) philox4x32_10_rk((draw + 3) >> 2, bounce, pixel, sample, w0, w1, w2, w3);
+        if (i != 1) philox4x32_10_rk(rk, (draw + 3) >> 2, bounce, pixel, sample, w0, w1, w2, w3);
         const uint32_t wx = i == 0 ? w0 : ox, wy = i == 0 ? w1 : (i == 3 ? w0 : oy), wz = i == 0 ? w2 : (i == 1 ? oz : (i == 2 ? w0 : w1));
         draw += 3;
         x = (float)(wx >> 8) * (1.0f / 16777216.0f); y = (float)(wy >> 8) * (1.0f / 16777216.0f); z = (float)(wz >> 8) * (1.0f / 16777216.0f);
@@ -226,14 +230,16 @@ RTW_DEV float perlin_noise(const uint8_t* __restrict__ tbl, V3 p) {
             }
     return accum;
 }
-RTW_DEV float perlin_turb(const uint8_t* __restrict__ tbl, V3 p, int depth) {
-    float accum = 0.0f, weight = 1.0f;
+// The octave sum runs in f64 (7 DFMA; the octave weights and coordinate doublings are powers of two, exact either way):
+// 10 * turb feeds a sine, and an f32 sum of seven f32 noise values alone leaves ~1e-6 on the phase.
+RTW_DEV double perlin_turb(const uint8_t* __restrict__ tbl, V3 p, int depth) {
+    double accum = 0.0; float weight = 1.0f;
     for (int i = 0; i < depth; ++i) {
-        accum += weight * perlin_noise(tbl, p);
+        accum = fma((double)weight, (double)perlin_noise(tbl, p), accum);
         weight *= 0.5f;
         p = p * 2.0f;
     }
-    return fabsf(accum);
+    return fabs(accum);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -257,7 +263,7 @@ RTW_DEV V3 texture_value(const DScene& sc, int tex, float u, float v, V3 p) {
     if (!(F & (FEAT_NOISE | FEAT_IMAGE))) return mk(t0.x, t0.y, t0.z);
     int4 ti = __ldg(reinterpret_cast<const int4*>(tp + 2));
     if ((F & FEAT_NOISE) && (kind == TEX_NOISE || !(F & FEAT_IMAGE))) {                                                               // :43-45
-        float c = 0.5f * (1.0f + sin_bounded(t0.w * p.z + 10.0f * perlin_turb(sc.perlin + (size_t)ti.x * RTW_PERLIN_BYTES, p, 7)));
+        float c = 0.5f * (1.0f + sin_bounded(fma((double)t0.w, (double)p.z, 10.0 * perlin_turb(sc.perlin + (size_t)ti.x * RTW_PERLIN_BYTES, p, 7))));
         return mk(c, c, c);
     }
     // TEX_IMAGE                                                                           // :46-73
@@ -405,10 +411,16 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
 RTW_DEV float slab_slack(V3 oi) { return 2.384185791015625e-07f * fmaxf(fmaxf(fabsf(oi.x), fabsf(oi.y)), fabsf(oi.z)); }
 // Per-ray constants of the slab test.  1/d from MUFU.RCP (relative error <= 2^-23): the SAME inv feeds o*inv, so the
 // error is purely relative on every plane distance and is covered by widening Ize's 2-ulp exit padding to 5 ulp.
+// A direction component of exactly +-0 (axis-parallel test rays; 2^-24 of the scatter draws) would give inv = +-inf and
+// plane distances inf - inf = NaN for a box that straddles the origin's coordinate — fmaxf/fminf drop the NaN and the
+// test MISSES a box the ray runs inside of (the reference's AABB::hit handles the infinities, src/aabb.rs:77-103).
+// Such a component is replaced by +-1e-30: every plane distance stays finite, the origin's side of each slab decides.
+// Its o/d (~1e30 |o|) is kept out of the shared slack term, which would otherwise open every box on the other two axes.
+RTW_DEV float slab_dir(float d) { return fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d; }
 RTW_DEV void slab_setup(V3 o, V3 d, V3& inv, V3& oi, float& slack) {
-    inv = mk(rcp_approx(d.x), rcp_approx(d.y), rcp_approx(d.z));
+    inv = mk(rcp_approx(slab_dir(d.x)), rcp_approx(slab_dir(d.y)), rcp_approx(slab_dir(d.z)));
     oi = mk(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-    slack = slab_slack(oi);
+    slack = slab_slack(mk(fabsf(d.x) < 1e-30f ? 0.f : oi.x, fabsf(d.y) < 1e-30f ? 0.f : oi.y, fabsf(d.z) < 1e-30f ? 0.f : oi.z));
 }
 RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
     float x0 = fmaf(mnx, inv.x, -oi.x), x1 = fmaf(mxx, inv.x, -oi.x);
@@ -572,7 +584,9 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     XfCache xc; xc.xf = -1; xc.o = r.o; xc.d = r.d;        // 6 faces x 2 probes of a rotated Box: one transform instead of 12
     // Small boundaries (a Box: 6 faces) are intersected ONCE: the first scan keeps every face's root, the second scan
     // (same faces, range [t1 + 0.0001, inf)) re-reads them — the same values hit_hittables would compute again.
-    float ts[8];
+    // A sphere among those faces returns its NEAR root to the (-inf, inf) probe; the second probe may need the FAR one
+    // (boundary.hit(rec1.t + 0.0001, inf) on a BvhNode / list of spheres), so both roots are kept.
+    float ts[8], tfar[8];
     const bool keep = md.y <= 8;
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
@@ -580,10 +594,12 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
 #pragma unroll 1
         for (int i = 0; i < md.y; ++i) {
             float t;
-            if (keep && pass == 1) t = ts[i];
+            if (keep && pass == 1) { t = ts[i]; if (!(t >= lo)) t = tfar[i]; }
             else {
-                t = prim_root(sc, md.x + i, r, keep ? -inf : lo, keep ? inf : hi, -1, &far_root, &xc);
-                if (keep) ts[i] = t;
+                float fr = CUDART_NAN_F;                             // stays NaN for rects
+                t = prim_root(sc, md.x + i, r, keep ? -inf : lo, keep ? inf : hi, -1, &fr, &xc);
+                if (keep) { ts[i] = t; tfar[i] = fr; }
+                if (one_sphere) far_root = fr;
             }
             if (t >= lo && t <= hi) { hi = t; found = t; }          // closest-so-far (hit_hittables :43-55); NaN fails
         }
@@ -777,8 +793,9 @@ RTW_DEV void flush_tile(const DParams& prm, float* __restrict__ fb, const float*
     }
 }
 
-RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, int s, PathState& ps) {   // :517-520
-    ps.rng.init(prm.seed_lo, prm.seed_hi, (uint32_t)(y * prm.width + x), (uint32_t)s);
+RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, int s, PathState& ps, bool bound = false) {   // :517-520
+    if (!bound) ps.rng.bind(prm);
+    ps.rng.start((uint32_t)(y * prm.width + x), (uint32_t)s);
     ps.ray = camera_ray_loop<true>(cam, 0.f, 0.f, (float)x, (float)y, (float)prm.width - 1.0f, (float)prm.height - 1.0f, ps.rng);
     ps.T = mk(1.f, 1.f, 1.f);
     ps.segment = 0; ps.last_prim = -1;

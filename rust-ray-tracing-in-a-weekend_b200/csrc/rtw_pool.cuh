@@ -72,9 +72,9 @@ RTW_DEV void shade_slot(PoolSmem<POOL>& P, int slot, const DScene& sc, const DPa
     }
     PhiloxRng g;
     const int x = tile_x0 + (pix & 7), y = tile_y0 + (pix >> 3);
-    g.init(prm.seed_lo, prm.seed_hi, (uint32_t)(y * prm.width + x), (uint32_t)sample);
+    g.init(prm, (uint32_t)(y * prm.width + x), (uint32_t)sample);
     g.bounce = (uint32_t)seg; g.draw = (uint32_t)ndraw;
-    if (ndraw & 3) philox4x32_10_rk((uint32_t)ndraw >> 2, g.bounce, g.pixel, g.sample, g.w0, g.w1, g.w2, g.w3);
+    if (ndraw & 3) philox4x32_10_rk(g.rk, (uint32_t)ndraw >> 2, g.bounce, g.pixel, g.sample, g.w0, g.w1, g.w2, g.w3);
     Ray sc_ray; V3 att, em;
     m.kind = KIND;                         // list membership == material kind: lets the compiler drop the other branches
     bool cont = scatter(sc, m, ray, rec, g, sc_ray, att, em);
@@ -174,7 +174,7 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                 if (sc.n_media) {
                     const int pix = meta & 31, seg = (meta >> 5) & 63, sample = meta >> 15;
                     PhiloxRng g;
-                    g.init(prm.seed_lo, prm.seed_hi, (uint32_t)((tile_y0 + (pix >> 3)) * prm.width + tile_x0 + (pix & 7)), (uint32_t)sample);
+                    g.init(prm, (uint32_t)((tile_y0 + (pix >> 3)) * prm.width + tile_x0 + (pix & 7)), (uint32_t)sample);
                     g.set_bounce((uint32_t)seg);
                     for (int mi = 0; mi < sc.n_media; ++mi) {
                         float t; int mat;

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <cmath>
 #include <thread>
+#include <unordered_map>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -108,6 +109,54 @@ struct Flattener {
         return (int)chains.size();
     }
 
+    // ---- structural identity of hittables ------------------------------------------------------------------------
+    // new_bvh_node puts a single-object span into BOTH children as separate clones (src/hittable.rs:96-98): a host that
+    // walks such a tree hands every odd-span leaf over twice.  Two coincident primitives would be tested twice and, worse,
+    // defeat the exact self-intersection rule (the twin of the primitive a ray starts on is not `skip`).  Members of one
+    // BvhNode that are field-by-field equal (what #[derive(Clone)] produces) are therefore emitted once; the closest hit
+    // is the same.  A ConstantMedium is never merged: two copies draw twice (src/hittable.rs:446).
+    std::vector<uint64_t> hash_memo;
+    std::vector<uint8_t> hash_done;
+    static uint64_t mix(uint64_t h, uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); return h * 0xBF58476D1CE4E5B9ull; }
+    static uint64_t bits(double d) { uint64_t u; std::memcpy(&u, &d, 8); return u; }
+    uint64_t hash_of(int id, int depth = 0) {
+        if (id < 0 || id >= (int)g.nodes.size() || depth > 64) return 0;
+        if (hash_done.empty()) { hash_done.assign(g.nodes.size(), 0); hash_memo.assign(g.nodes.size(), 0); }
+        if (hash_done[id]) return hash_memo[id];
+        const HNode& h = g.nodes[id];
+        uint64_t v = mix(0x1234567, (uint64_t)h.kind * 131 + (uint64_t)h.mat);
+        for (double d : {h.c0.x, h.c0.y, h.c0.z, h.c1.x, h.c1.y, h.c1.z, h.radius, h.time0, h.time1, h.a0, h.a1, h.b0, h.b1, h.k,
+                         h.bmin.x, h.bmin.y, h.bmin.z, h.bmax.x, h.bmax.y, h.bmax.z, h.offset.x, h.offset.y, h.offset.z,
+                         h.sin_theta, h.cos_theta, h.density}) v = mix(v, bits(d));
+        if (h.child >= 0) v = mix(v, hash_of(h.child, depth + 1));
+        for (int c : h.children) v = mix(v, hash_of(c, depth + 1));
+        hash_done[id] = 1; hash_memo[id] = v;
+        return v;
+    }
+    bool same_hittable(int a, int b, int depth = 0) const {
+        if (a == b) return true;
+        if (depth > 64) return false;
+        const HNode& x = g.nodes[a]; const HNode& y = g.nodes[b];
+        auto eq = [](double p, double q) { return bits(p) == bits(q); };
+        auto eq3 = [&](const V3d& p, const V3d& q) { return eq(p.x, q.x) && eq(p.y, q.y) && eq(p.z, q.z); };
+        if (x.kind != y.kind || x.mat != y.mat || !eq3(x.c0, y.c0) || !eq3(x.c1, y.c1) || !eq(x.radius, y.radius) || !eq(x.time0, y.time0) ||
+            !eq(x.time1, y.time1) || !eq(x.a0, y.a0) || !eq(x.a1, y.a1) || !eq(x.b0, y.b0) || !eq(x.b1, y.b1) || !eq(x.k, y.k) ||
+            !eq3(x.bmin, y.bmin) || !eq3(x.bmax, y.bmax) || !eq3(x.offset, y.offset) || !eq(x.sin_theta, y.sin_theta) ||
+            !eq(x.cos_theta, y.cos_theta) || !eq(x.density, y.density) || x.children.size() != y.children.size()) return false;
+        if ((x.child >= 0) != (y.child >= 0)) return false;
+        if (x.child >= 0 && !same_hittable(x.child, y.child, depth + 1)) return false;
+        for (size_t i = 0; i < x.children.size(); ++i) if (!same_hittable(x.children[i], y.children[i], depth + 1)) return false;
+        return true;
+    }
+    bool has_medium(int id, int depth = 0) const {
+        if (id < 0 || id >= (int)g.nodes.size() || depth > 64) return false;
+        const HNode& h = g.nodes[id];
+        if (h.kind == H_MEDIUM) return true;
+        if (h.child >= 0 && has_medium(h.child, depth + 1)) return true;
+        for (int c : h.children) if (has_medium(c, depth + 1)) return true;
+        return false;
+    }
+
     void push_prim(const DPrim& p, const Box3& b, bool boundary) {
         if (boundary) boundary_prims.push_back(p);
         else { bvh_prims.push_back(p); bvh_boxes.push_back(b); }
@@ -129,6 +178,7 @@ struct Flattener {
             p.dcx = (float)dcw[0]; p.dcy = (float)dcw[1]; p.dcz = (float)dcw[2];
             p.t0 = (float)h.time0; p.inv_dt = (float)(1.0 / (h.time1 - h.time0));
             p.type = PRIM_MOVING_SPHERE;
+            out.mov_t0 = std::max(out.mov_t0, std::min(h.time0, h.time1)); out.mov_t1 = std::min(out.mov_t1, std::max(h.time0, h.time1));
             // box over the sphere's own [time0, time1] (the MovingSphere arm shadows the arguments, hittable.rs:480-482),
             // spanned by BOTH the f64 motion vector and the f32 one the device moves the centre with
             const double dcf[3] = {(double)p.dcx, (double)p.dcy, (double)p.dcz};
@@ -171,9 +221,24 @@ struct Flattener {
         switch (h.kind) {
         case H_SPHERE: case H_MOVING_SPHERE: return emit_sphere(h, ch, boundary);
         case H_XY: case H_XZ: case H_YZ: return emit_rect(h, ch, boundary);
-        case H_BOX: case H_BVH_NODE:
+        case H_BOX:
             for (int c : h.children) { int rc = emit(c, ch, boundary, depth + 1); if (rc) return rc; }
             return 0;
+        case H_BVH_NODE: {
+            std::unordered_map<uint64_t, std::vector<int>> seen;       // structural hash -> members already emitted
+            for (int c : h.children) {
+                if (c < 0 || c >= (int)g.nodes.size()) return fail(RTW_ERR_INVALID_ARG, "hittable id out of range");
+                if (!has_medium(c)) {
+                    std::vector<int>& bucket = seen[hash_of(c)];
+                    bool dup = false;
+                    for (int o : bucket) if (same_hittable(o, c)) { dup = true; break; }
+                    if (dup) { ++out.n_dedup; continue; }
+                    bucket.push_back(c);
+                }
+                int rc = emit(c, ch, boundary, depth + 1); if (rc) return rc;
+            }
+            return 0;
+        }
         case H_TRANSLATE: case H_ROTATE_Y: {
             if ((int)ch.size() >= RTW_MAX_CHAIN)
                 return fail(RTW_ERR_UNSUPPORTED_NESTING, "more than 4 nested Translate/RotateY wrappers");

@@ -70,6 +70,10 @@ struct FlatScene {
     double sah_cost = 0;
     int max_depth = 0;
     int features = 0;                // FEAT_* bits (rtw_device.cuh) the scene needs: picks the kernel variant
+    int n_dedup = 0;                 // BvhNode members dropped because a field-by-field equal member came before (cloned leaves)
+    // Intersection of the [time0, time1] intervals of all MovingSpheres: their BVH boxes span exactly that interval (like the
+    // reference's BvhNode boxes, src/hittable.rs:480-482), so a camera shutter must stay inside it (checked at render).
+    double mov_t0 = -1e300, mov_t1 = 1e300;
 };
 
 // Flatten `roots` (world.hittables, or a single hittable for the test hooks).  Returns 0 or a negative

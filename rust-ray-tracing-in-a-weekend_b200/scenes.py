@@ -313,7 +313,7 @@ SCENES = {
 
 
 def build(lib, name, seed=1, wrap_bvh=False):
-    """-> (Scene, SceneSpec) built against `lib` (api.load_rtw() or api.load_oracle())."""
+    """-> (Scene, SceneSpec) built against `lib` (api.load_rtw(), or any other library exporting the same constructors)."""
     from .api import Scene
     sc = Scene(lib)
     spec = SCENES[name](sc, seed=seed, wrap_bvh=wrap_bvh)

@@ -18,7 +18,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def pkg():
     m = rtw_pkg.load()
-    need = [m.api.RTW_LIB_PATH, m.api.ORACLE_LIB_PATH]
+    from oracle.binding import ORACLE_LIB_PATH
+    need = [m.api.RTW_LIB_PATH, ORACLE_LIB_PATH]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__
         __graft_entry__.build()
@@ -28,7 +29,8 @@ def pkg():
 @pytest.fixture(scope="session")
 def orc(pkg):
     """CPU oracle (checker)."""
-    return pkg.api.load_oracle()
+    from oracle.binding import load_oracle
+    return load_oracle()
 
 
 @pytest.fixture(scope="session")

@@ -25,12 +25,26 @@ def test_product_does_not_link_or_load_the_oracle(rtw):
     assert "oracle" not in out
     syms = subprocess.run(["nm", "-D", "--defined-only", rtw.path], capture_output=True, text=True).stdout
     assert "orc_" not in syms
-    # no product source includes, links or dlopens anything under oracle/
+    # no product source — native OR Python — includes, links, imports or dlopens anything under oracle/: the package
+    # cannot reach the CPU path (the oracle's own loader lives in oracle/binding.py)
     pkg_dir = os.path.join(ROOT, "rust-ray-tracing-in-a-weekend_b200")
-    for base, _, files in os.walk(os.path.join(pkg_dir, "csrc")):
+    n = 0
+    for base, dirs, files in os.walk(pkg_dir):
+        dirs[:] = [d for d in dirs if d not in ("__pycache__", "variants")]
         for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h", "Makefile")):
+                continue
             src = open(os.path.join(base, f), errors="ignore").read()
-            assert "oracle/" not in src and "liboracle" not in src and "orc_" not in src, f
+            n += 1
+            assert "liboracle" not in src and "orc_" not in src and "load_oracle" not in src and "oracle.binding" not in src, f
+            assert "oracle/" not in src, f
+    assert n >= 10
+    assert not hasattr(pkg_mod(), "load_oracle") and not hasattr(pkg_mod().api, "load_oracle") and not hasattr(pkg_mod().api, "ORACLE_LIB_PATH")
+
+
+def pkg_mod():
+    import rtw_pkg
+    return rtw_pkg.load()
 
 
 def test_struct_layouts(pkg):
@@ -56,6 +70,96 @@ def test_status_codes_instead_of_panics(pkg, rtw):
     with pytest.raises(pkg.RtwError):
         sc.tex_noise(np.zeros((256, 3)), np.full(256, 300), np.zeros(256), np.zeros(256), 1.0)
     assert rtw.f("last_error")()
+
+
+def test_non_finite_and_degenerate_inputs_are_rejected(pkg, rtw):
+    """The reference turns these into NaN pixels or divisions by zero (src/hittable.rs:205 -1/density, :556-558
+    (time - time0) / (time1 - time0), :283 / radius, src/camera.rs:34 unit_vector(0)); the ABI returns INVALID_ARG."""
+    sc = pkg.Scene(rtw)
+    nan, inf = float("nan"), float("inf")
+    t = sc.tex_solid((1, 1, 1))
+    m = sc.lambertian(t)
+    s0 = sc.sphere(m, (0, 0, 0), 1.0)
+    bad = [
+        lambda: sc.tex_solid((nan, 0, 0)), lambda: sc.tex_checker((0, 0, 0), (0, inf, 0)),
+        lambda: sc.metal((1, nan, 1), 0.0), lambda: sc.metal((1, 1, 1), inf), lambda: sc.dielectric(nan), lambda: sc.dielectric(0.0),
+        lambda: sc.sphere(m, (nan, 0, 0), 1.0), lambda: sc.sphere(m, (0, 0, 0), 0.0), lambda: sc.sphere(m, (0, 0, 0), inf),
+        lambda: sc.moving_sphere(m, (0, 0, 0), (0, 1, 0), 0.5, 0.5, 1.0), lambda: sc.moving_sphere(m, (0, 0, 0), (0, nan, 0), 0.0, 1.0, 1.0),
+        lambda: sc.xy_rect(m, 0, 1, 0, nan, 0), lambda: sc.xz_rect(m, 0, inf, 0, 1, 0), lambda: sc.yz_rect(m, 0, 1, 0, 1, nan),
+        lambda: sc.box((0, 0, 0), (1, nan, 1), m), lambda: sc.translate(s0, (0, inf, 0)), lambda: sc.rotate_y(nan, s0),
+        lambda: sc.rotate_y_sincos(nan, 1.0, s0),
+        lambda: sc.constant_medium(s0, 0.0, m), lambda: sc.constant_medium(s0, nan, m),
+        lambda: sc.sphere_batch(np.array([m, m], np.int32), np.array([[0, 0, 0], [0, nan, 0]], float), np.array([1.0, 1.0])),
+        lambda: sc.sphere_batch(np.array([m], np.int32), np.array([[0, 0, 0]], float), np.array([0.0])),
+        lambda: rtw.camera_new((0, 0, 0), (0, 0, 0), (0, 1, 0), 20.0, 1.5, 0.1, 10.0),           # look_from == look_at
+        lambda: rtw.camera_new((0, 0, 1), (0, 0, 0), (0, 0, 1), 20.0, 1.5, 0.1, 10.0),           # vup parallel to the view axis
+        lambda: rtw.camera_new((0, 0, 1), (0, 0, 0), (0, 1, 0), nan, 1.5, 0.1, 10.0),
+    ]
+    for i, fn in enumerate(bad):
+        with pytest.raises(pkg.RtwError) as e:
+            fn()
+        assert e.value.code == -1, i
+    # negative radius stays legal (the hollow-glass trick of the book), and nothing above was added to the scene
+    sc.sphere(sc.dielectric(1.5), (0, 1, 0), -0.9)
+    sc.push(s0)
+    assert sc.debug_flatten()["prims"] == 1
+
+
+def test_rotate_y_sincos_equals_rotate_y(pkg, rtw):
+    """new_rotate_y stores sin/cos of the angle (src/hittable.rs:147-152); a host holding a built RotateY passes them on."""
+    import math
+    out = []
+    for how in ("deg", "sincos"):
+        sc = pkg.Scene(rtw)
+        b = sc.box((0, 0, 0), (1, 2, 3), sc.lambertian(sc.tex_solid((1, 1, 1))))
+        r = math.radians(15.0)
+        sc.push(sc.translate(sc.rotate_y(15.0, b) if how == "deg" else sc.rotate_y_sincos(math.sin(r), math.cos(r), b), (1, 0, 2)))
+        out.append(sc.debug_flatten())
+    assert out[0] == out[1]
+
+
+def test_bvh_node_members_cloned_by_the_reference_builder_are_emitted_once(pkg, rtw):
+    """new_bvh_node puts a single-object span into BOTH children as separate clones (src/hittable.rs:96-98), so a host
+    that walks the built tree hands odd-span leaves over twice.  The flattener drops members that are field-by-field
+    equal to an earlier member of the same BvhNode (nested wrappers included); ConstantMedium members are kept."""
+    def reference_tree(objs):                      # the shape new_bvh_node builds: [left, right] with left == right for one object
+        if len(objs) == 1:
+            return ("node", ("leaf", objs[0]), ("leaf", objs[0]))
+        if len(objs) == 2:
+            return ("node", ("leaf", objs[0]), ("leaf", objs[1]))
+        mid = len(objs) // 2
+        return ("node", reference_tree(objs[:mid]), reference_tree(objs[mid:]))
+
+    def register(sc, m, tree, make):               # every leaf visit builds a NEW hittable = a Rust clone (distinct ids, equal fields)
+        if tree[0] == "leaf":
+            return make(sc, m, tree[1])
+        return sc.bvh_node([register(sc, m, tree[1], make), register(sc, m, tree[2], make)], 0.0, 1.0)
+
+    rs = np.random.RandomState(5)
+    centers = rs.uniform(0, 165, (37, 3))
+    def sphere(sc, m, i):
+        return sc.translate(sc.rotate_y(15.0, sc.sphere(m, tuple(centers[i]), 10.0)), (-100.0, 270.0, 395.0)) if i % 2 else sc.sphere(m, tuple(centers[i]), 10.0)
+    sc = pkg.Scene(rtw)
+    m = sc.lambertian(sc.tex_solid((0.7, 0.7, 0.7)))
+    sc.push(register(sc, m, reference_tree(list(range(37))), sphere))
+    d = sc.debug_flatten()
+    assert d["prims"] == 37 and d["dedup"] > 0, d          # prim count = object count
+    # boxes (six rects each) and moving spheres dedupe the same way; a repeated id counts as a clone too
+    sc = pkg.Scene(rtw)
+    m = sc.lambertian(sc.tex_solid((0.7, 0.7, 0.7)))
+    b1 = sc.box((0, 0, 0), (1, 1, 1), m); b2 = sc.box((0, 0, 0), (1, 1, 1), m); b3 = sc.box((0, 0, 0), (1, 1, 2), m)
+    ms1 = sc.moving_sphere(m, (5, 0, 0), (5, 1, 0), 0.0, 1.0, 0.5); ms2 = sc.moving_sphere(m, (5, 0, 0), (5, 1, 0), 0.0, 1.0, 0.5)
+    sc.push(sc.bvh_node([b1, b2, b3, ms1, ms2, b1], 0.0, 1.0))
+    d = sc.debug_flatten()
+    assert d["prims"] == 6 + 6 + 1 and d["dedup"] == 3, d
+    # world-level repeats are NOT merged (the reference's world list tests both), nor are ConstantMedium members
+    sc = pkg.Scene(rtw)
+    m = sc.lambertian(sc.tex_solid((0.7, 0.7, 0.7))); iso = sc.isotropic(sc.tex_solid((1, 1, 1)))
+    s1 = sc.sphere(m, (0, 0, 0), 1.0)
+    sc.push(s1); sc.push(s1)
+    sc.push(sc.bvh_node([sc.constant_medium(s1, 0.1, iso), sc.constant_medium(s1, 0.1, iso)], 0.0, 1.0))
+    d = sc.debug_flatten()
+    assert d["bvh_prims"] == 2 and d["media"] == 2 and d["dedup"] == 0, d
 
 
 def test_unsupported_nesting_is_reported(pkg, rtw):

@@ -4,7 +4,7 @@ histogram of the ones that diverge.  Usage: diag_paths2.py [scene]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, rtw_pkg
-m = rtw_pkg.load(); rtw, orc = m.load_rtw(), m.api.load_oracle()
+m = rtw_pkg.load(); rtw, orc = m.load_rtw(), __import__("oracle.binding", fromlist=["x"]).load_oracle()
 name = sys.argv[1] if len(sys.argv) > 1 else "cornell_box"
 a, spec = m.scenes.build(rtw, name); a.commit(1, 0)
 b, _ = m.scenes.build(orc, name, wrap_bvh=name not in ("final_scene", "cornell_box_smoke")); b.set_media_deferred(True)

@@ -5,7 +5,8 @@ import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import rtw_pkg
 m = rtw_pkg.load()
-orc = m.api.load_oracle()
+from oracle.binding import load_oracle
+orc = load_oracle()
 
 COST = dict(raygen=52, aabb=27, sphere=24, sphere_accept=34, moving=12, rect=12, rect_accept=21, translate=15, rotate=33,
             medium=25, scatter=[42, 57, 56, 0, 23], tex=[0, 6, 1775, 14], accum=6)

@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import rtw_pkg
 m = rtw_pkg.load()
-orc = m.api.load_oracle()
+from oracle.binding import load_oracle
+orc = load_oracle()
 rs = np.random.RandomState(2024)
 W, H, n, seed = 96, 64, 1500, 7
 px, py, sm = rs.randint(0, W, n), rs.randint(0, H, n), rs.randint(0, 64, n)
