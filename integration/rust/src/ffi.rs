@@ -48,6 +48,7 @@ extern "C" {
     pub fn rtw_box(s: *mut rtw_scene, min: *const c_double, max: *const c_double, mat: c_int) -> c_int;
     pub fn rtw_translate(s: *mut rtw_scene, child: c_int, offset: *const c_double) -> c_int;
     pub fn rtw_rotate_y(s: *mut rtw_scene, angle_deg: c_double, child: c_int) -> c_int;
+    pub fn rtw_rotate_y_sincos(s: *mut rtw_scene, sin_theta: c_double, cos_theta: c_double, child: c_int) -> c_int;
     pub fn rtw_constant_medium(s: *mut rtw_scene, child: c_int, density: c_double, phase_mat: c_int) -> c_int;
     pub fn rtw_bvh_node(s: *mut rtw_scene, children: *const i32, n: i32, t0: c_double, t1: c_double) -> c_int;
     pub fn rtw_world_push(s: *mut rtw_scene, hittable: c_int) -> c_int;

@@ -27,8 +27,8 @@ unsafe fn hit(s: *mut rtw_scene, h: &Hittable) -> i32 {
         Hittable::YZRect { mat_handle, y0, y1, z0, z1, k } => ok(rtw_yz_rect(s, mat_handle.0 as i32, *y0, *y1, *z0, *z1, *k)),
         Hittable::Box { mat_handle, min, max, .. } => ok(rtw_box(s, v(min).as_ptr(), v(max).as_ptr(), mat_handle.0 as i32)),
         Hittable::Translate { offset, ptr } => { let c = hit(s, ptr); ok(rtw_translate(s, c, v(offset).as_ptr())) }
-        Hittable::RotateY { sin_theta, cos_theta, ptr, .. } => {     // new_rotate_y stores sin/cos: recover the angle
-            let c = hit(s, ptr); ok(rtw_rotate_y(s, sin_theta.atan2(*cos_theta).to_degrees(), c))
+        Hittable::RotateY { sin_theta, cos_theta, ptr, .. } => {     // new_rotate_y stores sin/cos (:147-152): passed on unchanged
+            let c = hit(s, ptr); ok(rtw_rotate_y_sincos(s, *sin_theta, *cos_theta, c))
         }
         Hittable::ConstantMedium { phase_function, boundary, neg_inv_density } => {
             let c = hit(s, boundary); ok(rtw_constant_medium(s, c, -1.0 / *neg_inv_density, phase_function.0 as i32))
@@ -39,10 +39,14 @@ unsafe fn hit(s: *mut rtw_scene, h: &Hittable) -> i32 {
         }
     }
 }
+// new_bvh_node puts a single-object span into BOTH children as two separate Box::new(clone) (:96-98), so pointer
+// identity never detects the copy.  The walk registers every leaf it meets; rtw_bvh_node drops members that are
+// field-by-field equal to an earlier member (what #[derive(Clone)] produces), so the backend sees each object once
+// (tests/test_host_abi.py::test_bvh_node_members_cloned_by_the_reference_builder_are_emitted_once walks such a tree).
 unsafe fn collect(s: *mut rtw_scene, h: &Hittable, out: &mut Vec<i32>) {
     if let Hittable::BvhNode { left, right, .. } = h {
         collect(s, left, out);
-        if !std::ptr::eq(&**left, &**right) { collect(s, right, out); }   // single-object leaves are duplicated (:96-98)
+        collect(s, right, out);
     } else { out.push(hit(s, h)); }
 }
 

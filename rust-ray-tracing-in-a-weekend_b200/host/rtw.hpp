@@ -110,8 +110,8 @@ struct Hittable {                                                     // src/hit
     Point3 center, center_1; double radius = 0, time_0 = 0, time_1 = 1;
     double a0 = 0, a1 = 0, b0 = 0, b1 = 0, k = 0;
     Point3 min, max;
-    Vector3 offset; double angle = 0, density = 0;
-    std::vector<Hittable> children;                                   // Box<Hittable> ptr / BvhNode members
+    Vector3 offset; double sin_theta = 0, cos_theta = 1, density = 0;   // RotateY keeps sin / cos, not the angle (:39)
+    std::vector<Hittable> children;                                   // Box<Hittable> ptr; BvhNode: { left, right }
 
     static Hittable Sphere(MaterialHandle m, Point3 c, double r) { Hittable h; h.kind = SphereK; h.mat_handle = m; h.center = c; h.radius = r; return h; }
     static Hittable MovingSphere(MaterialHandle m, Point3 c0, Point3 c1, double t0, double t1, double r) {
@@ -122,13 +122,28 @@ struct Hittable {                                                     // src/hit
     static Hittable YZRect(MaterialHandle m, double y0, double y1, double z0, double z1, double k) { return rect(YZRectK, m, y0, y1, z0, z1, k); }
     static Hittable new_box(Point3 mn, Point3 mx, MaterialHandle m) { Hittable h; h.kind = BoxK; h.mat_handle = m; h.min = mn; h.max = mx; return h; }   // :132-145
     static Hittable Translate(Vector3 offset, Hittable ptr) { Hittable h; h.kind = TranslateK; h.offset = offset; h.children.push_back(std::move(ptr)); return h; }
-    static Hittable new_rotate_y(double angle, Hittable ptr) { Hittable h; h.kind = RotateYK; h.angle = angle; h.children.push_back(std::move(ptr)); return h; }   // :147-199
+    static Hittable new_rotate_y(double angle, Hittable ptr) {                                                                                                      // :147-199
+        Hittable h; h.kind = RotateYK;
+        const double radians = angle * 3.1415926535897932385 / 180.0;           // degrees_to_radians, src/math.rs:8-10
+        h.sin_theta = std::sin(radians); h.cos_theta = std::cos(radians);
+        h.children.push_back(std::move(ptr)); return h;
+    }
     static Hittable new_constant_medium(Hittable boundary, double d, MaterialHandle m) {                                                                            // :201-207
         Hittable h; h.kind = ConstantMediumK; h.density = d; h.mat_handle = m; h.children.push_back(std::move(boundary)); return h;
     }
-    static Hittable new_bvh_node(const std::vector<Hittable>& list, size_t start, size_t end, double t0, double t1) {                                               // :77-130
+    // The SHAPE the reference builds (:77-130): a binary tree of { left, right }; a single-object span is cloned into BOTH
+    // children (:96-98).  The per-node sort (random axis, :82-94, :108-110) only permutes members and is left out: the
+    // backend takes membership from this tree and builds its own BVH (Backend::collect walks it like the Rust shim).
+    static Hittable new_bvh_node(const std::vector<Hittable>& list, size_t start, size_t end, double t0, double t1) {
         Hittable h; h.kind = BvhNodeK; h.time_0 = t0; h.time_1 = t1;
-        h.children.assign(list.begin() + (long)start, list.begin() + (long)end);     // membership; the backend builds its own BVH
+        const size_t span = end - start;
+        if (span == 1) { h.children.push_back(list[start]); h.children.push_back(list[start]); }
+        else if (span == 2) { h.children.push_back(list[start]); h.children.push_back(list[start + 1]); }
+        else {
+            const size_t mid = start + span / 2;
+            h.children.push_back(new_bvh_node(list, start, mid, t0, t1));
+            h.children.push_back(new_bvh_node(list, mid, end, t0, t1));
+        }
         return h;
     }
 private:
@@ -236,14 +251,18 @@ private:
         case Hittable::YZRectK: return ok(rtw_yz_rect(s_, mat, h.a0, h.a1, h.b0, h.b1, h.k));
         case Hittable::BoxK: v3(h.min, a); v3(h.max, b); return ok(rtw_box(s_, a, b, mat));
         case Hittable::TranslateK: { int c = hittable(h.children[0]); v3(h.offset, a); return ok(rtw_translate(s_, c, a)); }
-        case Hittable::RotateYK: { int c = hittable(h.children[0]); return ok(rtw_rotate_y(s_, h.angle, c)); }
+        case Hittable::RotateYK: { int c = hittable(h.children[0]); return ok(rtw_rotate_y_sincos(s_, h.sin_theta, h.cos_theta, c)); }
         case Hittable::ConstantMediumK: { int c = hittable(h.children[0]); return ok(rtw_constant_medium(s_, c, h.density, mat)); }
-        default: {
-            std::vector<int32_t> ids; ids.reserve(h.children.size());
-            for (const Hittable& c : h.children) ids.push_back(hittable(c));
+        default: {      // BvhNode: every leaf of the { left, right } tree, clones included — rtw_bvh_node drops the clones
+            std::vector<int32_t> ids;
+            collect(h, ids);
             return ok(rtw_bvh_node(s_, ids.data(), (int32_t)ids.size(), h.time_0, h.time_1));
         }
         }
+    }
+    void collect(const Hittable& h, std::vector<int32_t>& out) {      // = `collect` of integration/rust/src/gpu.rs
+        if (h.kind == Hittable::BvhNodeK) { collect(h.children[0], out); collect(h.children[1], out); }
+        else out.push_back(hittable(h));
     }
 };
 

@@ -68,16 +68,16 @@ _earth_cache = {}
 
 def earth_texels():
     """RGB8 texels of textures/earthmap.jpg (copied to tests/golden/).  stb_image is replaced by Pillow;
-    both libraries get the same decoded bytes (SURVEY §9 decoder note).  Falls back to a procedural
-    1024x512 map when Pillow or the file is missing, so the scene still has the reference's shape."""
+    both libraries get the same decoded bytes (SURVEY §9 decoder note).  A missing file or decoder is an error:
+    a bench / test input must never silently change the workload."""
     if "e" not in _earth_cache:
         try:
             from PIL import Image
-            _earth_cache["e"] = np.asarray(Image.open(EARTHMAP).convert("RGB"), dtype=np.uint8).copy()
-        except Exception:
-            y, x = np.mgrid[0:512, 0:1024]
-            img = np.stack([(x * 255 // 1023), (y * 255 // 511), ((x ^ y) & 255)], -1).astype(np.uint8)
-            _earth_cache["e"] = img
+        except ImportError as e:
+            raise RuntimeError("scenes.earth_texels: Pillow is needed to decode tests/golden/earthmap.jpg") from e
+        if not os.path.exists(EARTHMAP):
+            raise FileNotFoundError(f"scenes.earth_texels: {EARTHMAP} is missing (the earth / final_scene image texture)")
+        _earth_cache["e"] = np.asarray(Image.open(EARTHMAP).convert("RGB"), dtype=np.uint8).copy()
     return _earth_cache["e"]
 
 
