@@ -112,8 +112,8 @@ def run_reference(args, m):
     line = {"impl": "reference", "metric": "Mpaths/s, 1200x800 500spp depth 50 (book-1 random spheres)", "value": val, "unit": "Mpaths/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": val / README_MPATHS, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"book-1 random_scene (seed 1, 485 spheres) {W}x{H} {SPP}spp depth {DEPTH}", "paths_per_step": W * H * SPP,
-                       "sample": sample + " - each step is a bounded sample of the workload, throughput is spp-independent"},
+            "config": {"workload": f"book-1 random_scene (seed 1, 485 spheres) {W}x{H} {SPP}spp depth {DEPTH}", "paths_per_step": W * H * spp,
+                       "paths_full_workload": W * H * SPP, "sample": sample + " - each step is a bounded sample of the workload, throughput is spp-independent"},
             "cpu_baseline": {"value": val, "unit": "Mpaths/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "extrapolated_full_render_s": W * H * SPP / (val * 1e6)}
@@ -129,6 +129,8 @@ def main():
     ap.add_argument("--impl", default="rtw", choices=["rtw", "reference"])
     ap.add_argument("--spp", type=int, default=SPP, help="debug only; the reported config is 500")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE.json configs (C2-C5) after the headline")
+    ap.add_argument("--sweep", default="1,4,16", help="C5 sphere counts in Mi (comma separated; empty = skip)")
     args = ap.parse_args()
     m = rtw_pkg.load()
     from rtw_b200 import dist
@@ -162,7 +164,8 @@ def main():
         shared = dist.SharedRender(comm, sc, W, H)
         step = lambda: shared.step(cam, prm)                                   # noqa: E731
 
-    for _ in range(max(3, args.warmup)):
+    warmup_run = max(3, args.warmup)                      # never fewer than 3 untimed steps, whatever was asked
+    for _ in range(warmup_run):
         st = step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -216,20 +219,44 @@ def main():
     h2d = comm.reduce_sum(h2d)
     d2h = comm.reduce_sum(d2h)
     e2e_value = n_paths * args.steps / e2e_wall / 1e6
+    # ---------------- A27 check (src/main.rs:542-547): the image all ranks add up over NVLink == one GPU's image ----------
+    mgpu = None
     if world > 1:
+        lo_spp = 32
+        prm_lo = m.make_params(W, H, lo_spp, max_depth=DEPTH, background=spec.background, seed=7, n_gpus=world)
+        shared.step(cam, prm_lo)
+        if rank == 0:
+            img_all = shared.read().copy()
+            img_one, _ = sc.render(cam, m.make_params(W, H, lo_spp, max_depth=DEPTH, background=spec.background, seed=7))
+            diff = float(np.abs(img_all - img_one).max())
+            tol = 2e-4 * float(np.abs(img_one).max())
+            mgpu = {"max_abs_diff": diff, "tol": tol, "ok": bool(diff <= tol and np.isfinite(img_all).all()), "spp": lo_spp,
+                    "what": f"{W}x{H} radiance sums: {world} ranks into rank 0's framebuffer (peer atomics) vs rank 0 alone; f32 summation order is the only difference"}
+        comm.barrier()
         shared.close()
+
+    # ---------------- the other BASELINE.json configs at this N (device-timed, not the headline) -----------------------
+    configs = None
+    if not args.no_configs:
+        configs = run_configs(m, rtw, comm, dist, local_rank, world, args)
 
     if rank == 0:
         peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {})
         model = load_json(os.path.join(ROOT, "profiles", "flop_model.json"), {"configs": {}})
         fpp = model["configs"].get(SCENE, {}).get("flops_per_path", 5960.0)
         sm_max = float(peaks.get("sm_max_mhz", 1965.0))
-        peak_tflops = FP32_LANES * 2 * sm_max * 1e6 / 1e12
+        derived_peak = FP32_LANES * 2 * sm_max * 1e6 / 1e12
+        fp32 = measure_fp32_peak()                                             # tools/fp32_peak: FFMA chains, this GPU, now
+        peak_tflops = fp32["fp32_tflops_measured"] if fp32 else derived_peak
+        peak_source = (f"measured in this run by tools/fp32_peak ({fp32['how']}); derived 148 SM x 128 lanes x 2 x {sm_max:.0f} MHz = {derived_peak:.2f}"
+                       if fp32 else f"DERIVED 148 SM x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock; tools/fp32_peak not built)")
         achieved = fpp * n_paths / world / (kernel_ms * 1e-3) / 1e12          # per GPU, dominant kernel
+        # the same cost table applied to what THIS kernel executes (its own BVH, tile lists): tools/flop_model_device.py
+        fpp_dev = model.get("device_counts", {}).get(SCENE, {}).get("flops_per_path")
         ncu = load_json(os.path.join(ROOT, "profiles", "ncu_summary.json"), {})
         line = {
             "metric": "Mpaths/s, 1200x800 500spp depth 50 (book-1 random spheres)", "value": value, "unit": "Mpaths/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": 1e3 * wall / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "warmup_steps_run": warmup_run, "ms_per_step": 1e3 * wall / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": value / README_MPATHS, "dtype": "f32 (+f64 sphere discriminant)",
             "data": "synthetic",
             "config": {"workload": f"book-1 random_scene (seed 1, 485 spheres) {W}x{H} {spp}spp depth {DEPTH}", "paths_per_step": n_paths,
@@ -238,13 +265,18 @@ def main():
             "wall_time_s": wall / args.steps, "kernel_ms_per_step": kernel_ms, "commit_ms": commit_ms, "rays_per_path": rays / (n_paths * args.steps),
             "mrays_per_s": rays / wall / 1e6,
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": 1e3 * e2e_wall / args.steps, "includes": "scene flatten + BVH build + upload, render, framebuffer D2H"},
+                    "ms_per_step": 1e3 * e2e_wall / args.steps, "includes": "rtw_scene_commit (flatten + BVH build + H2D upload of the scene) + rtw_render (kernel + D2H of the H x W x 3 f32 sums into a pinned host buffer), every step",
+                    "excludes": "building the scene GRAPH (the ~1 400 constructor calls through the C ABI, done once before the loop: host-only bookkeeping, no device work)"},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
                          "traffic": ncu.get("render_kernel", {}).get("dram_bytes_per_launch"),
                          "kernel": "render_kernel", "flops_per_path": fpp,
-                         "peak_source": f"148 SM x 128 lanes x 2 x sm_max_mhz {sm_max:.0f} (MEASURED_PEAKS.json clock; FP32 pipe is the bound, no tensor/HBM-bound work on this path)",
+                         "flops_per_path_is": "REFERENCE-ALGORITHM-EQUIVALENT work (SURVEY 8d): oracle event counts with the world in a reference-style median-split BVH x the reference's f64 op costs (profiles/flop_model.json) - not the instructions this kernel executes",
+                         "frac_device_counts": (fpp_dev * n_paths / world / (kernel_ms * 1e-3) / 1e12 / peak_tflops) if fpp_dev else None,
+                         "flops_per_path_device_counts": fpp_dev,
+                         "peak_source": peak_source + "; FP32 pipe / issue is the bound, no tensor- or HBM-bound work on this path",
+                         "peak_derived_tflops": derived_peak,
                          "hbm_view": {"algorithmic_bytes_per_launch": W * H * 12 + int(sc_blob_bytes(sc)), "peak_gbs": peaks.get("hbm_gbs")}},
         }
         if not args.no_cpu_baseline:
@@ -256,14 +288,93 @@ def main():
                                     "extrapolated_full_render_s": n_paths / (v * 1e6)}
         if host_img is not None:
             line["image_mean"] = float(host_img.mean() / spp)
+        if mgpu is not None:
+            line["multi_gpu_check"] = mgpu
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line))
+    ok = comm.reduce_max(0.0 if (mgpu is None or mgpu["ok"]) else 1.0) == 0.0
     comm.close()
+    if not ok:
+        sys.stderr.write("multi_gpu_check FAILED: the multi-GPU image differs from the single-GPU image\n")
+        return 3
     return 0
+
+
+def run_configs(m, rtw, comm, dist, local_rank, world, args):
+    """BASELINE.json configs[1..4] at the run's N: C2a/b/c 800x450x200, C3a/b/c 600x600x1000, C4 final_scene 800x800 (timed at
+    1000 of its 10 000 spp: Mpaths/s is spp-independent), C5 the 1 M / 4 M / 16 M sphere sweep at 3840x2160x256.
+    Device-timed (CUDA events around the kernel, max over ranks); multi-rank renders go through the same shared-framebuffer
+    path as the headline.  Returns {name: {...}} on rank 0 (other ranks: partial)."""
+    out = {}
+    small = [("C2a two_spheres", "two_spheres", 800, 450, 200), ("C2b two_perlin_spheres", "two_perlin_spheres", 800, 450, 200),
+             ("C2c earth", "earth", 800, 450, 200), ("C3a simple_light", "simple_light", 600, 600, 1000),
+             ("C3b cornell_box", "cornell_box", 600, 600, 1000), ("C3c cornell_box_smoke", "cornell_box_smoke", 600, 600, 1000),
+             ("C4 final_scene (1000 of 10000 spp)", "final_scene", 800, 800, 1000)]
+    sweep = [int(float(x) * (1 << 20)) for x in args.sweep.split(",") if x]
+
+    def timed(sc, spec, Wc, Hc, sppc, reps, warm):
+        cam = spec.camera(rtw, Wc, Hc)
+        prm = m.make_params(Wc, Hc, sppc, max_depth=DEPTH, background=spec.background, seed=1, n_gpus=world)
+        sh = dist.SharedRender(comm, sc, Wc, Hc) if world > 1 else None
+        best, rays, mean = [], 0, None
+        for i in range(warm + reps):
+            if i < warm and sppc > 64:       # a short warm-up pass (same kernel, same scene; fills caches and instruction memory)
+                p_i = m.make_params(Wc, Hc, 16, max_depth=DEPTH, background=spec.background, seed=1, n_gpus=world)
+            else:
+                p_i = prm
+            if sh is None:
+                img, st = sc.render(cam, p_i)
+            else:
+                st = sh.step(cam, p_i)
+            if i >= warm:
+                best.append(comm.reduce_max(st["ms_render"]))
+                rays = comm.reduce_sum(st["rays"])
+        if sh is not None:
+            if comm.rank == 0:
+                mean = float(sh.read().mean() / sppc)
+            sh.close()
+        else:
+            mean = float(img.mean() / sppc)
+        ms = sum(best) / len(best)
+        n = Wc * Hc * sppc
+        return {"mpaths_per_s": n / ms / 1e3, "ms": ms, "rays_per_path": rays / n, "paths": n, "image_mean": mean}
+
+    for label, name, Wc, Hc, sppc in small:
+        sc, spec = m.scenes.build(rtw, name)
+        sc.commit(1, local_rank)
+        out[label] = dict(timed(sc, spec, Wc, Hc, sppc, reps=3, warm=2), workload=f"{name} {Wc}x{Hc} {sppc}spp depth {DEPTH}")
+        sc.close()
+    for n_sph in sweep:
+        sc = m.Scene(rtw)
+        t0 = time.perf_counter()
+        spec = m.scenes.sweep_scene(sc, n_sph)
+        t1 = time.perf_counter()
+        sc.commit(1, local_rank)
+        commit_s = comm.reduce_max(time.perf_counter() - t1)
+        r = timed(sc, spec, 3840, 2160, 256, reps=1, warm=1)
+        st = sc.debug_stats() if hasattr(sc, "debug_stats") else {}
+        out[f"C5 sweep {n_sph >> 20}M spheres"] = dict(r, workload=f"{n_sph} random spheres 3840x2160 256spp depth {DEPTH}", commit_s=commit_s,
+                                                       scene_build_host_s=t1 - t0, **st)
+        sc.close()
+    return out
+
+
+def measure_fp32_peak():
+    exe = os.path.join(ROOT, "tools", "fp32_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return d if r.returncode == 0 and d.get("fp32_tflops_measured", 0) > 1 else None
+    except Exception:
+        return None
 
 
 def sc_blob_bytes(sc):
     d = sc.debug_flatten()
-    return d["nodes"] * 64 + d["prims"] * 80 + d["xforms"] * 160 + d["media"] * 16 + d["mats"] * 32 + d["texs"] * 48
+    return d["nodes"] * 64 + d["prims"] * 64 + d["xforms"] * 160 + d["media"] * 16 + d["mats"] * 32 + d["texs"] * 48
 
 
 if __name__ == "__main__":

@@ -12,7 +12,7 @@ import zlib
 import numpy as np
 import pytest
 
-from conftest import f32, q24
+from conftest import f32, q24, record
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,7 +56,8 @@ def stable(oracle_hit, o, d, tm, scale, **kw):
     return base, ok
 
 
-def compare_hits(ha, hb, ok, pos_scale, d_len, min_stable=0.9, check_uv=True):
+def compare_hits(ha, hb, ok, pos_scale, d_len, min_stable=0.9, check_uv=True, tag=""):
+    record("compare_hits", tag=tag or os.environ.get("PYTEST_CURRENT_TEST", ""), stable=ok.mean(), flag_mismatch_all=np.mean(ha["hit"] != hb["hit"]))
     assert ok.mean() >= min_stable, ok.mean()
     assert np.array_equal(ha["hit"][ok], hb["hit"][ok])
     # over ALL rays (ill-conditioned included) the flags may differ only rarely
@@ -352,6 +353,7 @@ def test_texture_value(pkg, gpu, orc, kind):
     else:
         # marble = 0.5 (1 + sin(scale z + 10 turb)): f32 evaluation of a 7-octave sum feeding a sine of slope 10
         err = np.abs(ga - gb).max(1)
+        record("noise_texture", kind=kind, p999=np.percentile(err, 99.9), max=err.max())
         assert np.percentile(err, 99.9) <= 2 * REL and err.max() <= 1e-4, (np.percentile(err, 99.9), err.max())
 
 
@@ -372,6 +374,7 @@ def test_paths_match_oracle_and_golden(pkg, gpu, orc, name):
     ra, sa = a.trace_paths(spec.camera(gpu, W, H), p, g["px"], g["py"], g["sample"])
     rb, sb = g[name + "_rgb"], g[name + "_seg"]
     good = (sa == sb) & (np.abs(ra - rb).max(1) <= 1e-3 * np.maximum(1.0, np.abs(rb).max(1)))
+    record("paths_golden", name=name, match=good.mean())
     assert good.mean() >= PATH_BARS[name], good.mean()
     # a bigger live sample
     rs = np.random.RandomState(12)
@@ -380,6 +383,7 @@ def test_paths_match_oracle_and_golden(pkg, gpu, orc, name):
     ra, sa = a.trace_paths(spec.camera(gpu, W, H), p, px, py, sm)
     rb, sb = b.trace_paths(spec.camera(orc, W, H), p, px, py, sm)
     good = (sa == sb) & (np.abs(ra - rb).max(1) <= 1e-3 * np.maximum(1.0, np.abs(rb).max(1)))
+    record("paths_live", name=name, match=good.mean())
     assert good.mean() >= PATH_BARS[name], good.mean()
     assert np.isfinite(ra).all()
     se = rb.std(0) / math.sqrt(n) * math.sqrt(2 * (1 - good.mean()) + 1e-6)   # only unmatched paths contribute noise
@@ -410,6 +414,7 @@ def test_render_psnr_4096spp(pkg, gpu, orc, name, W, H):
     ref = b.render_oracle(spec.camera(orc, W, H), p, threads=0, sumsq=True)
     assert st["paths"] == W * H * spp and np.isfinite(img).all()
     psnr = _psnr(_display(img.astype(np.float64), spp), _display(ref["sum"], spp))
+    record("psnr_4096", name=name, psnr=psnr)
     assert psnr >= 40.0, psnr
     mean_ref = ref["sum"] / spp
     var = np.maximum(ref["sumsq"] / spp - mean_ref ** 2, 0)
@@ -754,7 +759,118 @@ def test_sweep_scene_parity_and_bulk_api(pkg, gpu, orc):
     good = (sa == sb) & (np.abs(ra - rb).max(1) <= 1e-3 * np.maximum(1.0, np.abs(rb).max(1)))
     # far camera (|o| ~ 2500) and r = 8.4 spheres: a hit point stored in f32 is known to 3e-5, i.e. 4e-6 of a radius, and
     # every specular bounce multiplies that by distance/radius — paths decorrelate after a few bounces (5 rays/path here)
+    record("paths_sweep20k", match=good.mean(), seg_match=np.mean(sa[:2000] == sb[:2000]))
     assert good.mean() >= 0.85, good.mean()
     assert np.mean(sa[:2000] == sb[:2000]) > 0.85
     se = rb.std(0) / math.sqrt(n) * math.sqrt(2 * (1 - good.mean()))
     assert (np.abs(ra.mean(0) - rb.mean(0)) <= 5 * se + 1e-4).all()
+
+
+def test_aabb_axis_parallel_rays(pkg, gpu, orc):
+    """AABB::hit (src/aabb.rs:77-103) with direction components of exactly +-0: 1/d is +-inf in the reference, which
+    its min/max handle; the f32 slab test replaces such a component by +-1e-30 and must never cull a box the reference
+    hits — in particular boxes that STRADDLE 0 on that axis while the origin is inside the slab (inf - inf = NaN before
+    the fix)."""
+    rs = np.random.RandomState(17)
+    n = 60000
+    bmin = f32(rs.uniform(-3, 0, (n, 3))); bmax = f32(bmin + rs.uniform(0.1, 4, (n, 3)))
+    o = f32(rs.uniform(-4, 4, (n, 3)))
+    d = f32(rs.randn(n, 3))
+    zero = rs.randint(0, 7, n)                       # bit mask of components forced to +-0 (never all three)
+    for k in range(3):
+        m = (zero >> k) & 1 == 1
+        d[m, k] = np.where(rs.rand(m.sum()) < 0.5, 0.0, -0.0)
+    d[np.all(d == 0, axis=1), 0] = 1.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        hb = orc.test_aabb(bmin, bmax, o, d, 0.001, 1e30)
+    ha = gpu.test_aabb(bmin, bmax, o, d, 0.001, 1e30)
+    assert hb.mean() > 0.05
+    assert (ha[hb == 1] == 1).all(), np.mean(ha[hb == 1] == 0)          # conservative: every reference hit is kept
+    assert np.mean(ha != hb) < 2e-3                                      # and (almost) nothing else gets through
+    # the advisor's case: o = 0.5, d = 0 on x, box [-1, 1]
+    ha = gpu.test_aabb([[-1, -1, -1]], [[1, 1, 1]], [[0.5, 0.0, -5.0]], [[0.0, 0.0, 1.0]], 0.001, 1e30)
+    assert ha[0] == 1
+
+
+def test_world_hit_axis_parallel_rays(pkg, gpu, orc):
+    """The same through the whole traversal: axis-parallel rays into cornell_box (rects, rotated boxes) and the book-1
+    scene hit what the oracle hits."""
+    for name in ("cornell_box", "random_scene"):
+        a, b, spec = build_both(pkg, gpu, orc, name)
+        rs = np.random.RandomState(23)
+        n = 20000
+        lo, hi = (np.array([1.0, 1.0, -700.0]), np.array([554.0, 554.0, 554.0])) if name == "cornell_box" else (np.array([-11.0, 0.05, -11.0]), np.array([11.0, 3.0, 11.0]))
+        o = f32(rs.uniform(lo, hi, (n, 3)))
+        axis = rs.randint(0, 3, n)
+        d = np.zeros((n, 3)); d[np.arange(n), axis] = np.where(rs.rand(n) < 0.5, 1.0, -1.0) * rs.uniform(0.5, 2.0, n)
+        d = f32(d)
+        hb, ok = stable(lambda oo, dd, tt: b.test_hit(-1, oo, dd, tt), o, d, np.zeros(n), float(np.abs(hi).max()))
+        # (the perturbation inside `stable` keeps the zero components zero: it is multiplicative on d)
+        ha = a.test_hit(-1, o, d, np.zeros(n))
+        compare_hits(ha, hb, ok, float(np.abs(hi).max()), np.linalg.norm(d, axis=1), min_stable=0.8, check_uv=False)
+
+
+def test_constant_medium_with_sphere_list_boundary(pkg, gpu, orc):
+    """hit_constant_medium (src/hittable.rs:417-473) whose boundary is a BvhNode of spheres: the second probe
+    boundary.hit(t1 + 0.0001, inf) must be able to return a sphere's FAR crossing."""
+    out = []
+    for lib in (gpu, orc):
+        sc = pkg.Scene(lib)
+        iso = sc.isotropic(sc.tex_solid((0.9, 0.9, 0.9)))
+        dummy = sc.lambertian(sc.tex_solid((0.5, 0.5, 0.5)))
+        members = [sc.sphere(dummy, (0.0, 0.0, 0.0), 2.0), sc.sphere(dummy, (5.0, 0.5, 0.0), 1.5), sc.sphere(dummy, (-4.0, 0.0, 1.0), 1.0)]
+        sc.push(sc.constant_medium(sc.bvh_node(members, 0.0, 1.0), 0.8, iso))
+        if lib is gpu:
+            sc.commit(1, 0)
+        else:
+            sc.set_media_deferred(True)
+        out.append(sc)
+    a, b = out
+    rs = np.random.RandomState(31)
+    n = 80000
+    o = f32(rs.uniform(-9, 9, (n, 3)))
+    tgt = rs.uniform(-5, 6, (n, 3)) * np.array([1.0, 0.3, 0.3])
+    d = f32((tgt - o) * rs.uniform(0.1, 1.5, (n, 1)))
+    xi = q24(rs, (n, 4)); xi[xi == 0] = 0.5
+    hb, ok = stable(lambda oo, dd, tt: b.test_hit(-1, oo, dd, tt, xi=xi), o, d, np.zeros(n), 10.0)
+    ha = a.test_hit(-1, o, d, np.zeros(n), xi=xi)
+    assert hb["hit"].mean() > 0.1                       # the media really scatter
+    assert np.array_equal(ha["ndraw"][ok], hb["ndraw"][ok])
+    compare_hits(ha, hb, ok, 10.0, np.linalg.norm(d, axis=1), min_stable=0.8, check_uv=False)
+
+
+def test_shutter_outside_moving_sphere_interval_is_refused(pkg, gpu):
+    """MovingSphere boxes in the BVH span the sphere's own [time0, time1] (like the reference's BvhNode boxes,
+    src/hittable.rs:480-482); a camera shutter beyond it is refused instead of silently culling."""
+    sc = pkg.Scene(gpu)
+    m = sc.lambertian(sc.tex_solid((0.5, 0.5, 0.5)))
+    sc.push(sc.moving_sphere(m, (0, 0, 0), (0, 1, 0), 0.0, 1.0, 0.5))
+    sc.commit(1, 0)
+    p = pkg.make_params(16, 16, 1)
+    ok_cam = gpu.camera_new((0, 0, 5), (0, 0, 0), (0, 1, 0), 40.0, 1.0, 0.0, 5.0, 0.25, 0.75)
+    sc.render(ok_cam, p)
+    bad_cam = gpu.camera_new((0, 0, 5), (0, 0, 0), (0, 1, 0), 40.0, 1.0, 0.0, 5.0, 0.0, 2.0)
+    with pytest.raises(pkg.RtwError) as e:
+        sc.render(bad_cam, p)
+    assert e.value.code == -1
+
+
+def test_concurrent_renders_with_different_seeds(pkg, gpu):
+    """The Philox key schedule travels in the kernel parameters: two host threads rendering two scene handles with
+    different seeds at the same time get exactly the images they get one after the other (no shared launch state)."""
+    import threading
+    jobs = []
+    for seed in (11, 22):
+        sc, spec = pkg.scenes.build(gpu, "random_scene")
+        sc.commit(1, 0)
+        jobs.append((sc, spec.camera(gpu, 96, 64), pkg.make_params(96, 64, 64, background=spec.background, seed=seed)))
+    serial = [sc.render(cam, p)[0].copy() for sc, cam, p in jobs]
+    for _ in range(3):
+        res = [None, None]
+        def run(i):
+            res[i] = jobs[i][0].render(jobs[i][1], jobs[i][2])[0].copy()
+        th = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+        [t.start() for t in th]; [t.join() for t in th]
+        for i in range(2):
+            assert np.abs(res[i] - serial[i]).max() <= 2e-4 * np.abs(serial[i]).max()
+    assert not np.array_equal(serial[0], serial[1])
