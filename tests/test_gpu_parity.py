@@ -56,7 +56,7 @@ def stable(oracle_hit, o, d, tm, scale, **kw):
     return base, ok
 
 
-def compare_hits(ha, hb, ok, pos_scale, d_len, min_stable=0.9, check_uv=True, tag=""):
+def compare_hits(ha, hb, ok, pos_scale, d_len, min_stable=0.99, check_uv=True, tag=""):
     record("compare_hits", tag=tag or os.environ.get("PYTEST_CURRENT_TEST", ""), stable=ok.mean(), flag_mismatch_all=np.mean(ha["hit"] != hb["hit"]))
     assert ok.mean() >= min_stable, ok.mean()
     assert np.array_equal(ha["hit"][ok], hb["hit"][ok])
@@ -205,7 +205,7 @@ def test_hit_range_edges(pkg, gpu, orc):
     d = f32(rs.randn(n, 3))
     hb, ok = stable(lambda oo, dd, tt: b.test_hit(b.target, oo, dd, tt), o, d, np.zeros(n), 1.0)
     ha = a.test_hit(a.target, o, d, np.zeros(n))
-    compare_hits(ha, hb, ok, 2.0, np.linalg.norm(d, axis=1), min_stable=0.8)
+    compare_hits(ha, hb, ok, 2.0, np.linalg.norm(d, axis=1), min_stable=0.97)        # measured 0.9806 (origins ON the sphere)
     inward = np.einsum("ij,ij->i", d, o - np.array([0, 1.0, 0])) < -0.2 * np.linalg.norm(d, axis=1)
     assert (ha["hit"][inward] == 1).all() and (ha["front"][inward] == 0).all()      # exits through the far side
     # finite t_max clips
@@ -257,7 +257,7 @@ def test_world_bvh_hit(pkg, gpu, orc, name):
     o2, d2, tm2, xi2 = o2[keep], d2[keep], tm2[keep], xi2[keep]
     hb2, ok2 = stable(lambda oo, dd, tt: b.test_hit(-1, oo, dd, tt, xi=xi2), o2, d2, tm2, scale)
     ha2 = a.test_hit(-1, o2, d2, tm2, xi=xi2)
-    compare_hits(ha2, hb2, ok2, scale, np.linalg.norm(d2, axis=1), min_stable=0.8, check_uv=name in ("earth", "final_scene"))
+    compare_hits(ha2, hb2, ok2, scale, np.linalg.norm(d2, axis=1), min_stable=SECONDARY_STABLE[name], check_uv=name in ("earth", "final_scene"))
 
 
 # --------------------------------------------------------------------------------------------- materials / textures
@@ -351,15 +351,21 @@ def test_texture_value(pkg, gpu, orc, kind):
         ok = (np.abs(uu - np.round(uu)) > 1e-3) & (np.abs(vv - np.round(vv)) > 1e-3)
         assert np.abs(ga[ok] - gb[ok]).max() <= 1e-7 and np.mean(np.any(np.abs(ga - gb) > 1e-7, axis=1)) < 1e-3
     else:
-        # marble = 0.5 (1 + sin(scale z + 10 turb)): f32 evaluation of a 7-octave sum feeding a sine of slope 10
+        # marble = 0.5 (1 + sin(scale z + 10 turb)): f32 noise values, octave sum and phase in f64 — the north-star 1e-5 holds for every point
         err = np.abs(ga - gb).max(1)
         record("noise_texture", kind=kind, p999=np.percentile(err, 99.9), max=err.max())
-        assert np.percentile(err, 99.9) <= 2 * REL and err.max() <= 1e-4, (np.percentile(err, 99.9), err.max())
+        assert err.max() <= REL, (np.percentile(err, 99.9), err.max())          # measured max 9.3e-7 (f64 octave sum + phase)
 
 
 # --------------------------------------------------------------------------------------------- whole paths
-PATH_BARS = dict(random_scene=0.995, two_spheres=0.995, two_perlin_spheres=0.995, earth=0.999, simple_light=0.995,
-                 cornell_box=0.98, cornell_box_smoke=0.97, final_scene=0.90)
+# fraction of paths whose segment count and radiance match the oracle's; measured on the B200 (round 2, profiles/
+# r2_parity_measured.jsonl): 0.9995 / 1.0 / 0.9993 / 0.99997 / 1.0 / 0.9993 / 0.99998 / 0.9973 — the bars sit just under
+PATH_BARS = dict(random_scene=0.996, two_spheres=0.997, two_perlin_spheres=0.996, earth=0.997, simple_light=0.997,
+                 cornell_box=0.996, cornell_box_smoke=0.997, final_scene=0.993)
+# fraction of SECONDARY rays whose oracle answer is stable under a 1e-6 input perturbation (measured 0.9905 / 0.9974 /
+# 0.9966 / 0.9979 / 0.9934 / 0.8311 / 0.9143: rays that leave a wall of the Cornell box graze the other walls' edges)
+SECONDARY_STABLE = dict(random_scene=0.98, two_spheres=0.99, two_perlin_spheres=0.99, earth=0.99, simple_light=0.985,
+                        cornell_box=0.82, final_scene=0.90)
 
 
 @pytest.mark.parametrize("name", list(PATH_BARS))
@@ -760,8 +766,8 @@ def test_sweep_scene_parity_and_bulk_api(pkg, gpu, orc):
     # far camera (|o| ~ 2500) and r = 8.4 spheres: a hit point stored in f32 is known to 3e-5, i.e. 4e-6 of a radius, and
     # every specular bounce multiplies that by distance/radius — paths decorrelate after a few bounces (5 rays/path here)
     record("paths_sweep20k", match=good.mean(), seg_match=np.mean(sa[:2000] == sb[:2000]))
-    assert good.mean() >= 0.85, good.mean()
-    assert np.mean(sa[:2000] == sb[:2000]) > 0.85
+    assert good.mean() >= 0.90, good.mean()                                     # measured 0.915 / 0.9185
+    assert np.mean(sa[:2000] == sb[:2000]) > 0.90
     se = rb.std(0) / math.sqrt(n) * math.sqrt(2 * (1 - good.mean()))
     assert (np.abs(ra.mean(0) - rb.mean(0)) <= 5 * se + 1e-4).all()
 
@@ -807,7 +813,7 @@ def test_world_hit_axis_parallel_rays(pkg, gpu, orc):
         hb, ok = stable(lambda oo, dd, tt: b.test_hit(-1, oo, dd, tt), o, d, np.zeros(n), float(np.abs(hi).max()))
         # (the perturbation inside `stable` keeps the zero components zero: it is multiplicative on d)
         ha = a.test_hit(-1, o, d, np.zeros(n))
-        compare_hits(ha, hb, ok, float(np.abs(hi).max()), np.linalg.norm(d, axis=1), min_stable=0.8, check_uv=False)
+        compare_hits(ha, hb, ok, float(np.abs(hi).max()), np.linalg.norm(d, axis=1), min_stable=0.985, check_uv=False)   # measured 0.998 / 0.995
 
 
 def test_constant_medium_with_sphere_list_boundary(pkg, gpu, orc):
@@ -836,7 +842,7 @@ def test_constant_medium_with_sphere_list_boundary(pkg, gpu, orc):
     ha = a.test_hit(-1, o, d, np.zeros(n), xi=xi)
     assert hb["hit"].mean() > 0.1                       # the media really scatter
     assert np.array_equal(ha["ndraw"][ok], hb["ndraw"][ok])
-    compare_hits(ha, hb, ok, 10.0, np.linalg.norm(d, axis=1), min_stable=0.8, check_uv=False)
+    compare_hits(ha, hb, ok, 10.0, np.linalg.norm(d, axis=1), check_uv=False)
 
 
 def test_shutter_outside_moving_sphere_interval_is_refused(pkg, gpu):
