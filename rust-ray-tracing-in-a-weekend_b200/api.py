@@ -180,6 +180,7 @@ class Lib:
         f("host_free").restype = None
         f("debug_flatten").argtypes = [vp, ip, dp]
         f("debug_flatten2").argtypes = [vp, ip, dp]
+        f("debug_wide").argtypes = [vp, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64)]
         f("rotate_y_sincos").argtypes = [vp, C.c_double, C.c_double, C.c_int]
         f("rotate_y_sincos").restype = C.c_int
 
@@ -371,10 +372,18 @@ class Scene:
         counts = np.zeros(16, np.int32)
         sah = C.c_double(0)
         self._c("debug_flatten2", _p(counts, C.c_int32), C.byref(sah))
-        keys = ("prims", "bvh_prims", "nodes", "xforms", "media", "mats", "texs", "depth", "dedup")
+        keys = ("prims", "bvh_prims", "nodes", "xforms", "media", "mats", "texs", "depth", "dedup", "bvh_width", "wide_depth")
         d = dict(zip(keys, (int(x) for x in counts)))
         d["sah"] = sah.value
         return d
+
+    def debug_wide(self, n_rays=2000, seed=1):
+        """Host-only: build the 8-wide compressed BVH, validate it, and run the quantised traversal on the CPU (the
+        device's arithmetic) against exact box tests.  Raises when a primitive box is missed."""
+        out = np.zeros(8, np.uint64)
+        self._c("debug_wide", n_rays, seed, _p(out, C.c_uint64))
+        keys = ("rays", "node_visits", "leaves_reached", "boxes_crossed", "missed", "wide_nodes", "wide_depth", "bvh_prims")
+        return dict(zip(keys, (int(x) for x in out)))
 
     def render(self, cam, params, out=None):
         """rtw_render: per-pixel radiance SUM, H x W x 3 float32, row 0 = top.  Returns (image, stats dict)."""

@@ -49,7 +49,7 @@ extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
 #define RTW_MIN_BLOCKS 7
 #endif
 
-template <int F>
+template <int F, int W>
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
 render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
@@ -77,8 +77,9 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
         const int n_items = prm.max_depth >= 1 ? npix * (s1 - s0) : 0;
         acc[warp][lane] = 0.f; acc[warp][lane + 32] = 0.f; acc[warp][lane + 64] = 0.f;
         // every primitive a primary ray of this tile can touch (-1: too many, traverse instead)
-        const int list_n = prm.no_tile_cull ? -1 : build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp],
-                                                                   reinterpret_cast<int*>(ring[warp][0]), lane);
+        const int list_n = prm.no_tile_cull ? -1
+                           : W ? build_tile_list_wide(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], reinterpret_cast<int*>(ring[warp][0]), lane)
+                               : build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], reinterpret_cast<int*>(ring[warp][0]), lane);
         __syncwarp();
         if (lane == 0) { if (list_n >= 0) atomicAdd(stats + 2, (unsigned long long)list_n); else atomicAdd(stats + 3, 1ull); }
         int next = 0, pix = 0;
@@ -162,9 +163,9 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
                     }
                 } else {
 #ifdef RTW_INSTRUMENT
-                    bvh_closest<F>(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, dbg_v, dbg_p);
+                    closest_hit<F, W>(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, dbg_v, dbg_p);
 #else
-                    bvh_closest<F>(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);
+                    closest_hit<F, W>(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);
 #endif
                 }
             }
@@ -473,7 +474,7 @@ void free_replicas(rtw_scene* s) {
 }
 
 // pack FlatScene into one host blob; offsets -> DScene (device pointers filled per replica)
-struct Packed { std::vector<uint8_t> bytes; size_t total = 0, o_nodes, o_prims, o_xf, o_media, o_mats, o_texs, o_perlin, o_image; };
+struct Packed { std::vector<uint8_t> bytes; size_t total = 0, o_nodes, o_wnodes, o_prims, o_xf, o_media, o_mats, o_texs, o_perlin, o_image; };
 // Up to this size the scene is staged in one host blob and uploaded with ONE copy (C1: 100 KB, latency matters);
 // beyond it (the 1 M - 16 M sphere sweep: 0.15 - 2.4 GB) zero-filling and filling a second host copy costs ~1 s.
 static const size_t kBlobStageLimit = 64u << 20;
@@ -481,6 +482,7 @@ void pack(const rtw::FlatScene& f, Packed& p) {
     size_t off = 0;
     auto place = [&](size_t n) { size_t o = off; off = align_up(off + std::max<size_t>(n, 16), 256); return o; };
     p.o_nodes = place(f.nodes.size() * sizeof(DNode));
+    p.o_wnodes = place(f.wnodes.size() * sizeof(DWNode));
     p.o_prims = place(f.prims.size() * sizeof(DPrim));
     p.o_xf = place(f.xforms.size() * sizeof(DXform));
     p.o_media = place(f.media.size() * sizeof(DMedium));
@@ -493,6 +495,7 @@ void pack(const rtw::FlatScene& f, Packed& p) {
     p.bytes.assign(off, 0);
     auto cp = [&](size_t o, const void* src, size_t n) { if (n) std::memcpy(p.bytes.data() + o, src, n); };
     cp(p.o_nodes, f.nodes.data(), f.nodes.size() * sizeof(DNode));
+    cp(p.o_wnodes, f.wnodes.data(), f.wnodes.size() * sizeof(DWNode));
     cp(p.o_prims, f.prims.data(), f.prims.size() * sizeof(DPrim));
     cp(p.o_xf, f.xforms.data(), f.xforms.size() * sizeof(DXform));
     cp(p.o_media, f.media.data(), f.media.size() * sizeof(DMedium));
@@ -506,6 +509,7 @@ cudaError_t upload(const rtw::FlatScene& f, const Packed& p, uint8_t* dst, cudaS
     cudaError_t e = cudaSuccess;
     auto cp = [&](size_t o, const void* src, size_t n) { if (n && e == cudaSuccess) e = cudaMemcpyAsync(dst + o, src, n, cudaMemcpyHostToDevice, st); };
     cp(p.o_nodes, f.nodes.data(), f.nodes.size() * sizeof(DNode));
+    cp(p.o_wnodes, f.wnodes.data(), f.wnodes.size() * sizeof(DWNode));
     cp(p.o_prims, f.prims.data(), f.prims.size() * sizeof(DPrim));
     cp(p.o_xf, f.xforms.data(), f.xforms.size() * sizeof(DXform));
     cp(p.o_media, f.media.data(), f.media.size() * sizeof(DMedium));
@@ -517,7 +521,8 @@ cudaError_t upload(const rtw::FlatScene& f, const Packed& p, uint8_t* dst, cudaS
 }
 DScene bind(const rtw::FlatScene& f, const Packed& p, uint8_t* base) {
     DScene d;
-    d.nodes = reinterpret_cast<const DNode*>(base + p.o_nodes);
+    d.nodes = f.wide ? nullptr : reinterpret_cast<const DNode*>(base + p.o_nodes);
+    d.wnodes = f.wide ? reinterpret_cast<const DWNode*>(base + p.o_wnodes) : nullptr;
     d.prims = reinterpret_cast<const DPrim*>(base + p.o_prims);
     d.xforms = reinterpret_cast<const DXform*>(base + p.o_xf);
     d.media = reinterpret_cast<const DMedium*>(base + p.o_media);
@@ -651,6 +656,7 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         CUDA_TRY(cudaMemsetAsync(r.stats, 0, 32, r.stream));
         CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
         if (mode >= 1 && dp.first_sample + dp.spp > (1 << 17)) return fail(RTW_ERR_INVALID_ARG, "the pool kernel packs the sample index into 17 bits: spp <= 131072");
+        if (mode >= 1 && s->flat.wide) return fail(RTW_ERR_INVALID_ARG, "the pool kernel traverses binary nodes only (RTW_BVH=2)");
         if (mode >= 1 && s->flat.media.size() > 15) return fail(RTW_ERR_INVALID_ARG, "the pool kernel packs the media draw count into 4 bits: at most 15 media");
         switch (mode) {
         case 1: TRY(launch_pool<64>(r, 0, dc, dp, counter, fb)); break;
@@ -660,7 +666,10 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         default: {
             // smallest kernel variant that covers the scene's features (code size = instruction-cache pressure)
             const int f = s->flat.features;
-#define RTW_TRY_VARIANT(V) if ((f & ~(V)) == 0) { render_kernel<V><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); break; }
+#define RTW_TRY_VARIANT(V) if ((f & ~(V)) == 0) { \
+                if (s->flat.wide) render_kernel<V, 1><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); \
+                else render_kernel<V, 0><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); \
+                break; }
             RTW_TRY_VARIANT(0)                                         // spheres, solid / checker         (C1, two_spheres)
             RTW_TRY_VARIANT(FEAT_NOISE)                                // + Perlin                         (two_perlin_spheres)
             RTW_TRY_VARIANT(FEAT_IMAGE)                                // + image                          (earth)
@@ -693,7 +702,7 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
 }
 
 void fill_scene_stats(rtw_scene* s, rtw_stats* st) {
-    st->n_prims = (int)s->flat.prims.size(); st->n_nodes = (int)s->flat.nodes.size();
+    st->n_prims = (int)s->flat.prims.size(); st->n_nodes = (int)(s->flat.wide ? s->flat.wnodes.size() : s->flat.nodes.size());
     st->n_materials = (int)s->flat.mats.size(); st->n_media = (int)s->flat.media.size();
     st->ms_commit = s->ms_commit;
 }
@@ -953,7 +962,7 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
             CUDA_TRY(cudaMalloc(&r.stats, 32));
             int sms = 0, per_sm = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FEAT_ALL>, RTW_BLOCK, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FEAT_ALL, 0>, RTW_BLOCK, 0));
             if (per_sm < 1) per_sm = 1;
             r.grid = sms * per_sm; r.sms = sms;
             for (int k = 0; k < 4; ++k) r.pool_grid[k] = 0;
@@ -1278,12 +1287,30 @@ int rtw_debug_flatten(rtw_scene* s, int32_t* out_counts /* prims, bvh_prims, nod
     rtw::FlatScene f; std::string err;
     int rc = rtw::flatten(s->g, s->g.world, f, err);
     if (rc) return fail(rc, err);
-    if (!rtw::validate_bvh(f, err)) return fail(RTW_ERR_INVALID_ARG, "invalid BVH: " + err);
+    if (!(f.wide ? rtw::validate_wide(f, err) : rtw::validate_bvh(f, err))) return fail(RTW_ERR_INVALID_ARG, "invalid BVH: " + err);
     if (out_counts) {
-        out_counts[0] = (int)f.prims.size(); out_counts[1] = f.n_bvh_prims; out_counts[2] = (int)f.nodes.size(); out_counts[3] = (int)f.xforms.size();
+        out_counts[0] = (int)f.prims.size(); out_counts[1] = f.n_bvh_prims; out_counts[2] = (int)(f.wide ? f.wnodes.size() : f.nodes.size()); out_counts[3] = (int)f.xforms.size();
         out_counts[4] = (int)f.media.size(); out_counts[5] = (int)f.mats.size(); out_counts[6] = (int)f.texs.size(); out_counts[7] = f.max_depth;
     }
     if (out_sah) *out_sah = f.sah_cost;
+    return RTW_OK;
+}
+// Host-only check of the 8-wide compressed BVH (no device needed): flatten with wide nodes, validate the structure, then
+// run `n_rays` seeded rays through the quantised traversal ON THE CPU with the device's arithmetic (bvh_wide.h) and require
+// that it reaches every primitive whose box a ray really crosses.
+// out[8]: rays, node visits, leaves reached, boxes really crossed, boxes MISSED (0), wide nodes, wide depth, bvh prims
+int rtw_debug_wide(rtw_scene* s, int32_t n_rays, uint64_t seed, uint64_t* out) {
+    if (!s || !out || n_rays < 0) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    rtw::FlatScene f; std::string err;
+    rtw::FlattenOptions opt; opt.bvh_width = 8; opt.keep_boxes = true;
+    int rc = rtw::flatten(s->g, s->g.world, f, err, opt);
+    if (rc) return fail(rc, err);
+    if (!rtw::validate_wide(f, err)) return fail(RTW_ERR_INVALID_ARG, "invalid wide BVH: " + err);
+    uint64_t st[5];
+    const bool ok = rtw::check_wide_traversal(f, n_rays, seed, st, err);
+    for (int i = 0; i < 5; ++i) out[i] = st[i];
+    out[5] = f.wnodes.size(); out[6] = (uint64_t)f.wide_depth; out[7] = (uint64_t)f.n_bvh_prims;
+    if (!ok) return fail(RTW_ERR_INVALID_ARG, err);
     return RTW_OK;
 }
 // same, with room to grow: out_counts[16] = the 8 above, [8] BvhNode members dropped as clones of an earlier member
@@ -1292,11 +1319,11 @@ int rtw_debug_flatten2(rtw_scene* s, int32_t* out_counts, double* out_sah) {
     rtw::FlatScene f; std::string err;
     int rc = rtw::flatten(s->g, s->g.world, f, err);
     if (rc) return fail(rc, err);
-    if (!rtw::validate_bvh(f, err)) return fail(RTW_ERR_INVALID_ARG, "invalid BVH: " + err);
+    if (!(f.wide ? rtw::validate_wide(f, err) : rtw::validate_bvh(f, err))) return fail(RTW_ERR_INVALID_ARG, "invalid BVH: " + err);
     std::memset(out_counts, 0, 16 * sizeof(int32_t));
-    out_counts[0] = (int)f.prims.size(); out_counts[1] = f.n_bvh_prims; out_counts[2] = (int)f.nodes.size(); out_counts[3] = (int)f.xforms.size();
+    out_counts[0] = (int)f.prims.size(); out_counts[1] = f.n_bvh_prims; out_counts[2] = (int)(f.wide ? f.wnodes.size() : f.nodes.size()); out_counts[3] = (int)f.xforms.size();
     out_counts[4] = (int)f.media.size(); out_counts[5] = (int)f.mats.size(); out_counts[6] = (int)f.texs.size(); out_counts[7] = f.max_depth;
-    out_counts[8] = f.n_dedup;
+    out_counts[8] = f.n_dedup; out_counts[9] = f.wide ? 8 : 2; out_counts[10] = f.wide_depth;
     if (out_sah) *out_sah = f.sah_cost;
     return RTW_OK;
 }

@@ -414,13 +414,13 @@ RTW_DEV float slab_slack(V3 oi) { return 2.384185791015625e-07f * fmaxf(fmaxf(fa
 // A direction component of exactly +-0 (axis-parallel test rays; 2^-24 of the scatter draws) would give inv = +-inf and
 // plane distances inf - inf = NaN for a box that straddles the origin's coordinate — fmaxf/fminf drop the NaN and the
 // test MISSES a box the ray runs inside of (the reference's AABB::hit handles the infinities, src/aabb.rs:77-103).
-// Such a component is replaced by +-1e-30: every plane distance stays finite, the origin's side of each slab decides.
-// Its o/d (~1e30 |o|) is kept out of the shared slack term, which would otherwise open every box on the other two axes.
-RTW_DEV float slab_dir(float d) { return fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d; }
+// Such a component is replaced by +-1e-20: every plane distance stays finite, the origin's side of each slab decides.
+// Its o/d (~1e20 |o|) is kept out of the shared slack term, which would otherwise open every box on the other two axes.
+RTW_DEV float slab_dir(float d) { return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; }
 RTW_DEV void slab_setup(V3 o, V3 d, V3& inv, V3& oi, float& slack) {
     inv = mk(rcp_approx(slab_dir(d.x)), rcp_approx(slab_dir(d.y)), rcp_approx(slab_dir(d.z)));
     oi = mk(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-    slack = slab_slack(mk(fabsf(d.x) < 1e-30f ? 0.f : oi.x, fabsf(d.y) < 1e-30f ? 0.f : oi.y, fabsf(d.z) < 1e-30f ? 0.f : oi.z));
+    slack = slab_slack(mk(fabsf(d.x) < 1e-20f ? 0.f : oi.x, fabsf(d.y) < 1e-20f ? 0.f : oi.y, fabsf(d.z) < 1e-20f ? 0.f : oi.z));
 }
 RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
     float x0 = fmaf(mnx, inv.x, -oi.x), x1 = fmaf(mxx, inv.x, -oi.x);
@@ -501,6 +501,79 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             if (node < 0) { node = sp[-1]; --sp; }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Closest surface hit over the 8-WIDE COMPRESSED BVH (bvh_wide.h) — scenes that do not fit the caches.
+// One node visit = five 16-byte loads and eight quantised slab tests (rtww::wide_node_hits); the children that pass
+// form a GROUP (base index + slot mask) from which the ray takes the slot with the highest priority  slot ^ (7 ^ octant)
+// (front to back along the ray's octant, no sorting); what is left of the group goes on a stack of 8-byte entries —
+// at most one per level of the tree.  Leaves that pass are intersected right away.
+// ------------------------------------------------------------------------------------------------
+template <int F = FEAT_ALL>
+RTW_DEV void bvh8_closest(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip
+#ifdef RTW_INSTRUMENT
+                          , int& dbg_visits, int& dbg_prims
+#endif
+                          ) {
+    if (sc.n_bvh_prims <= 0) return;
+    V3 inv, oi; rtww::WRay wr;
+    slab_setup(r.o, r.d, inv, oi, wr.slack);
+    wr.ix = inv.x; wr.iy = inv.y; wr.iz = inv.z; wr.oix = oi.x; wr.oiy = oi.y; wr.oiz = oi.z;
+    const uint32_t k = ((inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u)) ^ 7u;
+    wr.k = k;
+    wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31);           // = 0x3F800000, but opaque to the compiler (see WRay::one)
+    uint2 stack[RTW_WIDE_STACK];
+    int sp = 0;
+    uint32_t base = 0, grp = (1u << 8) | (1u << k);          // the root: a group of one inner slot (slot 0)
+    for (;;) {
+        if (!(grp & 0xffu)) {
+            if (sp == 0) break;
+            --sp; base = stack[sp].x; grp = stack[sp].y;
+            continue;
+        }
+        const int j = 31 - __clz(grp & 0xffu);
+        grp ^= 1u << j;
+        const uint32_t slot = (uint32_t)j ^ k;
+        const uint32_t node = base + __popc((grp >> 8) & ((1u << slot) - 1u));
+        if (grp & 0xffu) { stack[sp] = make_uint2(base, grp); ++sp; }
+        RTW_DBG_VISIT();
+        const uint4* np = reinterpret_cast<const uint4*>(sc.wnodes + node);
+        const uint4 h = __ldg(np), m = __ldg(np + 1), qa = __ldg(np + 2), qb = __ldg(np + 3), qc = __ldg(np + 4);
+        const uint32_t imask = h.w >> 24, lmask = m.z & 0xffu;
+        uint32_t hits = rtww::wide_node_hits(*reinterpret_cast<const rtww::W4*>(&h), *reinterpret_cast<const rtww::W4*>(&qa),
+                                             *reinterpret_cast<const rtww::W4*>(&qb), *reinterpret_cast<const rtww::W4*>(&qc), wr, t_min, t_best);
+        hits &= imask | lmask;
+        const uint32_t m16 = rtww::wide_perm16((hits & imask) | ((hits & lmask) << 8), k);
+        uint32_t pl = m16 >> 8;
+        while (pl) {                                          // leaves, nearest octant first
+            const int jj = 31 - __clz(pl);
+            pl ^= 1u << jj;
+            const uint32_t s = (uint32_t)jj ^ k;
+            const int pi = (int)(m.y + __popc(lmask & ((1u << s) - 1u)));
+            RTW_DBG_PRIM();
+            const float t = prim_root<F>(sc, pi, r, t_min, t_best, skip);
+            if (t == t) { t_best = t; prim_best = pi; }
+        }
+        base = m.x; grp = (imask << 8) | (m16 & 0xffu);
+    }
+}
+
+// closest surface hit, whichever BVH the scene was committed with (W: compile-time for the render kernel variants)
+template <int F = FEAT_ALL, int W = -1>
+RTW_DEV void closest_hit(const DScene& sc, const TRay& r, float t_min, float& t_best, int& prim_best, int skip
+#ifdef RTW_INSTRUMENT
+                         , int& dbg_visits, int& dbg_prims
+#endif
+                         ) {
+    const bool wide = W < 0 ? sc.wnodes != nullptr : W != 0;
+#ifdef RTW_INSTRUMENT
+    if (wide) bvh8_closest<F>(sc, r, t_min, t_best, prim_best, skip, dbg_visits, dbg_prims);
+    else bvh_closest<F>(sc, r, t_min, t_best, prim_best, skip, dbg_visits, dbg_prims);
+#else
+    if (wide) bvh8_closest<F>(sc, r, t_min, t_best, prim_best, skip);
+    else bvh_closest<F>(sc, r, t_min, t_best, prim_best, skip);
+#endif
 }
 
 // set_face_normal :23-26
@@ -631,9 +704,9 @@ RTW_DEV bool world_hit(const DScene& sc, const TRay& r, float t_min, float t_max
     float t_best = t_max; int prim_best = -1;
 #ifdef RTW_INSTRUMENT
     int dv = 0, dp = 0;
-    bvh_closest(sc, r, t_min, t_best, prim_best, -1, dv, dp);
+    closest_hit(sc, r, t_min, t_best, prim_best, -1, dv, dp);
 #else
-    bvh_closest(sc, r, t_min, t_best, prim_best, -1);
+    closest_hit(sc, r, t_min, t_best, prim_best, -1);
 #endif
     int med_mat = -1; float med_t = 0.0f;
     for (int m = 0; m < sc.n_media; ++m) {
@@ -844,9 +917,9 @@ RTW_DEV bool path_step(const DScene& sc, const DParams& prm, PathState& ps, V3& 
     TRay tr = make_tray(ps.ray);
     float t_best = CUDART_INF_F; int prim_best = -1;
 #ifdef RTW_INSTRUMENT
-    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, ps.dbg_visits, ps.dbg_prims);
+    closest_hit(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim, ps.dbg_visits, ps.dbg_prims);
 #else
-    bvh_closest(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);                       // :25
+    closest_hit(sc, tr, prm.t_min, t_best, prim_best, ps.last_prim);                       // :25
 #endif
     return path_finish(sc, prm, ps, tr, t_best, prim_best, add);
 }
@@ -947,6 +1020,59 @@ RTW_DEV int build_tile_list(const DScene& sc, const RayBounds& rb, float t_min, 
                         const int code = ~child, first = code >> 3, count = (code & 7) + 1;
                         const int pos = atomicAdd(&cnt[1], count);
                         if (pos + count <= RTW_TILE_LIST) for (int k = 0; k < count; ++k) list[pos + k] = first + k;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        n_front = cnt[0];
+        overflow |= n_front > 64 || cnt[1] > RTW_TILE_LIST;
+        __syncwarp();
+        if (lane == 0) cnt[0] = 0;
+        cur ^= 1;
+        if (overflow) break;
+        __syncwarp();
+    }
+    __syncwarp();
+    const int n = cnt[1];
+    __syncwarp();
+    return overflow ? -1 : n;
+}
+
+// The same walk over the 8-wide compressed BVH: one (node, slot) pair per lane and round; child boxes are decoded from
+// the quantised planes with directed rounding (the decoded box contains the stored one).
+RTW_DEV int build_tile_list_wide(const DScene& sc, const RayBounds& rb, float t_min, int* list, int* scratch, int lane) {
+    if (sc.n_bvh_prims == 0) return 0;
+    int* front[2] = {scratch, scratch + 64};
+    int* cnt = scratch + 128;
+    int cur = 0, n_front = 1;
+    if (lane == 0) { front[0][0] = 0; cnt[0] = 0; cnt[1] = 0; }
+    __syncwarp();
+    bool overflow = false;
+    while (n_front > 0) {
+        const int n_tests = 8 * n_front;
+        for (int b0 = 0; b0 < n_tests; b0 += 32) {
+            const int i = b0 + lane;
+            if (i < n_tests) {
+                const int node = front[cur][i >> 3], s = i & 7;
+                const DWNode* wn = sc.wnodes + node;
+                const uint4 h = __ldg(reinterpret_cast<const uint4*>(wn)), m = __ldg(reinterpret_cast<const uint4*>(wn) + 1);
+                const uint32_t imask = h.w >> 24, lmask = m.z & 0xffu;
+                if (((imask | lmask) >> s) & 1u) {
+                    const uint8_t* q = reinterpret_cast<const uint8_t*>(wn) + 32;
+                    const float sx = __uint_as_float((h.w & 0xffu) << 23), sy = __uint_as_float(((h.w >> 8) & 0xffu) << 23), sz = __uint_as_float(((h.w >> 16) & 0xffu) << 23);
+                    const float px = __uint_as_float(h.x), py = __uint_as_float(h.y), pz = __uint_as_float(h.z);
+                    const float mnx = __fadd_rd(px, (float)__ldg(q + s) * sx), mny = __fadd_rd(py, (float)__ldg(q + 8 + s) * sy), mnz = __fadd_rd(pz, (float)__ldg(q + 16 + s) * sz);
+                    const float mxx = __fadd_ru(px, (float)__ldg(q + 24 + s) * sx), mxy = __fadd_ru(py, (float)__ldg(q + 32 + s) * sy), mxz = __fadd_ru(pz, (float)__ldg(q + 40 + s) * sz);
+                    if (bounds_hit_box(rb, mnx, mxx, mny, mxy, mnz, mxz, t_min)) {
+                        const uint32_t below = (1u << s) - 1u;
+                        if ((imask >> s) & 1u) {
+                            const int pos = atomicAdd(&cnt[0], 1);
+                            if (pos < 64) front[cur ^ 1][pos] = (int)(m.x + __popc(imask & below));
+                        } else {
+                            const int pos = atomicAdd(&cnt[1], 1);
+                            if (pos < RTW_TILE_LIST) list[pos] = (int)(m.y + __popc(lmask & below));
+                        }
                     }
                 }
             }

@@ -15,6 +15,8 @@
 
 #include <stdint.h>
 
+#include "bvh_wide.h"
+
 #if defined(__CUDACC__)
 #define RTW_ALIGN(n) __align__(n)
 #else
@@ -95,7 +97,8 @@ struct RTW_ALIGN(16) DTex {
 #define RTW_PERLIN_BYTES (256 * 16 + 768)   // float4 ranvec[256] + u8 perm_x/y/z[256]
 
 struct DScene {
-    const DNode* nodes;
+    const DNode* nodes;         // binary BVH, or nullptr when the scene uses the wide one
+    const DWNode* wnodes;       // 8-wide compressed BVH (bvh_wide.h), or nullptr
     const DPrim* prims;
     const DXform* xforms;
     const DMedium* media;

@@ -538,7 +538,52 @@ void pack_materials(const SceneGraph& g, FlatScene& out) {
 
 }  // namespace
 
-int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, std::string& err) {
+// ---- BVH2 -> BVH8 on the host (small scenes, CPU tests); the device builder runs the same collapse_one per node ----
+namespace {
+struct HostAlloc {
+    int n_nodes = 1, n_prims = 0, n_queue = 0, max_depth = 0;     // node 0 = root, allocated up front
+    int nodes(int k) { int b = n_nodes; n_nodes += k; return b; }
+    int prims(int k) { int b = n_prims; n_prims += k; return b; }
+    int queue(int k) { int b = n_queue; n_queue += k; return b; }
+    void depth(int d) { if (d > max_depth) max_depth = d; }
+};
+}  // namespace
+
+int collapse_to_wide(const rtww::B2View& v, std::vector<DWNode>& wnodes, std::vector<int>& leaf_order) {
+    leaf_order.assign((size_t)v.n_leaves, -1);
+    wnodes.clear();
+    if (v.n_leaves == 0) return 0;
+    if (v.n_inner == 0) {                   // a single primitive: a root with one leaf slot
+        DWNode w; std::memset(&w, 0, sizeof(w));
+        const float* b = v.box;             // leaf 0 = ref 0
+        float p[3], step[3];
+        w.ex = (uint8_t)rtww::wide_axis_grid(b[0], b[3], p[0], step[0]);
+        w.ey = (uint8_t)rtww::wide_axis_grid(b[1], b[4], p[1], step[1]);
+        w.ez = (uint8_t)rtww::wide_axis_grid(b[2], b[5], p[2], step[2]);
+        w.px = p[0]; w.py = p[1]; w.pz = p[2];
+        for (int s = 0; s < 8; ++s) { w.qlox[s] = w.qloy[s] = w.qloz[s] = 255; w.qhix[s] = w.qhiy[s] = w.qhiz[s] = 0; }
+        w.qlox[0] = rtww::wide_qlo(b[0], p[0], step[0]); w.qhix[0] = rtww::wide_qhi(b[3], p[0], step[0]);
+        w.qloy[0] = rtww::wide_qlo(b[1], p[1], step[1]); w.qhiy[0] = rtww::wide_qhi(b[4], p[1], step[1]);
+        w.qloz[0] = rtww::wide_qlo(b[2], p[2], step[2]); w.qhiz[0] = rtww::wide_qhi(b[5], p[2], step[2]);
+        w.lmask = 1;
+        wnodes.push_back(w); leaf_order[0] = 0;
+        return 1;
+    }
+    wnodes.resize((size_t)v.n_inner);       // upper bound: every wide node consumes at least one binary inner node
+    HostAlloc alloc;
+    std::vector<rtww::WideItem> cur{rtww::WideItem{0, 0, 0}}, next;
+    while (!cur.empty()) {
+        next.assign(cur.size() * 8, rtww::WideItem{0, 0, 0});
+        alloc.n_queue = 0;
+        for (const rtww::WideItem& it : cur) rtww::collapse_one(v, it, wnodes.data(), leaf_order.data(), next.data(), alloc);
+        next.resize((size_t)alloc.n_queue);
+        cur.swap(next);
+    }
+    wnodes.resize((size_t)alloc.n_nodes);
+    return alloc.max_depth;
+}
+
+int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, std::string& err, const FlattenOptions& opt) {
     const bool timing = getenv("RTW_TIMING") != nullptr;
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char* what) { if (timing) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[flatten] %s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
@@ -573,8 +618,19 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
     for (const DMedium& m : out.media) if (m.mat < 0 || m.mat >= (int)out.mats.size()) { err = "phase material handle out of range"; return RTW_ERR_INVALID_ARG; }
     const int n = (int)fl.bvh_prims.size();
     if (n >= (1 << 28)) { err = "too many primitives"; return RTW_ERR_INVALID_ARG; }
+    // node format: binary for scenes that live in the caches, 8-wide compressed beyond (FlattenOptions / RTW_BVH / RTW_WIDE_MIN)
+    int width = opt.bvh_width;
+    if (width == 0) { if (const char* e = getenv("RTW_BVH")) width = atoi(e); }
+    if (width != 2 && width != 8) {
+        int wide_min = kWideMinPrims;
+        if (const char* e = getenv("RTW_WIDE_MIN")) wide_min = std::max(1, atoi(e));
+        width = n >= wide_min ? 8 : 2;
+    }
+    out.wide = width == 8;
     // BVH (RTW_BVH_LEAF / RTW_BVH_CI: tuning overrides for kernel experiments)
+    Builder::MAX_LEAF = 1;
     if (const char* e = getenv("RTW_BVH_LEAF")) Builder::MAX_LEAF = std::max(1, std::min(8, atoi(e)));
+    if (out.wide) Builder::MAX_LEAF = 1;              // a wide leaf slot holds exactly one primitive
     if (const char* e = getenv("RTW_BVH_CI")) Builder::C_ISECT = atof(e);
     Builder b(fl.bvh_boxes);
     DNode root; std::memset(&root, 0, sizeof(root));
@@ -629,6 +685,42 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
     lap("emit nodes");
     out.max_depth = b.max_depth;
     out.n_bvh_prims = n;
+    if (opt.keep_boxes && n > 0) {
+        out.prim_boxes.resize((size_t)n * 6);
+        for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) { out.prim_boxes[(size_t)i * 6 + a] = b.items[i].b.mn[a]; out.prim_boxes[(size_t)i * 6 + 3 + a] = b.items[i].b.mx[a]; }
+    }
+    if (out.wide && n > 0) {
+        // the binary tree as a B2View: inner nodes keep their DNode index, leaf j = position j of the leaf order
+        const size_t nb = b.nodes.size();
+        std::vector<int> inner_of(nb, -1);
+        int n_inner = 0;
+        for (size_t i = 0; i < nb; ++i) if (b.nodes[i].left >= 0) inner_of[i] = n_inner++;
+        std::vector<float> box((size_t)(n_inner + n) * 6);
+        std::vector<int> left((size_t)std::max(n_inner, 1)), right((size_t)std::max(n_inner, 1));
+        auto put_box = [&](size_t ref, const FBox& fb) { for (int a = 0; a < 3; ++a) { box[ref * 6 + a] = fb.mn[a]; box[ref * 6 + 3 + a] = fb.mx[a]; } };
+        auto ref_of = [&](int bi) { const BuildNode& c = b.nodes[bi]; return c.left >= 0 ? inner_of[bi] : n_inner + c.first; };
+        parallel_chunks(nb, 1 << 16, [&](int, size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i) {
+                const BuildNode& bn = b.nodes[i];
+                if (bn.left >= 0) { put_box((size_t)inner_of[i], bn.box); left[inner_of[i]] = ref_of(bn.left); right[inner_of[i]] = ref_of(bn.right); }
+                else put_box((size_t)(n_inner + bn.first), bn.box);
+            }
+        });
+        rtww::B2View view{box.data(), left.data(), right.data(), n_inner, n};
+        std::vector<int> order;
+        out.wide_depth = collapse_to_wide(view, out.wnodes, order);
+        std::vector<DPrim> reordered((size_t)n);
+        parallel_chunks((size_t)n, 1 << 16, [&](int, size_t i0, size_t i1) { for (size_t i = i0; i < i1; ++i) reordered[i] = out.prims[order[i]]; });
+        out.prims.swap(reordered);
+        if (!out.prim_boxes.empty()) {
+            std::vector<float> pb((size_t)n * 6);
+            for (int i = 0; i < n; ++i) std::memcpy(&pb[(size_t)i * 6], &out.prim_boxes[(size_t)order[i] * 6], 24);
+            out.prim_boxes.swap(pb);
+        }
+        std::vector<DNode>().swap(out.nodes);
+        lap("collapse to 8-wide");
+        if (out.wide_depth > RTW_WIDE_STACK) { err = "wide BVH deeper than the traversal stack"; return RTW_ERR_UNSUPPORTED_NESTING; }
+    }
     // feature bits (must match the FEAT_* enum of rtw_device.cuh): RECT 1, XFORM 2, MEDIA 4, NOISE 8, IMAGE 16, RXFORM 32 (an instanced RECT)
     for (const DPrim& p : fl.bvh_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= p.type >= PRIM_XY ? 2 | 32 : 2; }
     for (const DPrim& p : fl.boundary_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= p.type >= PRIM_XY ? 2 | 32 : 2; }
@@ -664,6 +756,153 @@ bool validate_bvh(const FlatScene& f, std::string& err) {
     }
     const int want = (f.nodes.size() == 1 && f.nodes[0].child0 == f.nodes[0].child1 && f.nodes[0].child0 < 0) ? 2 : 1;
     for (int i = 0; i < f.n_bvh_prims; ++i) if (seen[i] != want) { err = "prim not referenced exactly once"; return false; }
+    return true;
+}
+
+bool validate_wide(const FlatScene& f, std::string& err) {
+    const int n = f.n_bvh_prims;
+    if (n == 0) return true;
+    if (f.wnodes.empty()) { err = "no wide nodes"; return false; }
+    std::vector<int> seen((size_t)n, 0);
+    std::vector<uint8_t> node_seen(f.wnodes.size(), 0);
+    const bool boxes = f.prim_boxes.size() == (size_t)n * 6;
+    struct Frame { int node; float box[6]; bool has_box; };
+    std::vector<Frame> stack;
+    Frame root; root.node = 0; root.has_box = false;
+    stack.push_back(root);
+    while (!stack.empty()) {
+        Frame fr = stack.back(); stack.pop_back();
+        if (fr.node < 0 || fr.node >= (int)f.wnodes.size()) { err = "wide node index out of range"; return false; }
+        if (node_seen[fr.node]++) { err = "wide node referenced twice"; return false; }
+        const DWNode& w = f.wnodes[fr.node];
+        if (w.imask & w.lmask) { err = "slot is both inner and leaf"; return false; }
+        if (!(w.imask | w.lmask)) { err = "empty wide node"; return false; }
+        // union of the child boxes must stay inside what the parent promised for this node
+        for (int s = 0; s < 8; ++s) {
+            const bool in = (w.imask >> s) & 1, lf = (w.lmask >> s) & 1;
+            if (!in && !lf) continue;
+            float cb[6]; rtww::wide_child_box(w, s, cb);
+            if (fr.has_box) for (int a = 0; a < 3; ++a) {
+                // a child box may stick out of the parent's quantised box by its own grid padding only
+                const float tol = 4.0f * std::ldexp(1.0f, (int)(a == 0 ? w.ex : a == 1 ? w.ey : w.ez) - 127) + 1e-6f * (std::fabs(cb[a]) + std::fabs(cb[a + 3]));
+                if (cb[a] < fr.box[a] - tol || cb[a + 3] > fr.box[a + 3] + tol) { err = "child box outside its parent's box"; return false; }
+            }
+            const int below = (1 << s) - 1;
+            if (in) {
+                Frame c; c.node = (int)w.child_base + __builtin_popcount(w.imask & below); c.has_box = true; std::memcpy(c.box, cb, sizeof(cb));
+                stack.push_back(c);
+            } else {
+                const int pi = (int)w.prim_base + __builtin_popcount(w.lmask & below);
+                if (pi < 0 || pi >= n) { err = "leaf primitive index out of range"; return false; }
+                seen[pi]++;
+                if (boxes) for (int a = 0; a < 3; ++a)
+                    if (f.prim_boxes[(size_t)pi * 6 + a] < cb[a] || f.prim_boxes[(size_t)pi * 6 + 3 + a] > cb[a + 3]) { err = "leaf box does not contain its primitive"; return false; }
+            }
+        }
+    }
+    for (int i = 0; i < n; ++i) if (seen[i] != 1) { err = "prim not referenced exactly once by the wide BVH"; return false; }
+    for (size_t i = 0; i < f.wnodes.size(); ++i) if (!node_seen[i]) { err = "unreachable wide node"; return false; }
+    return true;
+}
+
+bool check_wide_traversal(const FlatScene& f, int n_rays, uint64_t seed, uint64_t out[5], std::string& err) {
+    for (int i = 0; i < 5; ++i) out[i] = 0;
+    const int n = f.n_bvh_prims;
+    if (n == 0 || f.wnodes.empty()) return true;
+    if (f.prim_boxes.size() != (size_t)n * 6) { err = "prim boxes were not kept"; return false; }
+    // scene bounds
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], (double)f.prim_boxes[(size_t)i * 6 + a]); hi[a] = std::max(hi[a], (double)f.prim_boxes[(size_t)i * 6 + 3 + a]); }
+    // a huge primitive (the r = 1000 ground sphere) would put every origin far away from everything else: aim at the
+    // median-sized part of the scene as well
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 12345;
+    auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)((st >> 11) & ((1ull << 53) - 1)) / (double)(1ull << 53); };
+    const float t_min = 0.001f;
+    std::vector<uint8_t> reached((size_t)n);
+    for (int ri = 0; ri < n_rays; ++ri) {
+        // origin: around a random primitive (near or far), direction: towards another random primitive, or axis-parallel
+        const int pa = (int)(rnd() * n) % n, pb = (int)(rnd() * n) % n;
+        float o[3], d[3];
+        const double spread = rnd() < 0.5 ? 2.0 : 50.0;
+        for (int a = 0; a < 3; ++a) {
+            const double ca = 0.5 * (f.prim_boxes[(size_t)pa * 6 + a] + f.prim_boxes[(size_t)pa * 6 + 3 + a]);
+            const double ea = std::min(1e3, 0.5 * (f.prim_boxes[(size_t)pa * 6 + 3 + a] - f.prim_boxes[(size_t)pa * 6 + a]) + 1e-3);
+            o[a] = (float)(ca + (rnd() * 2 - 1) * spread * ea);
+            const double cb = f.prim_boxes[(size_t)pb * 6 + a] + rnd() * (f.prim_boxes[(size_t)pb * 6 + 3 + a] - f.prim_boxes[(size_t)pb * 6 + a]);
+            d[a] = (float)((cb - o[a]) * (0.05 + rnd()));
+        }
+        const int mode = ri % 8;
+        if (mode == 5) { d[0] = 0.0f; }                                   // axis-parallel cases (zero components, both signs of zero)
+        if (mode == 6) { d[1] = -0.0f; d[2] = 0.0f; }
+        if (mode == 7) { d[0] = 0.0f; d[2] = -0.0f; }
+        if (d[0] == 0.0f && d[1] == 0.0f && d[2] == 0.0f) d[1] = 1.0f;
+        // per-ray constants exactly as rtw_device.cuh slab_setup / bvh8_closest derive them (1/d: IEEE here, MUFU there)
+        rtww::WRay r;
+        auto sdir = [](float v) { return std::fabs(v) < 1e-20f ? std::copysign(1e-20f, v) : v; };
+        r.ix = 1.0f / sdir(d[0]); r.iy = 1.0f / sdir(d[1]); r.iz = 1.0f / sdir(d[2]);
+        r.oix = o[0] * r.ix; r.oiy = o[1] * r.iy; r.oiz = o[2] * r.iz;
+        const float sx = std::fabs(d[0]) < 1e-20f ? 0.f : std::fabs(r.oix), sy = std::fabs(d[1]) < 1e-20f ? 0.f : std::fabs(r.oiy), sz = std::fabs(d[2]) < 1e-20f ? 0.f : std::fabs(r.oiz);
+        r.slack = 2.384185791015625e-07f * std::max(sx, std::max(sy, sz));
+        const uint32_t oct = (r.ix < 0 ? 1u : 0u) | (r.iy < 0 ? 2u : 0u) | (r.iz < 0 ? 4u : 0u);
+        r.k = oct ^ 7u; r.one = 0x3F800000u;
+        std::fill(reached.begin(), reached.end(), 0);
+        // traversal with t_best = inf (every leaf whose box passes is reached), the device's group / stack scheme
+        struct Grp { uint32_t base, g; };
+        std::vector<Grp> stack;
+        uint32_t base = 0, grp = (1u << 8) | (1u << (0u ^ r.k));
+        for (;;) {
+            if (!(grp & 0xffu)) { if (stack.empty()) break; base = stack.back().base; grp = stack.back().g; stack.pop_back(); continue; }
+            const int j = 31 - __builtin_clz(grp & 0xffu);
+            grp ^= 1u << j;
+            const uint32_t slot = (uint32_t)j ^ r.k, imask = grp >> 8;
+            const uint32_t node = base + (uint32_t)__builtin_popcount(imask & ((1u << slot) - 1u));
+            if (grp & 0xffu) stack.push_back(Grp{base, grp});
+            if (stack.size() > RTW_WIDE_STACK) { err = "traversal stack overflow"; return false; }
+            const DWNode& w = f.wnodes[node];
+            rtww::W4 q[5]; std::memcpy(q, &w, 80);
+            uint32_t hits = rtww::wide_node_hits(q[0], q[2], q[3], q[4], r, t_min, INFINITY);
+            hits &= (uint32_t)(w.imask | w.lmask);
+            out[1]++;
+            const uint32_t m16 = rtww::wide_perm16((hits & w.imask) | ((hits & w.lmask) << 8), r.k);
+            uint32_t pl = m16 >> 8;
+            while (pl) {
+                const int jj = 31 - __builtin_clz(pl); pl ^= 1u << jj;
+                const uint32_t s = (uint32_t)jj ^ r.k;
+                reached[w.prim_base + (uint32_t)__builtin_popcount(w.lmask & ((1u << s) - 1u))] = 1;
+                out[2]++;
+            }
+            base = w.child_base; grp = ((uint32_t)w.imask << 8) | (m16 & 0xffu);
+        }
+        // exact slab test in double against every primitive box
+        for (int i = 0; i < n; ++i) {
+            double tn = t_min, tf = 1e300; bool miss = false;
+            for (int a = 0; a < 3 && !miss; ++a) {
+                const double mn = f.prim_boxes[(size_t)i * 6 + a], mx = f.prim_boxes[(size_t)i * 6 + 3 + a], oo = o[a], dd = d[a];
+                if (dd == 0.0) {
+                    // origin within rounding distance of a face and no motion along this axis: "inside" is undecidable in
+                    // f32 (o / d is rounded at 1e20 |o|; the reference itself computes 0 * inf = NaN there) — not counted
+                    const double eps = 1e-6 * (std::fabs(oo) + 1.0);
+                    if (oo < mn + eps || oo > mx - eps) miss = true;
+                    continue;
+                }
+                double t0 = (mn - oo) / dd, t1 = (mx - oo) / dd;
+                if (t0 > t1) std::swap(t0, t1);
+                tn = std::max(tn, t0); tf = std::min(tf, t1);
+                if (tn > tf) miss = true;
+            }
+            if (!miss) {
+                out[3]++;
+                if (!reached[i]) {
+                    out[4]++;
+                    if (getenv("RTW_DEBUG_WIDE")) fprintf(stderr, "[wide] ray %d o (%.9g %.9g %.9g) d (%.9g %.9g %.9g) misses prim %d box (%.9g %.9g %.9g)-(%.9g %.9g %.9g) tn %.9g tf %.9g\n", ri,
+                        o[0], o[1], o[2], d[0], d[1], d[2], i, f.prim_boxes[(size_t)i * 6], f.prim_boxes[(size_t)i * 6 + 1], f.prim_boxes[(size_t)i * 6 + 2],
+                        f.prim_boxes[(size_t)i * 6 + 3], f.prim_boxes[(size_t)i * 6 + 4], f.prim_boxes[(size_t)i * 6 + 5], tn, tf);
+                }
+            }
+        }
+        out[0]++;
+    }
+    if (out[4]) { err = "the quantised traversal missed a primitive box the ray crosses"; return false; }
     return true;
 }
 

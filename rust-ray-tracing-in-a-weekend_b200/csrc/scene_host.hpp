@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 
+#include "bvh_wide.h"
 #include "rtw_types.h"
 
 namespace rtw {
@@ -58,7 +59,11 @@ struct SceneGraph {
 
 // The flattened scene, still on the host, ready to be packed into one blob.
 struct FlatScene {
-    std::vector<DNode> nodes;
+    std::vector<DNode> nodes;        // binary BVH (empty when the scene uses the wide one)
+    std::vector<DWNode> wnodes;      // 8-wide compressed BVH (bvh_wide.h); [0] = root
+    bool wide = false;
+    int wide_depth = 0;              // levels of the wide tree (bounds the traversal stack)
+    std::vector<float> prim_boxes;   // 6 floats per BVH prim in final order (only with FlattenOptions::keep_boxes: validation)
     std::vector<DPrim> prims;        // [0, n_bvh_prims) in leaf order, then medium boundary prims
     int32_t n_bvh_prims = 0;
     std::vector<DXform> xforms;      // [0] = identity
@@ -76,9 +81,27 @@ struct FlatScene {
     double mov_t0 = -1e300, mov_t1 = 1e300;
 };
 
+// bvh_width: 2 = binary nodes, 8 = wide compressed nodes, 0 = by size (RTW_BVH=2|8 overrides; scenes of at least
+// RTW_WIDE_MIN primitives, default kWideMinPrims, go wide: they no longer fit the caches).
+struct FlattenOptions { int bvh_width = 0; bool keep_boxes = false; };
+static const int kWideMinPrims = 1 << 15;
+
 // Flatten `roots` (world.hittables, or a single hittable for the test hooks).  Returns 0 or a negative
 // rtw_status; `err` gets a message.
-int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, std::string& err);
+int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, std::string& err, const FlattenOptions& opt = FlattenOptions());
+
+// Host-side BVH2 -> BVH8 collapse (the device builder runs the same rtww::collapse_one per node).  `box`: 6 floats per
+// ref as in rtww::B2View.  Fills wnodes / leaf_order (final position -> leaf number); returns the depth of the wide tree.
+int collapse_to_wide(const rtww::B2View& v, std::vector<DWNode>& wnodes, std::vector<int>& leaf_order);
+
+// Structural check of the wide BVH: every BVH prim referenced exactly once, every child box contains the boxes below it
+// (needs prim_boxes), masks / ranges consistent.
+bool validate_wide(const FlatScene& f, std::string& err);
+
+// Conservativeness of the quantised traversal, on the CPU with the arithmetic the device uses (rtww::wide_node_hits):
+// for `n_rays` seeded rays the leaves the traversal reaches must include every primitive whose box the ray really
+// crosses.  out: [0] rays, [1] node visits, [2] leaves reached, [3] boxes really crossed, [4] MISSED (must be 0).
+bool check_wide_traversal(const FlatScene& f, int n_rays, uint64_t seed, uint64_t out[5], std::string& err);
 
 // Structural check used by the CPU tests: every BVH prim referenced exactly once and inside its ancestors' boxes.
 bool validate_bvh(const FlatScene& f, std::string& err);
