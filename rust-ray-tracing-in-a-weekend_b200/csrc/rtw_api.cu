@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/rtw.h"
+#include "bvh_build.hpp"
 #include "rtw_device.cuh"
 #include "rtw_pool.cuh"
 #include "scene_host.hpp"
@@ -432,6 +433,7 @@ struct Replica {
     int grid = 0;                           // megakernel grid (also sizes the work units)
     int pool_grid[4] = {0, 0, 0, 0};        // warp-pool kernel grids for POOL = 64/128/192/256 (lazy)
     int sms = 0;
+    rtwb::BuildOutput built;                // device-built BVH + primitive records (own allocations, outside the blob)
 };
 
 struct SharedFb {          // framebuffer + unit counter reachable by every GPU / rank
@@ -449,6 +451,8 @@ struct rtw_scene {
     rtw::SceneGraph g;
     rtw::FlatScene flat;
     bool committed = false;
+    int n_prims_dev = 0, n_nodes_dev = 0;   // sizes when the BVH was built on the device (flat.prims then holds only its input)
+    double ms_build_dev = 0;
     std::vector<Replica> reps;
     SharedFb local;        // used by rtw_render (in-process, on reps[0].device)
     SharedFb shared;       // used by rtw_render_shared (cross-process)
@@ -464,6 +468,7 @@ void free_replicas(rtw_scene* s) {
     for (Replica& r : s->reps) {
         cudaSetDevice(r.device);
         if (r.blob) cudaFree(r.blob);
+        rtwb::free_output(r.built);
         if (r.stats) cudaFree(r.stats);
         if (r.ev0) cudaEventDestroy(r.ev0);
         if (r.ev1) cudaEventDestroy(r.ev1);
@@ -703,6 +708,7 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
 
 void fill_scene_stats(rtw_scene* s, rtw_stats* st) {
     st->n_prims = (int)s->flat.prims.size(); st->n_nodes = (int)(s->flat.wide ? s->flat.wnodes.size() : s->flat.nodes.size());
+    if (s->flat.emit_only) { st->n_prims = s->n_prims_dev; st->n_nodes = s->n_nodes_dev; }
     st->n_materials = (int)s->flat.mats.size(); st->n_media = (int)s->flat.media.size();
     st->ms_commit = s->ms_commit;
 }
@@ -943,8 +949,24 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     if (first_device < 0 || n_gpus < 1 || first_device + n_gpus > ndev || n_gpus > 8) return fail(RTW_ERR_INVALID_ARG, "device range not available");
     double t0 = now_ms();
     std::string err;
-    int rc = rtw::flatten(s->g, s->g.world, s->flat, err);
+    // Where the BVH is built.  Scenes beyond the cache-resident range (RTW_DEVICE_BUILD_MIN primitives, default 32768) are
+    // built ON THE DEVICE from what the constructors were given (bvh_build.cu); small ones keep the host SAH builder
+    // (C1: 1 ms, better trees).  RTW_DEVICE_BUILD=0 / 1 forces either.
+    rtw::FlattenOptions fo;
+    {
+        long long n_guess = (long long)s->g.bulk.size() + (long long)s->g.nodes.size();
+        long long dev_min = 32768;
+        if (const char* e = getenv("RTW_DEVICE_BUILD_MIN")) dev_min = atoll(e);
+        fo.emit_only = n_guess >= dev_min;
+        if (const char* e = getenv("RTW_DEVICE_BUILD")) fo.emit_only = atoi(e) != 0;
+    }
+    int rc = rtw::flatten(s->g, s->g.world, s->flat, err, fo);
     if (rc) return fail(rc, err);
+    if (s->flat.emit_only && s->flat.n_bvh_prims == 0) {         // nothing to build: the plain path handles the empty world
+        fo.emit_only = false;
+        rc = rtw::flatten(s->g, s->g.world, s->flat, err, fo);
+        if (rc) return fail(rc, err);
+    }
     Packed pk; pack(s->flat, pk);
     // replicas (stream, events, grid size, blob allocation) are reused across commits on the same devices:
     // a re-commit is then one flatten + one H2D copy per GPU
@@ -978,9 +1000,50 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
             if (r.blob) { CUDA_TRY(cudaFree(r.blob)); r.blob = nullptr; }
             CUDA_TRY(cudaMalloc(&r.blob, pk.total)); r.blob_bytes = pk.total;
         }
-        CUDA_TRY(upload(s->flat, pk, r.blob, r.stream));
-        s->h2d_commit += pk.total;
+        rtwb::free_output(r.built);
+        if (!s->flat.emit_only) {
+            CUDA_TRY(upload(s->flat, pk, r.blob, r.stream));
+            s->h2d_commit += pk.total;
+            r.ds = bind(s->flat, pk, r.blob);
+            continue;
+        }
+        // ---- device-side build: the blob carries the small tables only; nodes and primitive records are built in place
+        const size_t small = pk.o_xf;                         // [o_xf, total): xforms, media, materials, textures, perlin, image
+        {
+            const rtw::FlatScene& f = s->flat;
+            auto cp = [&](size_t o, const void* src, size_t n) { return n ? cudaMemcpyAsync(r.blob + o, src, n, cudaMemcpyHostToDevice, r.stream) : cudaSuccess; };
+            CUDA_TRY(cp(pk.o_xf, f.xforms.data(), f.xforms.size() * sizeof(DXform)));
+            CUDA_TRY(cp(pk.o_media, f.media.data(), f.media.size() * sizeof(DMedium)));
+            CUDA_TRY(cp(pk.o_mats, f.mats.data(), f.mats.size() * sizeof(DMat)));
+            CUDA_TRY(cp(pk.o_texs, f.texs.data(), f.texs.size() * sizeof(DTex)));
+            CUDA_TRY(cp(pk.o_perlin, f.perlin.data(), f.perlin.size()));
+            CUDA_TRY(cp(pk.o_image, f.image.data(), f.image.size()));
+            s->h2d_commit += pk.total - small;
+        }
         r.ds = bind(s->flat, pk, r.blob);
+        if (i == 0) {
+            rtwb::BuildInput in;
+            in.host_prims = s->flat.prims.data(); in.host_boxes = s->flat.prim_boxes.data(); in.n_host = (int)s->flat.prims.size();
+            in.bulk = reinterpret_cast<const rtwb::BulkSphereD*>(s->g.bulk.data()); in.n_bulk = s->flat.n_bvh_prims - in.n_host;
+            in.boundary_prims = s->flat.boundary.data(); in.n_boundary = (int)s->flat.boundary.size();
+            in.width = s->flat.wide ? 8 : 2;
+            const double tb = now_ms();
+            const int brc = rtwb::build_on_device(r.stream, in, r.built, err);
+            if (brc) return fail(brc, "device BVH build: " + err);
+            s->ms_build_dev = now_ms() - tb;
+            s->h2d_commit += r.built.h2d_bytes;
+            s->n_prims_dev = r.built.n_prims; s->n_nodes_dev = s->flat.wide ? r.built.n_wnodes : r.built.n_nodes;
+            s->flat.wide_depth = r.built.depth;
+        } else {                                              // other replicas: copy the finished arrays over NVLink
+            const rtwb::BuildOutput& b0 = s->reps[0].built;
+            r.built.n_wnodes = b0.n_wnodes; r.built.n_nodes = b0.n_nodes; r.built.n_prims = b0.n_prims; r.built.depth = b0.depth;
+            if (b0.n_wnodes) { CUDA_TRY(cudaMalloc(&r.built.wnodes, (size_t)b0.n_wnodes * sizeof(DWNode))); CUDA_TRY(cudaMemcpyPeerAsync(r.built.wnodes, r.device, b0.wnodes, s->reps[0].device, (size_t)b0.n_wnodes * sizeof(DWNode), r.stream)); }
+            if (b0.n_nodes) { CUDA_TRY(cudaMalloc(&r.built.nodes, (size_t)b0.n_nodes * sizeof(DNode))); CUDA_TRY(cudaMemcpyPeerAsync(r.built.nodes, r.device, b0.nodes, s->reps[0].device, (size_t)b0.n_nodes * sizeof(DNode), r.stream)); }
+            CUDA_TRY(cudaMalloc(&r.built.prims, (size_t)b0.n_prims * sizeof(DPrim)));
+            CUDA_TRY(cudaMemcpyPeerAsync(r.built.prims, r.device, b0.prims, s->reps[0].device, (size_t)b0.n_prims * sizeof(DPrim), r.stream));
+        }
+        r.ds.nodes = r.built.nodes; r.ds.wnodes = r.built.wnodes; r.ds.prims = r.built.prims;
+        r.ds.n_nodes = s->flat.wide ? r.built.n_wnodes : r.built.n_nodes; r.ds.n_prims = r.built.n_prims; r.ds.n_bvh_prims = s->flat.n_bvh_prims;
     }
     for (Replica& r : s->reps) { CUDA_TRY(cudaSetDevice(r.device)); CUDA_TRY(cudaStreamSynchronize(r.stream)); }
     s->committed = true;

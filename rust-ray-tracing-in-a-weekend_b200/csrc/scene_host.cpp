@@ -583,6 +583,18 @@ int collapse_to_wide(const rtww::B2View& v, std::vector<DWNode>& wnodes, std::ve
     return alloc.max_depth;
 }
 
+int kWideMinPrims = 0x7fffffff;          // binary nodes everywhere unless RTW_BVH=8 / RTW_WIDE_MIN say otherwise
+int choose_bvh_width(long long n, int requested) {
+    int width = requested;
+    if (width == 0) { if (const char* e = getenv("RTW_BVH")) width = atoi(e); }
+    if (width != 2 && width != 8) {
+        long long wide_min = kWideMinPrims;
+        if (const char* e = getenv("RTW_WIDE_MIN")) wide_min = std::max(1, atoi(e));
+        width = n >= wide_min ? 8 : 2;
+    }
+    return width;
+}
+
 int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, std::string& err, const FlattenOptions& opt) {
     const bool timing = getenv("RTW_TIMING") != nullptr;
     auto T0 = std::chrono::steady_clock::now();
@@ -596,7 +608,30 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         int rc = fl.emit(id, ch, false, 0);
         if (rc) return rc;
     }
-    if (&roots == &g.world) {           // bulk spheres belong to the world, not to a single-hittable view
+    const bool with_bulk = &roots == &g.world;
+    if (opt.emit_only) {
+        // input of the device builder: scene-graph primitives + boxes as they are, bulk spheres untouched
+        pack_materials(g, out);
+        for (const DPrim& p : fl.bvh_prims) if (p.mat < 0 || p.mat >= (int)out.mats.size()) { err = "material handle out of range"; return RTW_ERR_INVALID_ARG; }
+        for (const DMedium& m : out.media) if (m.mat < 0 || m.mat >= (int)out.mats.size()) { err = "phase material handle out of range"; return RTW_ERR_INVALID_ARG; }
+        if (with_bulk) for (const BulkSphere& b : g.bulk) if (b.mat < 1 || b.mat > (int)out.mats.size()) { err = "material handle out of range"; return RTW_ERR_INVALID_ARG; }
+        const long long n_all = (long long)fl.bvh_prims.size() + (with_bulk ? (long long)g.bulk.size() : 0);
+        if (n_all >= (1 << 28)) { err = "too many primitives"; return RTW_ERR_INVALID_ARG; }
+        out.emit_only = true;
+        out.wide = choose_bvh_width(n_all, opt.bvh_width) == 8;
+        out.n_bvh_prims = (int)n_all;
+        out.prim_boxes.resize(fl.bvh_prims.size() * 6);
+        for (size_t i = 0; i < fl.bvh_prims.size(); ++i) for (int a = 0; a < 3; ++a) { out.prim_boxes[i * 6 + a] = down(fl.bvh_boxes[i].mn[a]); out.prim_boxes[i * 6 + 3 + a] = up(fl.bvh_boxes[i].mx[a]); }
+        for (const DPrim& p : fl.bvh_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= p.type >= PRIM_XY ? 2 | 32 : 2; }
+        for (const DPrim& p : fl.boundary_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= p.type >= PRIM_XY ? 2 | 32 : 2; }
+        if (!out.media.empty()) out.features |= 4;
+        for (const DTex& t : out.texs) { if (t.kind == TEX_NOISE) out.features |= 8; if (t.kind == TEX_IMAGE) out.features |= 16; }
+        for (DMedium& m : out.media) m.first += (int)n_all;
+        out.prims.swap(fl.bvh_prims);
+        out.boundary.swap(fl.boundary_prims);
+        return 0;
+    }
+    if (with_bulk) {           // bulk spheres belong to the world, not to a single-hittable view
         const size_t base = fl.bvh_prims.size();
         fl.bvh_prims.resize(base + g.bulk.size());
         fl.bvh_boxes.resize(base + g.bulk.size());
@@ -618,15 +653,8 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
     for (const DMedium& m : out.media) if (m.mat < 0 || m.mat >= (int)out.mats.size()) { err = "phase material handle out of range"; return RTW_ERR_INVALID_ARG; }
     const int n = (int)fl.bvh_prims.size();
     if (n >= (1 << 28)) { err = "too many primitives"; return RTW_ERR_INVALID_ARG; }
-    // node format: binary for scenes that live in the caches, 8-wide compressed beyond (FlattenOptions / RTW_BVH / RTW_WIDE_MIN)
-    int width = opt.bvh_width;
-    if (width == 0) { if (const char* e = getenv("RTW_BVH")) width = atoi(e); }
-    if (width != 2 && width != 8) {
-        int wide_min = kWideMinPrims;
-        if (const char* e = getenv("RTW_WIDE_MIN")) wide_min = std::max(1, atoi(e));
-        width = n >= wide_min ? 8 : 2;
-    }
-    out.wide = width == 8;
+    // node format: binary or 8-wide compressed (FlattenOptions / RTW_BVH / RTW_WIDE_MIN)
+    out.wide = choose_bvh_width(n, opt.bvh_width) == 8;
     // BVH (RTW_BVH_LEAF / RTW_BVH_CI: tuning overrides for kernel experiments)
     Builder::MAX_LEAF = 1;
     if (const char* e = getenv("RTW_BVH_LEAF")) Builder::MAX_LEAF = std::max(1, std::min(8, atoi(e)));

@@ -65,6 +65,8 @@ struct FlatScene {
     int wide_depth = 0;              // levels of the wide tree (bounds the traversal stack)
     std::vector<float> prim_boxes;   // 6 floats per BVH prim in final order (only with FlattenOptions::keep_boxes: validation)
     std::vector<DPrim> prims;        // [0, n_bvh_prims) in leaf order, then medium boundary prims
+    std::vector<DPrim> boundary;     // emit_only: the medium boundary records (they follow the BVH prims on the device)
+    bool emit_only = false;
     int32_t n_bvh_prims = 0;
     std::vector<DXform> xforms;      // [0] = identity
     std::vector<DMedium> media;
@@ -83,8 +85,13 @@ struct FlatScene {
 
 // bvh_width: 2 = binary nodes, 8 = wide compressed nodes, 0 = by size (RTW_BVH=2|8 overrides; scenes of at least
 // RTW_WIDE_MIN primitives, default kWideMinPrims, go wide: they no longer fit the caches).
-struct FlattenOptions { int bvh_width = 0; bool keep_boxes = false; };
-static const int kWideMinPrims = 1 << 15;
+// emit_only: stop after the primitive records — no BVH, rtw_sphere_batch spheres left alone (`prims` = the scene-graph
+// primitives in emission order with their boxes in `prim_boxes`, `boundary` = the medium boundary records, n_bvh_prims =
+// scene-graph primitives + bulk spheres): the input of the device-side builder (bvh_build.cu).
+struct FlattenOptions { int bvh_width = 0; bool keep_boxes = false; bool emit_only = false; };
+// Scenes of at least this many primitives get wide nodes.  Measured on the B200 (profiles/r2_*): ... see DESIGN.md 4.5.
+extern int kWideMinPrims;
+int choose_bvh_width(long long n_prims, int requested);
 
 // Flatten `roots` (world.hittables, or a single hittable for the test hooks).  Returns 0 or a negative
 // rtw_status; `err` gets a message.
