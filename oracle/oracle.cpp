@@ -20,6 +20,9 @@
 //  * random_double() is replaced by an injectable stream: either an explicit array of U[0,1)
 //    draws, or Philox4x32-10 keyed by seed with counter (draw block, bounce, pixel, sample);
 //    a draw is (word >> 8) * 2^-24 so that the f32 device path consumes the identical value.
+//    The two rejection loops (unit sphere, unit disk) take their attempts from blocks of their own,
+//    indexed by the attempt number (Rng::sphere_attempt / disk_attempt) — same distribution, same
+//    acceptance test; explicit streams stay sequential like the reference.
 //  * random_double_range(a,b) (inclusive in rand 0.8, src/math.rs:273-276) is a + (b-a)*xi.
 //  * optional `media_deferred` world scan (all non-medium items first, then the media in list
 //    order) — the order the device uses; the default is the literal list order.
@@ -145,22 +148,45 @@ struct Rng {
         return (double)(w >> 8) * (1.0 / 16777216.0);
     }
     double range(double a, double b) { return a + (b - a) * next(); }  // random_double_range :273-276
+    // The rejection loops (math.rs:51-58, :69-76) draw from their OWN Philox blocks, indexed by the attempt: attempt a of the
+    // unit-sphere loop of this bounce is block 0x40000000 + a (words 0..2 = x, y, z), attempt a of the unit-disk loop is
+    // words 2(a & 1), 2(a & 1) + 1 of block 0x20000000 + (a >> 1).  They do not advance the scalar stream.  (The device can
+    // then evaluate ANY attempt of ANY lane: finished lanes help unlucky ones, csrc/rtw_device.cuh coop_unit_sphere.)
+    // With an explicit stream (parity hooks) the draws stay sequential, as in the reference.
+    static double u01(uint32_t w) { return (double)(w >> 8) * (1.0 / 16777216.0); }
+    void sphere_attempt(uint32_t a, double& x, double& y, double& z) {
+        if (!philox) { x = next(); y = next(); z = next(); return; }
+        total += 3;
+        uint32_t ctr[4] = {0x40000000u + a, bounce, pixel, sample}, w[4];
+        philox4x32_10(ctr, key, w);
+        x = u01(w[0]); y = u01(w[1]); z = u01(w[2]);
+    }
+    void disk_attempt(uint32_t a, double& x, double& y) {
+        if (!philox) { x = next(); y = next(); return; }
+        total += 2;
+        uint32_t ctr[4] = {0x20000000u + (a >> 1), bounce, pixel, sample}, w[4];
+        philox4x32_10(ctr, key, w);
+        x = u01(w[2 * (a & 1)]); y = u01(w[2 * (a & 1) + 1]);
+    }
 };
 
 inline V3 random_range_v3(Rng& g, double a, double b) {          // Vector3::random_range :43-49 (x, y, z order)
     double x = g.range(a, b); double y = g.range(a, b); double z = g.range(a, b);
     return V3(x, y, z);
 }
-inline V3 random_in_unit_sphere(Rng& g) {                         // :51-58
-    for (;;) {
-        V3 p = random_range_v3(g, -1.0, 1.0);
+inline V3 random_in_unit_sphere(Rng& g) {                         // :51-58; Vector3::random_range(-1, 1) :43-49 per attempt
+    for (uint32_t a = 0;; ++a) {
+        double x, y, z;
+        g.sphere_attempt(a, x, y, z);
+        V3 p(-1.0 + 2.0 * x, -1.0 + 2.0 * y, -1.0 + 2.0 * z);      // a + (b - a) * random_double() :273-276
         if (length_squared(p) < 1.0) return p;
     }
 }
 inline V3 random_in_unit_disk(Rng& g) {                           // :69-76
-    for (;;) {
-        double x = g.range(-1.0, 1.0); double y = g.range(-1.0, 1.0);
-        V3 p(x, y, 0.0);
+    for (uint32_t a = 0;; ++a) {
+        double x, y;
+        g.disk_attempt(a, x, y);
+        V3 p(-1.0 + 2.0 * x, -1.0 + 2.0 * y, 0.0);
         if (length_squared(p) < 1.0) return p;
     }
 }

@@ -49,6 +49,9 @@ extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
 #ifndef RTW_MIN_BLOCKS
 #define RTW_MIN_BLOCKS 7
 #endif
+#ifndef RTW_COOP
+#define RTW_COOP 1          // unit-ball samples drawn by the whole warp (coop_unit_sphere); 0 = every lane loops on its own
+#endif
 
 template <int F, int W>
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
@@ -57,6 +60,7 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
     __shared__ __align__(16) float acc[RTW_WARPS][96];    // per-warp tile accumulator (32 px x rgb)
     __shared__ float ring[RTW_WARPS][12][64];             // secondary-ray ring: o(3) d(3) time T(3) last_prim meta, 64 per warp
     __shared__ int tlist[RTW_WARPS][RTW_TILE_LIST];       // primitives the tile's primary rays can touch
+    __shared__ int coop_scr[RTW_WARPS][32];               // coop_unit_sphere: failed-lane directory
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long rays = 0, units = 0;
@@ -172,9 +176,9 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
             }
             // ---- media, miss, hit record, emitted + scatter (main.rs:26-37)
             bool cont = false;
+            V3 add;
+            cont = path_finish<F, RTW_COOP != 0>(sc, prm, ps, tr, t_best, prim_best, add, work, lane, coop_scr[warp]);    // all 32 lanes
             if (work) {
-                V3 add;
-                cont = path_finish<F>(sc, prm, ps, tr, t_best, prim_best, add);
                 ++rays;
                 if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
                     atomicAdd(&acc[warp][wpix * 3 + 0], add.x);

@@ -113,6 +113,18 @@ RTW_DEV void philox4x32_10_rk(const uint32_t* __restrict__ rk, uint32_t c0, uint
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
+// Stream layout (identical in oracle/oracle.cpp Rng): scalar draws of a bounce are words of blocks 0, 1, 2, ... of its
+// counter line; the two rejection loops take their attempts from blocks of their own, indexed by the ATTEMPT: unit sphere
+// (src/math.rs:51-58) attempt a = words 0..2 of block 0x40000000 + a, unit disk (:69-76) attempt a = words 2(a & 1),
+// 2(a & 1) + 1 of block 0x20000000 + (a >> 1).  They do not advance the scalar stream.  Any lane can therefore evaluate any
+// attempt of any other lane from (pixel, sample, bounce) alone — coop_unit_sphere below.
+RTW_DEV float u01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+RTW_DEV void philox_sphere_attempt(const uint32_t* __restrict__ rk, uint32_t a, uint32_t bounce, uint32_t pixel, uint32_t sample, float& x, float& y, float& z) {
+    uint32_t w0, w1, w2, w3;
+    philox4x32_10_rk(rk, 0x40000000u + a, bounce, pixel, sample, w0, w1, w2, w3);
+    x = u01(w0); y = u01(w1); z = u01(w2);
+}
+
 struct PhiloxRng {
     uint32_t pixel, sample, bounce, draw;
     uint32_t w0, w1, w2, w3;
@@ -139,6 +151,13 @@ struct PhiloxRng {
         draw += single ? 1u : 2u;
         x = (float)(wx >> 8) * (1.0f / 16777216.0f); y = (float)(wy >> 8) * (1.0f / 16777216.0f);
     }
+    RTW_DEV void sphere_attempt(uint32_t a, float& x, float& y, float& z) const { philox_sphere_attempt(rk, a, bounce, pixel, sample, x, y, z); }
+    // two unit-disk attempts (2 blk, 2 blk + 1) from one block; `second` = the second pair is a real attempt
+    RTW_DEV void disk_pair(uint32_t blk, float& x0, float& y0, float& x1, float& y1, bool& second) const {
+        uint32_t a0, a1, a2, a3;
+        philox4x32_10_rk(rk, 0x20000000u + blk, bounce, pixel, sample, a0, a1, a2, a3);
+        x0 = u01(a0); y0 = u01(a1); x1 = u01(a2); y1 = u01(a3); second = true;
+    }
     RTW_DEV void next3(float& x, float& y, float& z) {
         const uint32_t i = draw & 3u;
         const uint32_t ox = i == 1 ? w1 : (i == 2 ? w2 : w3), oy = i == 1 ? w2 : w3, oz = w3;
@@ -153,6 +172,8 @@ struct PhiloxRng {
 struct StreamRng {
     const double* xi; int n; int draw;
     RTW_DEV void set_bounce(uint32_t) {}
+    RTW_DEV void sphere_attempt(uint32_t, float& x, float& y, float& z) { x = next(); y = next(); z = next(); }     // sequential, like the reference
+    RTW_DEV void disk_pair(uint32_t, float& x0, float& y0, float& x1, float& y1, bool& second) { x0 = next(); y0 = next(); x1 = 0.f; y1 = 0.f; second = false; }
     RTW_DEV float next() { float v = draw < n ? (float)xi[draw] : 0.5f; ++draw; return v; }
     RTW_DEV void next2(float& x, float& y, bool single = false) { x = next(); y = single ? 0.5f : next(); }
     RTW_DEV void next3(float& x, float& y, float& z) { x = next(); y = next(); z = next(); }
@@ -160,12 +181,64 @@ struct StreamRng {
 
 template <class R> RTW_DEV float rng_range(R& g, float a, float b) { return a + (b - a) * g.next(); }   // :273-276
 template <class R> RTW_DEV V3 random_in_unit_sphere(R& g) {                                               // :51-58, draw order x,y,z :43-49
-    for (;;) {
+#pragma unroll 1
+    for (uint32_t a = 0;; ++a) {
         float x, y, z;
-        g.next3(x, y, z);
+        g.sphere_attempt(a, x, y, z);
         V3 p = mk(-1.0f + 2.0f * x, -1.0f + 2.0f * y, -1.0f + 2.0f * z);                  // random_range(-1, 1) :273-276
         if (length_squared(p) < 1.0f) return p;
     }
+}
+
+// The same sample, drawn by the whole WARP for the lanes that `need` one (all 32 lanes must call).  Every lane tries its
+// own attempt 0; then, round by round, the lanes that are done evaluate the NEXT attempts of the lanes that are not (an
+// attempt is a Philox block addressed by (pixel, sample, bounce, attempt): any lane can compute it).  With f failed lanes
+// each gets 32 / f attempts per round, so the loop ends after ~2 rounds instead of running until the unluckiest lane's
+// private loop does (acceptance pi/6: the slowest of 16 lanes needs ~5 attempts).  Same attempts in the same order as
+// random_in_unit_sphere: the first accepted attempt wins, bit-identical to the scalar loop (and to the oracle).
+// `scr`: 32 ints of per-warp shared memory.
+__constant__ uint32_t c_stride_mask[33] = {
+    0u, 0xffffffffu, 0x55555555u, 0x09249249u, 0x11111111u, 0x02108421u, 0x01041041u, 0x00204081u, 0x01010101u, 0x00040201u, 0x00100401u,
+    0x00000801u, 0x00001001u, 0x00002001u, 0x00004001u, 0x00008001u, 0x00010001u,
+    1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u, 1u};
+RTW_DEV V3 coop_unit_sphere(bool need, const PhiloxRng& g, int lane, int* scr) {
+    V3 p = mk(0.f, 0.f, 0.f);
+    bool ok = !need;
+    if (need) {
+        float x, y, z;
+        g.sphere_attempt(0u, x, y, z);
+        p = mk(-1.0f + 2.0f * x, -1.0f + 2.0f * y, -1.0f + 2.0f * z);
+        ok = length_squared(p) < 1.0f;
+    }
+    unsigned failed = __ballot_sync(0xffffffffu, !ok);
+    uint32_t base = 1u;
+#pragma unroll 1
+    while (failed) {
+        const int nf = __popc(failed);
+        const int idx = __popc(failed & ((1u << lane) - 1u));            // my index among the failed lanes (if I am one)
+        if (!ok) scr[idx] = lane;
+        __syncwarp();
+        const int j = __float2int_rz(((float)lane + 0.5f) * rcp_approx((float)nf));      // lane / nf
+        const int t = lane - j * nf;                                                     // lane % nf
+        const int per = __float2int_rz(32.5f * rcp_approx((float)nf));                    // attempts per failed lane this round
+        const int tgt = scr[t];
+        const uint32_t tp = __shfl_sync(0xffffffffu, g.pixel, tgt), ts = __shfl_sync(0xffffffffu, g.sample, tgt), tb = __shfl_sync(0xffffffffu, g.bounce, tgt);
+        float x, y, z;
+        philox_sphere_attempt(g.rk, base + (uint32_t)j, tb, tp, ts, x, y, z);
+        const V3 q = mk(-1.0f + 2.0f * x, -1.0f + 2.0f * y, -1.0f + 2.0f * z);
+        const bool okq = j < per && length_squared(q) < 1.0f;
+        const unsigned won = __ballot_sync(0xffffffffu, okq);
+        // the workers of failed lane #idx are lanes idx, idx + nf, idx + 2 nf, ...: the lowest one that accepted holds the
+        // earliest accepted attempt
+        const unsigned mine = won & (c_stride_mask[nf] << idx);
+        const bool got = !ok && mine != 0u;
+        const int src = got ? __ffs(mine) - 1 : lane;
+        const float qx = __shfl_sync(0xffffffffu, q.x, src), qy = __shfl_sync(0xffffffffu, q.y, src), qz = __shfl_sync(0xffffffffu, q.z, src);
+        if (got) { p = mk(qx, qy, qz); ok = true; }
+        base += (uint32_t)per;
+        failed = __ballot_sync(0xffffffffu, !ok);
+    }
+    return p;
 }
 template <class R> RTW_DEV V3 random_unit_vector(R& g) { return normalize(random_in_unit_sphere(g)); }   // :78-80
 
@@ -181,18 +254,28 @@ RTW_DEV V3 ray_at(const Ray& r, float t) { return mk(fmaf(t, r.d.x, r.o.x), fmaf
 // One loop, one next2() call site: pass 0 draws the pixel jitter (src/main.rs:518-519; skipped when the caller
 // supplies s, t), the next passes the lens-disk attempts, the last one the shutter time.
 template <bool JITTER, class R> RTW_DEV Ray camera_ray_loop(const DCamera& c, float s, float t, float px, float py, float wm1, float hm1, R& g) {
-    float rx = 0.f, ry = 0.f, tm = 0.f;
-    int phase = JITTER ? 0 : 1;
-#pragma unroll 1
-    for (;;) {
-        float a, b;
-        g.next2(a, b, phase == 2);
-        if (JITTER && phase == 0) { s = __fdividef(px + a, wm1); t = __fdividef(py + b, hm1); phase = 1; }    // 2 ulp: sub-pixel jitter
-        else if (phase == 1) {
-            rx = -1.0f + 2.0f * a; ry = -1.0f + 2.0f * b;
-            if (rx * rx + ry * ry < 1.0f) phase = 2;
-        } else { tm = c.time0 + (c.time1 - c.time0) * a; break; }
+    // scalar draws of bounce 0: pixel jitter u, v (src/main.rs:518-519), then the shutter time (camera.rs:64) — one block;
+    // the lens-disk loop draws pairs of attempts from its own blocks (stream layout above)
+    float tm;
+    if (JITTER) {
+        float a, b, d;
+        g.next3(a, b, d);
+        s = __fdividef(px + a, wm1); t = __fdividef(py + b, hm1);                             // 2 ulp: sub-pixel jitter
+        tm = c.time0 + (c.time1 - c.time0) * d;
     }
+    float rx = 0.f, ry = 0.f;
+#pragma unroll 1
+    for (uint32_t blk = 0;; ++blk) {
+        float x0, y0, x1, y1; bool second;
+        g.disk_pair(blk, x0, y0, x1, y1, second);
+        rx = -1.0f + 2.0f * x0; ry = -1.0f + 2.0f * y0;
+        if (rx * rx + ry * ry < 1.0f) break;
+        if (second) {
+            rx = -1.0f + 2.0f * x1; ry = -1.0f + 2.0f * y1;
+            if (rx * rx + ry * ry < 1.0f) break;
+        }
+    }
+    if (!JITTER) tm = c.time0 + (c.time1 - c.time0) * g.next();         // explicit stream: disk draws first, then the time
     rx *= c.lens_radius; ry *= c.lens_radius;
     V3 offset = mk(c.ux * rx + c.wx * ry, c.uy * rx + c.wy * ry, c.uz * rx + c.wz * ry);
     Ray r;
@@ -432,6 +515,30 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
     return tn <= tf;
 }
 
+// The same test with the near / far plane of each axis picked by ARITHMETIC instead of min / max: per ray and axis two
+// weights (inv, 0) or (0, inv) by the sign of the direction, so t_near = mn * w0 + mx * w1 - o/d (two FFMA, the zero
+// term is exact).  Moves 6 FMNMX per box from the ALU pipe (the busy one: ncu 60 %) to the FMA pipe (25 %).
+// Boxes must be finite (0 * inf); the builders never emit an infinite box into a reachable slot.
+#ifndef RTW_SLAB_FMA
+#define RTW_SLAB_FMA 0
+#endif
+struct SlabW { V3 w0, w1; };                       // w0 multiplies the min plane for t_near (and the max plane for t_far)
+RTW_DEV SlabW slab_weights(V3 inv) {
+    SlabW w;
+    w.w0 = mk(inv.x >= 0.f ? inv.x : 0.f, inv.y >= 0.f ? inv.y : 0.f, inv.z >= 0.f ? inv.z : 0.f);
+    w.w1 = mk(inv.x >= 0.f ? 0.f : inv.x, inv.y >= 0.f ? 0.f : inv.y, inv.z >= 0.f ? 0.f : inv.z);
+    return w;
+}
+RTW_DEV bool slab_w(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, const SlabW& w, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
+    const float nx = fmaf(mnx, w.w0.x, fmaf(mxx, w.w1.x, -oi.x)), fx = fmaf(mnx, w.w1.x, fmaf(mxx, w.w0.x, -oi.x));
+    const float ny = fmaf(mny, w.w0.y, fmaf(mxy, w.w1.y, -oi.y)), fy = fmaf(mny, w.w1.y, fmaf(mxy, w.w0.y, -oi.y));
+    const float nz = fmaf(mnz, w.w0.z, fmaf(mxz, w.w1.z, -oi.z)), fz = fmaf(mnz, w.w1.z, fmaf(mxz, w.w0.z, -oi.z));
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_lo));
+    const float tf = fmaf(fminf(fminf(fx, fy), fminf(fz, t_hi)), 1.0000006f, slack);
+    t_enter = tn;
+    return tn <= tf;
+}
+
 #define RTW_STACK 64
 #ifndef RTW_SPECULATIVE
 #define RTW_SPECULATIVE 1
@@ -459,6 +566,9 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
     if (sc.n_bvh_prims == 0) return;
     V3 inv, oi; float slack;
     slab_setup(r.o, r.d, inv, oi, slack);
+#if RTW_SLAB_FMA
+    const SlabW sw = slab_weights(inv);
+#endif
     int stack[RTW_STACK];
     stack[0] = RTW_SENTINEL;
     int* sp = stack + 1;                          // points at the next free entry
@@ -471,8 +581,13 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
             float e0, e1;
+#if RTW_SLAB_FMA
+            const bool h0 = slab_w(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sw, oi, slack, t_min, t_best, e0);
+            const bool h1 = slab_w(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sw, oi, slack, t_min, t_best, e1);
+#else
             const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, t_min, t_best, e0);
             const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, t_min, t_best, e1);
+#endif
             // straight-line child selection: nearer hit child next, the other one pushed
             const bool closer1 = e1 < e0;
             const bool second = h1 & (!h0 | closer1);
@@ -755,8 +870,10 @@ RTW_DEV V3 mat_color(const DScene& sc, const DMatRec& m, const HitRec& rec) {
 // Returns true when a scattered ray exists.  `emitted` is always written.
 // Lambertian, Metal and Isotropic all start with the same unit-ball rejection loop (src/math.rs:51-58): it is
 // hoisted to ONE call site so the lanes of a warp run it — and the Philox blocks behind it — together.
+RTW_DEV bool mat_needs_ball(int kind) { return kind != MAT_DIFFUSE_LIGHT && kind != MAT_DIELECTRIC; }
 template <class R, int F = FEAT_ALL>
-RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const HitRec& rec, R& g, Ray& scattered, V3& attenuation, V3& emitted) {
+RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const HitRec& rec, R& g, Ray& scattered, V3& attenuation, V3& emitted,
+                     const V3* ball_in = nullptr) {
     emitted = mk(0.f, 0.f, 0.f);
     scattered.o = rec.p; scattered.time = ray.time;
     const int kind = m.kind;
@@ -792,7 +909,7 @@ RTW_DEV bool scatter(const DScene& sc, const DMatRec& m, const Ray& ray, const H
         }
         return true;
     }
-    V3 ball = random_in_unit_sphere(g);                                                    // :37 / :52 / :85
+    const V3 ball = ball_in ? *ball_in : random_in_unit_sphere(g);                         // :37 / :52 / :85 (drawn by the warp: coop_unit_sphere)
     if (kind == MAT_LAMBERTIAN) {                                                          // :36-48
         V3 dir = rec.normal + normalize(ball);
         if (near_zero(dir)) dir = rec.normal;
@@ -877,29 +994,38 @@ RTW_DEV void path_begin(const DCamera& cam, const DParams& prm, int x, int y, in
 // Second half of one level of ray_color: media (list order, after the surfaces), miss -> background, otherwise
 // hit record + Material::emitted/scatter.  `tr`/(t_best, prim_best) = the segment's ray and its closest surface hit.
 // Returns true while the path continues; `add` = this level's radiance term (often 0).
-template <int F = FEAT_ALL>
-RTW_DEV bool path_finish(const DScene& sc, const DParams& prm, PathState& ps, const TRay& tr, float t_best, int prim_best, V3& add) {
+// COOP: called by ALL 32 lanes of the warp (`work` = this lane has a segment to finish); the unit-ball sample of the
+// lanes that need one is then drawn by the whole warp (coop_unit_sphere) — BEFORE the hit record is built, while few
+// values are live; the f64 copies of the ray are re-derived afterwards instead of being kept across the sampling loop.
+// !COOP: independent threads (parity hooks).
+RTW_DEV float opaque(float v) { asm volatile("" : "+f"(v)); return v; }
+template <int F = FEAT_ALL, bool COOP = false>
+RTW_DEV bool path_finish(const DScene& sc, const DParams& prm, PathState& ps, const TRay& tr, float t_best, int prim_best, V3& add,
+                         bool work = true, int lane = 0, int* scr = nullptr) {
     add = mk(0.f, 0.f, 0.f);
-    int med_mat = -1; float med_t = 0.f;
-    if (F & FEAT_MEDIA) for (int m = 0; m < sc.n_media; ++m) {
-        float t; int mat;
-        if (medium_hit(sc, m, tr, prm.t_min, t_best, ps.rng, t, mat)) { t_best = t; med_t = t; med_mat = mat; prim_best = -2; }
+    int med_mat = -1, mat = -1;
+    if (work) {
+        if (F & FEAT_MEDIA) for (int mi = 0; mi < sc.n_media; ++mi) {
+            float t; int mm;
+            if (medium_hit(sc, mi, tr, prm.t_min, t_best, ps.rng, t, mm)) { t_best = t; med_mat = mm; prim_best = -2; }
+        }
+        if (prim_best == -1) add = ps.T * mk(prm.bg_r, prm.bg_g, prm.bg_b);                // :37
+        else mat = ((F & FEAT_MEDIA) && prim_best == -2) ? med_mat : __ldg(&sc.prims[prim_best].mat);
     }
-    if (prim_best == -1) {                                                                 // :37
-        add = ps.T * mk(prm.bg_r, prm.bg_g, prm.bg_b);
-        return false;
-    }
-    HitRec rec; DMatRec m;
+    V3 ball = mk(0.f, 0.f, 0.f);
+    if (COOP) ball = coop_unit_sphere(mat >= 0 && mat_needs_ball(__ldg(&sc.mats[mat].kind)), ps.rng, lane, scr);
+    if (mat < 0) return false;
+    HitRec rec;
+    const DMatRec m = load_mat(sc, mat);                                                   // :26
     if ((F & FEAT_MEDIA) && prim_best == -2) {
-        rec.t = med_t; rec.p = ray_at(ps.ray, med_t); rec.normal = mk(1.f, 0.f, 0.f); rec.front = 1; rec.mat = med_mat; rec.u = 0.f; rec.v = 0.f;
-        m = load_mat(sc, med_mat);
-    } else {
-        int mat = __ldg(&sc.prims[prim_best].mat);
-        m = load_mat(sc, mat);                                                             // :26
-        finalize_hit<F>(sc, prim_best, t_best, tr, mat_needs_uv<F>(sc, m), rec);
-    }
+        rec.t = t_best; rec.p = ray_at(ps.ray, t_best); rec.normal = mk(1.f, 0.f, 0.f); rec.front = 1; rec.mat = med_mat; rec.u = 0.f; rec.v = 0.f;
+    } else if (COOP) {
+        Ray rr; rr.o = mk(opaque(ps.ray.o.x), opaque(ps.ray.o.y), opaque(ps.ray.o.z)); rr.d = mk(opaque(ps.ray.d.x), opaque(ps.ray.d.y), opaque(ps.ray.d.z));
+        rr.time = ps.ray.time;
+        finalize_hit<F>(sc, prim_best, t_best, make_tray(rr), mat_needs_uv<F>(sc, m), rec);
+    } else finalize_hit<F>(sc, prim_best, t_best, tr, mat_needs_uv<F>(sc, m), rec);
     Ray scattered; V3 att, em;
-    bool cont = scatter<PhiloxRng, F>(sc, m, ps.ray, rec, ps.rng, scattered, att, em);                  // :28-33
+    bool cont = scatter<PhiloxRng, F>(sc, m, ps.ray, rec, ps.rng, scattered, att, em, COOP ? &ball : nullptr);   // :28-33
     add = ps.T * em;
     if (!cont) return false;
     ps.T = ps.T * att;

@@ -374,7 +374,7 @@ def test_paths_match_oracle_and_golden(pkg, gpu, orc, name):
     radiance within 1e-3 relative for at least PATH_BARS of the paths (f32 vs f64 can only diverge at discrete
     decisions: rejection-loop acceptance, Schlick test, grazing hits, checker cell), equal means."""
     a, b, spec = build_both(pkg, gpu, orc, name)
-    g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_paths_v1.npz"))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_paths_v2.npz"))
     W, H = int(g["size"][0]), int(g["size"][1])
     p = pkg.make_params(W, H, 64, background=spec.background, seed=int(g["seed"]))
     ra, sa = a.trace_paths(spec.camera(gpu, W, H), p, g["px"], g["py"], g["sample"])

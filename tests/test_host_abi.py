@@ -247,9 +247,9 @@ def test_no_cpu_fallback(pkg, rtw):
 
 
 def test_golden_fixture_matches_oracle(pkg, orc):
-    """tests/golden/oracle_paths_v1.npz (made by tools/make_golden.py from THIS oracle) pins the restatement against
+    """tests/golden/oracle_paths_v2.npz (made by tools/make_golden.py from THIS oracle) pins the restatement against
     accidental edits: same scenes, same Philox keys, bit-identical radiance."""
-    path = os.path.join(ROOT, "tests", "golden", "oracle_paths_v1.npz")
+    path = os.path.join(ROOT, "tests", "golden", "oracle_paths_v2.npz")
     g = np.load(path)
     for name in pkg.scenes.SCENES:
         sc, spec = pkg.scenes.build(orc, name, wrap_bvh=name not in ("cornell_box_smoke", "final_scene"))

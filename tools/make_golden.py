@@ -1,4 +1,4 @@
-"""Generates tests/golden/oracle_paths_v1.npz: per-path radiance of fixed (pixel, sample) paths for every reference
+"""Generates tests/golden/oracle_paths_v2.npz: per-path radiance of fixed (pixel, sample) paths for every reference
 scene, computed by the CPU oracle (media_deferred order = the device's).  The reference itself cannot run here
 (Rust toolchain absent), so this fixture pins the ORACLE, and gives the GPU tests a committed target."""
 import os, sys
@@ -19,4 +19,4 @@ for name in m.scenes.SCENES:
     rgb, seg = sc.trace_paths(spec.camera(orc, W, H), p, px, py, sm)
     out[name + "_rgb"], out[name + "_seg"] = rgb, seg
     print(name, rgb.mean(), seg.mean())
-np.savez_compressed(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "oracle_paths_v1.npz"), **out)
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "..", "tests", "golden", "oracle_paths_v2.npz"), **out)
