@@ -178,7 +178,8 @@ def main():
         comm.barrier()                                   # barrier + cuda synchronize
         t0 = time.perf_counter()
         st = step()                                      # blocking: returns after the kernel's stream is synchronised
-        comm.barrier()
+        if world == 1:
+            comm.barrier()                               # (N > 1: the step itself ends with the barrier + cuda synchronize)
         wall += time.perf_counter() - t0
         dev_ms += st["ms_render"]
         rays += st["rays"]

@@ -182,6 +182,12 @@ int rtw_shared_open(rtw_scene*, int32_t width, int32_t height, const uint8_t han
 int rtw_shared_reset(rtw_scene*);
 /* every rank: pull tiles from the shared counter until exhausted, accumulate into the shared framebuffer */
 int rtw_render_shared(rtw_scene*, const rtw_camera*, const rtw_render_params*, rtw_stats* stats);
+/* The same without reset call and pre-launch barrier: epoch e renders into half (e & 1) of the shared allocation while
+ * rank 0 zeroes the other half for epoch e + 1.  Contract: every rank has returned from epoch e - 1 before any rank calls
+ * epoch e, and rank 0's device is synchronised in between (one barrier per step).  Epochs count up from 0 after
+ * rtw_shared_create / rtw_shared_open. */
+int rtw_render_shared_epoch(rtw_scene*, const rtw_camera*, const rtw_render_params*, int32_t epoch, rtw_stats* stats);
+int rtw_shared_read_epoch(rtw_scene*, int32_t epoch, float* out_rgb_sum);   /* rank 0: the image of that epoch */
 /* rank 0: copy the shared framebuffer to host */
 int rtw_shared_read(rtw_scene*, float* out_rgb_sum);
 int rtw_shared_close(rtw_scene*);

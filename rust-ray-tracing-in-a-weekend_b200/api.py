@@ -173,6 +173,8 @@ class Lib:
         f("shared_reset").argtypes = [vp]
         f("render_shared").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.POINTER(Stats)]
         f("shared_read").argtypes = [vp, fp]
+        f("render_shared_epoch").argtypes = [vp, C.POINTER(Camera), C.POINTER(RenderParams), C.c_int32, C.POINTER(Stats)]
+        f("shared_read_epoch").argtypes = [vp, C.c_int32, fp]
         f("shared_close").argtypes = [vp]
         f("host_alloc").argtypes = [C.c_uint64]
         f("host_alloc").restype = C.c_void_p

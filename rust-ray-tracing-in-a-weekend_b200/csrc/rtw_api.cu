@@ -441,12 +441,14 @@ struct Replica {
 };
 
 struct SharedFb {          // framebuffer + unit counter reachable by every GPU / rank
-    uint8_t* base = nullptr;     // [counter (256 B)] [fb floats]
+    uint8_t* base = nullptr;     // [counter 0 (128 B)] [counter 1 (128 B)] [fb 0 floats] ([fb 1 floats]: cross-process sharing only)
     size_t bytes = 0;
     int width = 0, height = 0;
     bool owner = false, ipc_mapped = false;
-    unsigned int* counter() const { return reinterpret_cast<unsigned int*>(base); }
-    float* fb() const { return reinterpret_cast<float*>(base + 256); }
+    cudaStream_t side = nullptr; // owner: zeroes the idle half while the other one is rendered into (rtw_render_shared_epoch)
+    size_t fb_bytes() const { return (((size_t)width * height * 3 * sizeof(float)) + 255) / 256 * 256; }
+    unsigned int* counter(int half = 0) const { return reinterpret_cast<unsigned int*>(base + 128 * half); }
+    float* fb(int half = 0) const { return reinterpret_cast<float*>(base + 256 + fb_bytes() * half); }
 };
 
 }  // namespace
@@ -1166,10 +1168,12 @@ int rtw_shared_create(rtw_scene* s, int32_t w, int32_t h, uint8_t handle[RTW_IPC
     if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "commit first");
     if (s->shared.base) rtw_shared_close(s);
     CUDA_TRY(cudaSetDevice(s->reps[0].device));
-    size_t need = 256 + (size_t)w * h * 3 * sizeof(float);
+    s->shared.width = w; s->shared.height = h;
+    size_t need = 256 + 2 * s->shared.fb_bytes();        // two halves: epochs alternate (rtw_render_shared_epoch)
     CUDA_TRY(cudaMalloc(&s->shared.base, need));
-    s->shared.bytes = need; s->shared.width = w; s->shared.height = h; s->shared.owner = true;
+    s->shared.bytes = need; s->shared.owner = true;
     CUDA_TRY(cudaMemset(s->shared.base, 0, need));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->shared.side, cudaStreamNonBlocking));
     IpcBlob b; std::memset(&b, 0, sizeof(b));
     CUDA_TRY(cudaIpcGetMemHandle(&b.h, s->shared.base));
     b.bytes = need; b.width = w; b.height = h; b.magic = 0x52545721u;
@@ -1196,6 +1200,36 @@ int rtw_shared_reset(rtw_scene* s) {
     CUDA_TRY(cudaDeviceSynchronize());
     return RTW_OK;
 }
+// One whole-image render per EPOCH without a reset call or a barrier before the launch: epoch e renders into half e & 1 of
+// the shared allocation (its own unit counter and framebuffer) while the owner zeroes the other half on a side stream for
+// epoch e + 1.  Contract: every rank has returned from epoch e - 1 before any rank calls epoch e (one barrier per step, which
+// a timed loop needs anyway), and the owner's device is synchronised before epoch e + 1 starts (the barrier's cuda
+// synchronize).  Replaces reset + barrier + render + barrier: one barrier per step instead of three.
+int rtw_render_shared_epoch(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, int32_t epoch, rtw_stats* st) {
+    if (!s || !cam || !p || !s->shared.base || epoch < 0) return fail(RTW_ERR_INVALID_ARG, "no shared framebuffer");
+    if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "rtw_scene_commit has not been called since the last edit");
+    if (p->width != s->shared.width || p->height != s->shared.height) return fail(RTW_ERR_INVALID_ARG, "size mismatch");
+    double t0 = now_ms();
+    const int half = epoch & 1;
+    int world = p->n_gpus > 0 ? p->n_gpus : 1;
+    DParams dp; TRY(make_params(*p, world * s->reps[0].grid * RTW_WARPS, dp));
+    dp.accumulate = 1;
+    if (st) { std::memset(st, 0, sizeof(*st)); fill_scene_stats(s, st); }
+    if (s->shared.owner) {                       // the idle half, for the next epoch (nobody touches it during this one)
+        CUDA_TRY(cudaSetDevice(s->reps[0].device));
+        CUDA_TRY(cudaMemsetAsync(s->shared.counter(half ^ 1), 0, 128, s->shared.side));
+        CUDA_TRY(cudaMemsetAsync(s->shared.fb(half ^ 1), 0, s->shared.fb_bytes(), s->shared.side));
+    }
+    TRY(launch_all(s, 1, cam, dp, s->shared.counter(half), s->shared.fb(half), st, kernel_mode(p->flags)));
+    if (st) { st->paths = (uint64_t)p->width * p->height * p->spp; st->ms_total = now_ms() - t0; }
+    return RTW_OK;
+}
+int rtw_shared_read_epoch(rtw_scene* s, int32_t epoch, float* out) {
+    if (!s || !out || !s->shared.base || epoch < 0) return fail(RTW_ERR_INVALID_ARG, "no shared framebuffer");
+    CUDA_TRY(cudaSetDevice(s->reps[0].device));
+    CUDA_TRY(cudaMemcpy(out, s->shared.fb(epoch & 1), (size_t)s->shared.width * s->shared.height * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RTW_OK;
+}
 int rtw_render_shared(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, rtw_stats* st) {
     if (!s || !cam || !p || !s->shared.base) return fail(RTW_ERR_INVALID_ARG, "no shared framebuffer");
     if (!s->committed) return fail(RTW_ERR_NOT_COMMITTED, "rtw_scene_commit has not been called since the last edit");
@@ -1218,6 +1252,7 @@ int rtw_shared_read(rtw_scene* s, float* out) {
 int rtw_shared_close(rtw_scene* s) {
     if (!s || !s->shared.base) return RTW_OK;
     if (!s->reps.empty()) cudaSetDevice(s->reps[0].device);
+    if (s->shared.side) { cudaStreamSynchronize(s->shared.side); cudaStreamDestroy(s->shared.side); }
     if (s->shared.ipc_mapped) cudaIpcCloseMemHandle(s->shared.base); else cudaFree(s->shared.base);
     s->shared = SharedFb();
     return RTW_OK;

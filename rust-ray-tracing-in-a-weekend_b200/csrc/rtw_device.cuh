@@ -113,7 +113,7 @@ RTW_DEV void philox4x32_10_rk(const uint32_t* __restrict__ rk, uint32_t c0, uint
     o0 = c0; o1 = c1; o2 = c2; o3 = c3;
 }
 
-// Stream layout (identical in oracle/oracle.cpp Rng): scalar draws of a bounce are words of blocks 0, 1, 2, ... of its
+// Stream layout (the CPU checker of the test suite uses the same one): scalar draws of a bounce are words of blocks 0, 1, 2, ... of its
 // counter line; the two rejection loops take their attempts from blocks of their own, indexed by the ATTEMPT: unit sphere
 // (src/math.rs:51-58) attempt a = words 0..2 of block 0x40000000 + a, unit disk (:69-76) attempt a = words 2(a & 1),
 // 2(a & 1) + 1 of block 0x20000000 + (a >> 1).  They do not advance the scalar stream.  Any lane can therefore evaluate any

@@ -81,7 +81,9 @@ class Comm:
 
 
 class SharedRender:
-    """Drives rtw_shared_* across ranks: create/open once, then step() = reset -> barrier -> render -> barrier."""
+    """Drives rtw_shared_* across ranks: create/open once, then step() = render epoch e -> barrier.  Epochs alternate between
+    the two halves of the shared allocation (rank 0 zeroes the idle half during the render), so a step needs no reset call
+    and no barrier before the launch: ONE barrier per step (it also is the contract's end-of-step synchronisation)."""
 
     def __init__(self, comm, scene, width, height, handle_bytes=160):
         import ctypes as C
@@ -95,25 +97,24 @@ class SharedRender:
             buf2 = (C.c_uint8 * handle_bytes).from_buffer_copy(raw)
             scene._c("shared_open", width, height, buf2)
         self.handle = raw
+        self.epoch = 0
         comm.barrier()
 
     def step(self, cam, params):
         """One whole-image render over all ranks.  Returns this rank's stats dict (ms_render = its device time)."""
         from .api import Stats
         C = self.C
-        if self.comm.rank == 0:
-            self.scene._c("shared_reset")
-        self.comm.barrier()
         st = Stats()
-        self.scene._c("render_shared", C.byref(cam), C.byref(params), C.byref(st))
-        self.comm.barrier()
+        self.scene._c("render_shared_epoch", C.byref(cam), C.byref(params), self.epoch, C.byref(st))
+        self.comm.barrier()                 # every rank is done with this epoch (and rank 0's side stream has zeroed the other half)
+        self.epoch += 1
         return st.as_dict()
 
     def read(self, out=None):
         assert self.comm.rank == 0
         if out is None:
             out = np.zeros((self.h, self.w, 3), np.float32)
-        self.scene._c("shared_read", out.ctypes.data_as(self.C.POINTER(self.C.c_float)))
+        self.scene._c("shared_read_epoch", max(self.epoch - 1, 0), out.ctypes.data_as(self.C.POINTER(self.C.c_float)))
         return out
 
     def close(self):

@@ -31,8 +31,9 @@ class FakeScene:
                 buf[i] = (i * 7 + 3) & 255
         if name == "shared_open":
             self.handle = bytes(a[2])
-        if name == "render_shared":
-            st = a[2]._obj
+        if name == "render_shared_epoch":
+            self.epochs = getattr(self, "epochs", []) + [a[2]]
+            st = a[3]._obj
             st.ms_render = 10.0 + self.rank
             st.rays = 100 * (self.rank + 1)
         return 0
@@ -58,11 +59,14 @@ def _worker(rank, world, port, q):
         assert sc.handle == want
     cam, prm = m.api.Camera(), m.make_params(64, 32, 4)
     st = sr.step(cam, prm)
+    sr.step(cam, prm)                            # a second epoch: the halves alternate, no reset call in between
+    if rank == 0:
+        sr.read()
     ms = comm.reduce_max(st["ms_render"])
     rays = comm.reduce_sum(st["rays"])
     sr.close()
     comm.close()
-    q.put((rank, sc.calls, ms, rays))
+    q.put((rank, sc.calls, ms, rays, sc.epochs))
 
 
 def test_two_rank_gloo_plumbing():
@@ -76,8 +80,9 @@ def test_two_rank_gloo_plumbing():
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    assert res[0][1] == ["shared_create", "shared_reset", "render_shared", "shared_close"]
-    assert res[1][1] == ["shared_open", "render_shared", "shared_close"]
+    assert res[0][1] == ["shared_create", "render_shared_epoch", "render_shared_epoch", "shared_read_epoch", "shared_close"]
+    assert res[1][1] == ["shared_open", "render_shared_epoch", "render_shared_epoch", "shared_close"]
+    assert res[0][4] == res[1][4] == [0, 1]       # every rank renders the same epoch (= the same half of the shared buffers)
     assert res[0][2] == res[1][2] == 11.0          # max over ranks of the device time
     assert res[0][3] == res[1][3] == 300.0
 
