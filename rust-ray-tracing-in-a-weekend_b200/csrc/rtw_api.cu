@@ -29,10 +29,10 @@ using namespace rtwd;
 // kernels
 // =================================================================================================
 #ifdef RTW_INSTRUMENT
-__device__ unsigned long long g_dbg_counters[6];
-extern "C" int rtw_debug_counters(unsigned long long out[6], int reset) {
-    if (cudaMemcpyFromSymbol(out, g_dbg_counters, 48) != cudaSuccess) return -3;
-    if (reset) { unsigned long long z[6] = {0}; cudaMemcpyToSymbol(g_dbg_counters, z, 48); }
+__device__ unsigned long long g_dbg_counters[8];     // [0..5] secondary steps (see below), [6] primary-ray primitive tests, [7] primary rays
+extern "C" int rtw_debug_counters(unsigned long long out[8], int reset) {
+    if (cudaMemcpyFromSymbol(out, g_dbg_counters, 64) != cudaSuccess) return -3;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbg_counters, z, 64); }
     return 0;
 }
 #endif
@@ -65,7 +65,7 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long rays = 0, units = 0;
 #ifdef RTW_INSTRUMENT
-    unsigned long long dbg[6] = {0, 0, 0, 0, 0, 0};
+    unsigned long long dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #endif
     PathState ps;
     ps.rng.bind(prm);                                          // key schedule: a constant-bank address, set once
@@ -177,7 +177,11 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
             // ---- media, miss, hit record, emitted + scatter (main.rs:26-37)
             bool cont = false;
             V3 add;
-            cont = path_finish<F, RTW_COOP != 0>(sc, prm, ps, tr, t_best, prim_best, add, work, lane, coop_scr[warp]);    // all 32 lanes
+            // unit-ball samples by the whole warp — except in the variants that carry the Perlin / image texture code, where
+            // the extra live state across the sampling loop costs more than the loop saves (measured: C1 -2.0 %, cornell_box
+            // -1.2 %, but final_scene +11 %, two_perlin_spheres +6 %: profiles/r2_d_ab_coop.log)
+            constexpr bool kCoop = RTW_COOP != 0 && !(F & (FEAT_NOISE | FEAT_IMAGE));
+            cont = path_finish<F, kCoop>(sc, prm, ps, tr, t_best, prim_best, add, work, lane, coop_scr[warp]);    // all 32 lanes
             if (work) {
                 ++rays;
                 if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
@@ -196,6 +200,10 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
                     as += __shfl_xor_sync(0xffffffffu, as, o);
                 }
                 if (lane == 0) { dbg[0] += 1; dbg[1] += as; dbg[2] += vs; dbg[3] += vm; dbg[4] += pss; dbg[5] += pm; }
+            } else {          // primary batch: every working lane tests the tile's candidate list (or traverses: counted in dbg_p)
+                const unsigned wm = __ballot_sync(0xffffffffu, work);
+                int p = dbg_p; for (int o = 16; o; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+                if (lane == 0) { dbg[6] += (unsigned long long)__popc(wm) * (unsigned long long)(list_n >= 0 ? list_n : 0) + (unsigned long long)p; dbg[7] += __popc(wm); }
             }
 #endif
             if (primary) {
@@ -221,7 +229,7 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
     for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
     if (lane == 0) { atomicAdd(stats, rays); atomicAdd(stats + 1, units); }
 #ifdef RTW_INSTRUMENT
-    if (lane == 0) for (int k = 0; k < 6; ++k) atomicAdd(&g_dbg_counters[k], dbg[k]);
+    if (lane == 0) for (int k = 0; k < 8; ++k) atomicAdd(&g_dbg_counters[k], dbg[k]);
 #endif
 }
 

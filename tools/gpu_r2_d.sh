@@ -12,3 +12,6 @@ for L in rust-ray-tracing-in-a-weekend_b200/librtw.so $V/occ8.so $V/occ9.so; do
   T=$(basename $L .so)
   RTW_LIB_PATH=$PWD/$L RTW_BVH=2 RTW_DEVICE_BUILD=0 timeout 900 python tools/sweep.py 1 4 --spp 32 2>&1 | sed "s/^/[$T] /" | tee -a gpurun_out/d_ab.log
 done
+RTW_LIB_PATH=$PWD/$V/instr.so timeout 600 python tools/flop_model_device.py 2>&1 | tail -4 | tee gpurun_out/flop_model_device.log
+cp profiles/flop_model.json gpurun_out/flop_model.json
+RTW_LIB_PATH=$PWD/$V/instr.so timeout 600 python tools/diag_div.py 2>&1 | tail -4 | tee gpurun_out/diag_div.log
