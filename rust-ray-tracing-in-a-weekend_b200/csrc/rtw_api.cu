@@ -72,7 +72,7 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
+        unit = __shfl_sync(0xffffffffu, unit, 0) * prm.unit_stride;
         if (unit >= prm.n_units) break;
         ++units;
         int tile, s0, s1;
@@ -591,15 +591,22 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
         // RTW_UNITS_PER_WARP / RTW_ONE_PHASE: tuning switches for tools/ab2.sh.
         static const bool one_phase = std::getenv("RTW_ONE_PHASE") != nullptr;
         static const char* wu = std::getenv("RTW_UNITS_PER_WARP");
-        const int spp_b = (p.spp >= 160 && !one_phase) ? p.spp / 5 : 0;
+        static const char* bspp = getenv("RTW_B_SPP");          // tuning (tools/ab_env.sh): phase-B unit size, share in %, phase-A minimum
+        static const char* bshare = getenv("RTW_B_SHARE");
+        static const char* amin = getenv("RTW_A_MIN");
+        const int spp_b = (p.spp >= 160 && !one_phase) ? (int)((long long)p.spp * (bshare ? atoi(bshare) : 20) / 100) : 0;
         d.spp_a = p.spp - spp_b;
         long long want_units = (wu ? atoll(wu) : 24LL) * total_warps;
+        if (const char* e = getenv("RTW_EMULATE_RANKS")) want_units *= std::max(1, atoi(e));
         long long chunks = (want_units + tiles - 1) / tiles;
         if (chunks < 1) chunks = 1;
         chunk = (int)((d.spp_a + chunks - 1) / chunks);
-        if (chunk < 32) chunk = 32;
+        const int a_min = amin ? std::max(1, atoi(amin)) : 32;
+        if (chunk < a_min) chunk = a_min;
         if (spp_b > 0) {
-            d.chunk_spp_b = chunk >= 64 ? 32 : 16;
+            // (8 when phase A already sits at its floor — the 8-GPU regime: the frame then ends ~0.3 ms earlier, measured with
+            // RTW_EMULATE_RANKS=8, profiles/r2_f_units.log; a warp needs ~1 ms of wall time per 32-sample unit at full residency)
+            d.chunk_spp_b = bspp ? std::max(1, atoi(bspp)) : (chunk >= 64 ? 32 : (chunk > a_min ? 16 : 8));
             d.chunks_b = (spp_b + d.chunk_spp_b - 1) / d.chunk_spp_b;
         }
     }
@@ -612,6 +619,8 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     d.n_units = (uint32_t)n_units;
     d.accumulate = 1;
     d.no_tile_cull = (p.flags & RTW_FLAG_NO_TILE_CULL) ? 1 : 0;
+    d.unit_stride = 1;
+    if (const char* e = getenv("RTW_EMULATE_RANKS")) d.unit_stride = (uint32_t)std::max(1, atoi(e));   // tuning aid: image incomplete
     return 0;
 }
 

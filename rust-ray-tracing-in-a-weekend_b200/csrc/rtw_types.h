@@ -134,6 +134,7 @@ struct DParams {
     int32_t no_tile_cull;              // 1: primary rays traverse the BVH like all others (RTW_FLAG_NO_TILE_CULL)
     int32_t first_sample;              // sample index of this launch's sample 0 (progressive passes / resume)
     uint32_t philox_rk[20];            // Philox4x32-10 key schedule of `seed` (round r: key + r * Weyl constants)
+    uint32_t unit_stride;              // 1; RTW_EMULATE_RANKS=k: this GPU takes every k-th unit only (tuning the k-GPU unit sizes on one GPU)
 };
 
 #endif

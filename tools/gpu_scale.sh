@@ -5,8 +5,8 @@ N=${1:-8}
 nvidia-smi -L | head -8
 for n in 1 2 4 8; do
   if [ $n -gt $N ]; then break; fi
-  if [ $n -eq 1 ]; then python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err
-  else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; fi
+  if [ $n -eq 1 ]; then python bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err
+  else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err; fi
   python - <<PY
 import json
 try:
