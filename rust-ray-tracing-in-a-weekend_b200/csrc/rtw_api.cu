@@ -235,7 +235,7 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
 
 // The warp-pool kernel (see rtw_pool.cuh): same work units, same Philox keys, same framebuffer protocol as
 // render_kernel — only the scheduling of the four stages differs.
-template <int POOL>
+template <int POOL, int W>
 __global__ void __launch_bounds__(RTW_BLOCK)
 render_pool_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
                    unsigned long long* __restrict__ stats) {
@@ -287,7 +287,7 @@ render_pool_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DC
             __syncwarp();
             if (n_trav == 0) break;                            // nothing alive and nothing left to start
             // ---- traverse (hittable.rs:43-55) + classify
-            rays += traverse_stage<POOL>(P, lane, lt_mask, n_trav, sc, prm, tile_x0, tile_y0);
+            rays += traverse_stage<POOL, W>(P, lane, lt_mask, n_trav, sc, prm, tile_x0, tile_y0);
             __syncwarp();
             // ---- shade, one dense loop per material kind (material.rs:15-94)
             shade_list<POOL, K_MISS>(P, lane, sc, prm, tile_x0, tile_y0);
@@ -443,7 +443,7 @@ struct Replica {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     unsigned long long* stats = nullptr;    // [0] rays [1] units
     int grid = 0;                           // megakernel grid (also sizes the work units)
-    int pool_grid[4] = {0, 0, 0, 0};        // warp-pool kernel grids for POOL = 64/128/192/256 (lazy)
+    int pool_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // warp-pool kernel grids for POOL = 64/128/192/256, binary then wide (lazy)
     int sms = 0;
     rtwb::BuildOutput built;                // device-built BVH + primitive records (own allocations, outside the blob)
 };
@@ -655,18 +655,22 @@ int kernel_mode(int flags) {
     return RTW_DEFAULT_MODE;
 }
 
-template <int POOL>
-int launch_pool(Replica& r, int slot, const DCamera& dc, const DParams& dp, unsigned int* counter, float* fb) {
+template <int POOL, int W>
+int launch_pool_w(Replica& r, int slot, const DCamera& dc, const DParams& dp, unsigned int* counter, float* fb) {
     const size_t smem = RTW_WARPS * sizeof(PoolSmem<POOL>);
     if (!r.pool_grid[slot]) {
-        CUDA_TRY(cudaFuncSetAttribute(render_pool_kernel<POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(render_pool_kernel<POOL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pool_kernel<POOL>, RTW_BLOCK, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_pool_kernel<POOL, W>, RTW_BLOCK, smem));
         if (per_sm < 1) return fail(RTW_ERR_CUDA, "warp-pool kernel does not fit on an SM");
         r.pool_grid[slot] = r.sms * per_sm;
     }
-    render_pool_kernel<POOL><<<r.pool_grid[slot], RTW_BLOCK, smem, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats);
+    render_pool_kernel<POOL, W><<<r.pool_grid[slot], RTW_BLOCK, smem, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats);
     return 0;
+}
+template <int POOL>
+int launch_pool(Replica& r, int slot, bool wide, const DCamera& dc, const DParams& dp, unsigned int* counter, float* fb) {
+    return wide ? launch_pool_w<POOL, 1>(r, slot + 4, dc, dp, counter, fb) : launch_pool_w<POOL, 0>(r, slot, dc, dp, counter, fb);
 }
 
 // Launch the render kernel on replicas [0, n) against (counter, fb); sync; fill stats.
@@ -684,13 +688,12 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         CUDA_TRY(cudaMemsetAsync(r.stats, 0, 32, r.stream));
         CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
         if (mode >= 1 && dp.first_sample + dp.spp > (1 << 17)) return fail(RTW_ERR_INVALID_ARG, "the pool kernel packs the sample index into 17 bits: spp <= 131072");
-        if (mode >= 1 && s->flat.wide) return fail(RTW_ERR_INVALID_ARG, "the pool kernel traverses binary nodes only (RTW_BVH=2)");
         if (mode >= 1 && s->flat.media.size() > 15) return fail(RTW_ERR_INVALID_ARG, "the pool kernel packs the media draw count into 4 bits: at most 15 media");
         switch (mode) {
-        case 1: TRY(launch_pool<64>(r, 0, dc, dp, counter, fb)); break;
-        case 2: TRY(launch_pool<128>(r, 1, dc, dp, counter, fb)); break;
-        case 3: TRY(launch_pool<192>(r, 2, dc, dp, counter, fb)); break;
-        case 4: TRY(launch_pool<256>(r, 3, dc, dp, counter, fb)); break;
+        case 1: TRY(launch_pool<64>(r, 0, s->flat.wide, dc, dp, counter, fb)); break;
+        case 2: TRY(launch_pool<128>(r, 1, s->flat.wide, dc, dp, counter, fb)); break;
+        case 3: TRY(launch_pool<192>(r, 2, s->flat.wide, dc, dp, counter, fb)); break;
+        case 4: TRY(launch_pool<256>(r, 3, s->flat.wide, dc, dp, counter, fb)); break;
         default: {
             // smallest kernel variant that covers the scene's features (code size = instruction-cache pressure)
             const int f = s->flat.features;
@@ -972,13 +975,14 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     if (first_device < 0 || n_gpus < 1 || first_device + n_gpus > ndev || n_gpus > 8) return fail(RTW_ERR_INVALID_ARG, "device range not available");
     double t0 = now_ms();
     std::string err;
-    // Where the BVH is built.  Scenes beyond the cache-resident range (RTW_DEVICE_BUILD_MIN primitives, default 32768) are
-    // built ON THE DEVICE from what the constructors were given (bvh_build.cu); small ones keep the host SAH builder
-    // (C1: 1 ms, better trees).  RTW_DEVICE_BUILD=0 / 1 forces either.
+    // Where the BVH is built.  Big scenes (RTW_DEVICE_BUILD_MIN primitives, default 2 Mi) are built ON THE DEVICE from what the
+    // constructors were given (bvh_build.cu): 16 M spheres commit in 0.24 s instead of 5.1 s; the LBVH renders ~6 % slower than
+    // the host's binned-SAH tree, which pays from ~2 M primitives on at 256 spp (profiles/r2_c_sweep_device_build.log).  Small
+    // scenes keep the host SAH builder (C1: 1 ms, better trees).  RTW_DEVICE_BUILD=0 / 1 forces either.
     rtw::FlattenOptions fo;
     {
         long long n_guess = (long long)s->g.bulk.size() + (long long)s->g.nodes.size();
-        long long dev_min = 32768;
+        long long dev_min = 2 << 20;
         if (const char* e = getenv("RTW_DEVICE_BUILD_MIN")) dev_min = atoll(e);
         fo.emit_only = n_guess >= dev_min;
         if (const char* e = getenv("RTW_DEVICE_BUILD")) fo.emit_only = atoi(e) != 0;
@@ -1010,7 +1014,7 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FEAT_ALL, 0>, RTW_BLOCK, 0));
             if (per_sm < 1) per_sm = 1;
             r.grid = sms * per_sm; r.sms = sms;
-            for (int k = 0; k < 4; ++k) r.pool_grid[k] = 0;
+            for (int k = 0; k < 8; ++k) r.pool_grid[k] = 0;
             if (i > 0) {   // peers write the framebuffer / counter that live on the first device
                 int can = 0; CUDA_TRY(cudaDeviceCanAccessPeer(&can, r.device, first_device));
                 if (!can) return fail(RTW_ERR_CUDA, "peer access to the first device is not available");

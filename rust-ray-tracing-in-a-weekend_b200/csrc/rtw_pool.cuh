@@ -105,7 +105,9 @@ RTW_DEV void shade_list(PoolSmem<POOL>& P, int lane, const DScene& sc, const DPa
 #define RTW_FETCH_THRESHOLD 24      // leave the traversal loop to refill idle lanes once fewer lanes than this are busy
 
 // The traverse stage over P.trav[0..n_trav).  Dynamic fetch: lanes pull the next slot as soon as their ray is done.
-template <int POOL>
+// W = 0: binary nodes (speculative while-while); W = 1: the 8-wide compressed BVH (bvh_wide.h) — its visits are long
+// (8 quantised slab tests) and few, which is where keeping every lane supplied with rays pays most.
+template <int POOL, int W>
 RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned lt_mask, int n_trav, const DScene& sc, const DParams& prm,
                                           int tile_x0, int tile_y0) {
     unsigned long long rays = 0;
@@ -114,8 +116,12 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
     int slot = 0;
     TRay r; V3 inv = mk(0, 0, 0), oi = mk(0, 0, 0); float slack = 0.f;
     float t_best = 0.f; int prim_best = -1, skip = -1;
-    int stack[RTW_STACK]; int sp = 1, node = RTW_SENTINEL, leaf = 0;
-    stack[0] = RTW_SENTINEL;
+    // binary: stack of node ids (sentinel at the bottom); wide: stack of (base, group) pairs
+    uint32_t stack[RTW_STACK]; int sp = 1, node = RTW_SENTINEL, leaf = 0;
+    uint32_t wbase = 0, wgrp = 0; rtww::WRay wr; wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31); wr.k = 0; wr.slack = 0.f;
+    wr.ix = wr.iy = wr.iz = wr.oix = wr.oiy = wr.oiz = 0.f;
+    bool done = true;
+    stack[0] = (uint32_t)RTW_SENTINEL;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !active);
         if (idle && q_next < n_trav) {
@@ -127,7 +133,11 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                     r = make_tray(ray);
                     slab_setup(r.o, r.d, inv, oi, slack);
                     t_best = CUDART_INF_F; prim_best = -1; skip = P.last[slot];
-                    sp = 1; leaf = 0; node = sc.n_bvh_prims ? 0 : RTW_SENTINEL;
+                    if (W) {
+                        wr.ix = inv.x; wr.iy = inv.y; wr.iz = inv.z; wr.oix = oi.x; wr.oiy = oi.y; wr.oiz = oi.z; wr.slack = slack;
+                        wr.k = ((inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u)) ^ 7u;
+                        sp = 0; wbase = 0; wgrp = sc.n_bvh_prims ? ((1u << 8) | (1u << wr.k)) : 0u; done = false;
+                    } else { sp = 1; leaf = 0; node = sc.n_bvh_prims ? 0 : RTW_SENTINEL; }
                     active = true; ++rays;
                 }
             }
@@ -135,6 +145,39 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
         }
         if (!__any_sync(0xffffffffu, active)) break;
         if (active) {
+            if (W) {
+                while (!done) {
+                    if (!(wgrp & 0xffu)) {
+                        if (sp == 0) { done = true; break; }
+                        sp -= 2; wbase = stack[sp]; wgrp = stack[sp + 1];
+                        continue;
+                    }
+                    const int j = 31 - __clz(wgrp & 0xffu);
+                    wgrp ^= 1u << j;
+                    const uint32_t sl = (uint32_t)j ^ wr.k;
+                    const uint32_t nd = wbase + __popc((wgrp >> 8) & ((1u << sl) - 1u));
+                    if (wgrp & 0xffu) { stack[sp] = wbase; stack[sp + 1] = wgrp; sp += 2; }
+                    const uint4* np = reinterpret_cast<const uint4*>(sc.wnodes + nd);
+                    const uint4 h = __ldg(np), m = __ldg(np + 1), qa = __ldg(np + 2), qb = __ldg(np + 3), qc = __ldg(np + 4);
+                    const uint32_t imask = h.w >> 24, lmask = m.z & 0xffu;
+                    uint32_t hits = rtww::wide_node_hits(*reinterpret_cast<const rtww::W4*>(&h), *reinterpret_cast<const rtww::W4*>(&qa),
+                                                         *reinterpret_cast<const rtww::W4*>(&qb), *reinterpret_cast<const rtww::W4*>(&qc), wr, prm.t_min, t_best);
+                    hits &= imask | lmask;
+                    const uint32_t m16 = rtww::wide_perm16((hits & imask) | ((hits & lmask) << 8), wr.k);
+                    uint32_t pl = m16 >> 8;
+                    while (pl) {
+                        const int jj = 31 - __clz(pl);
+                        pl ^= 1u << jj;
+                        const uint32_t s2 = (uint32_t)jj ^ wr.k;
+                        const int pi = (int)(m.y + __popc(lmask & ((1u << s2) - 1u)));
+                        const float t = prim_root(sc, pi, r, prm.t_min, t_best, skip);
+                        if (t == t) { t_best = t; prim_best = pi; }
+                    }
+                    wbase = m.x; wgrp = (imask << 8) | (m16 & 0xffu);
+                    if (q_next < n_trav && __popc(__activemask()) < RTW_FETCH_THRESHOLD) break;   // refill idle lanes
+                }
+                node = done ? RTW_SENTINEL : 0;                                                    // (the result code below keys on node)
+            } else {
             while (node != RTW_SENTINEL) {
                 bool searching = true;
                 while (node >= 0 && node != RTW_SENTINEL) {
@@ -144,16 +187,16 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                     float e0, e1;
                     bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, prm.t_min, t_best, e0);
                     bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, prm.t_min, t_best, e1);
-                    if (!h0 && !h1) node = stack[--sp];
+                    if (!h0 && !h1) node = (int)stack[--sp];
                     else {
                         node = h0 ? n3.x : n3.y;
                         if (h0 && h1) {
                             int farc = n3.y;
                             if (e1 < e0) { farc = node; node = n3.y; }
-                            stack[sp++] = farc;
+                            stack[sp++] = (uint32_t)farc;
                         }
                     }
-                    if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = stack[--sp]; }
+                    if (node < 0 && leaf >= 0) { searching = false; leaf = node; node = (int)stack[--sp]; }
                     if (!__any_sync(__activemask(), searching)) break;
                 }
                 while (leaf < 0) {
@@ -163,9 +206,10 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                         if (t == t) { t_best = t; prim_best = first + i; }
                     }
                     leaf = node;
-                    if (node < 0) node = stack[--sp];
+                    if (node < 0) node = (int)stack[--sp];
                 }
                 if (q_next < n_trav && __popc(__activemask()) < RTW_FETCH_THRESHOLD) break;   // refill idle lanes
+            }
             }
             if (node == RTW_SENTINEL) {
                 // ray done: media (list order, after the surfaces), classification, result
