@@ -30,11 +30,20 @@ using namespace rtwd;
 // =================================================================================================
 #ifdef RTW_INSTRUMENT
 __device__ unsigned long long g_dbg_counters[8];     // [0..5] secondary steps (see below), [6] primary-ray primitive tests, [7] primary rays
+// warp timeline of the last launch (ns, %globaltimer): [0] first warp start, [1] last warp start, [2] sum of warp end times,
+// [3] last warp end, [4] warps, [5] first warp end
+__device__ unsigned long long g_dbg_time[6] = {~0ull, 0, 0, 0, 0, ~0ull};
 extern "C" int rtw_debug_counters(unsigned long long out[8], int reset) {
     if (cudaMemcpyFromSymbol(out, g_dbg_counters, 64) != cudaSuccess) return -3;
     if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_dbg_counters, z, 64); }
     return 0;
 }
+extern "C" int rtw_debug_timeline(unsigned long long out[6]) {
+    if (cudaMemcpyFromSymbol(out, g_dbg_time, 48) != cudaSuccess) return -3;
+    unsigned long long z[6] = {~0ull, 0, 0, 0, 0, ~0ull}; cudaMemcpyToSymbol(g_dbg_time, z, 48);
+    return 0;
+}
+__device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #endif
 #define RTW_BLOCK 128
 #define RTW_WARPS (RTW_BLOCK / 32)
@@ -69,6 +78,9 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
 #endif
     PathState ps;
     ps.rng.bind(prm);                                          // key schedule: a constant-bank address, set once
+#ifdef RTW_INSTRUMENT
+    if (lane == 0) { const unsigned long long t = dbg_now(); atomicMin(&g_dbg_time[0], t); atomicMax(&g_dbg_time[1], t); }
+#endif
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
@@ -230,6 +242,7 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
     if (lane == 0) { atomicAdd(stats, rays); atomicAdd(stats + 1, units); }
 #ifdef RTW_INSTRUMENT
     if (lane == 0) for (int k = 0; k < 8; ++k) atomicAdd(&g_dbg_counters[k], dbg[k]);
+    if (lane == 0) { const unsigned long long t = dbg_now(); atomicAdd(&g_dbg_time[2], t); atomicMax(&g_dbg_time[3], t); atomicAdd(&g_dbg_time[4], 1ull); atomicMin(&g_dbg_time[5], t); }
 #endif
 }
 
