@@ -712,6 +712,25 @@ def test_two_gpus_in_process(pkg, gpu):
     assert np.abs(one - two).max() <= 2e-4 * one.max()
 
 
+@pytest.mark.parametrize("width", [2, 8])
+def test_two_gpus_in_process_device_built_scene(pkg, gpu, monkeypatch, width):
+    """A scene whose BVH is built ON THE DEVICE (bvh_build.cu) is built once on the first GPU and copied to the other
+    replica over NVLink: the two-GPU image equals the one-GPU image, both GPUs work."""
+    if gpu.f("device_count")() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("RTW_BVH", str(width))
+    monkeypatch.setenv("RTW_DEVICE_BUILD", "1")
+    sc = pkg.Scene(gpu)
+    spec = pkg.scenes.sweep_scene(sc, 50000, seed=2)
+    sc.commit(2, 0)
+    cam = spec.camera(gpu, 960, 540)                  # enough units that the second GPU's kernel finds work when it starts
+    one, st1 = sc.render(cam, pkg.make_params(960, 540, 64, background=spec.background, n_gpus=1))
+    two, st2 = sc.render(cam, pkg.make_params(960, 540, 64, background=spec.background, n_gpus=2))
+    assert st2["n_devices"] == 2 and min(st2["units_per_device"][:2]) > 0.2 * sum(st2["units_per_device"])
+    assert st1["rays"] == st2["rays"] and st2["n_prims"] == 50000
+    assert np.abs(one - two).max() <= 2e-4 * one.max()
+
+
 @pytest.mark.parametrize("scene_id,name", [(0, "random_scene"), (5, "cornell_box"), (7, "final_scene")])
 def test_cpp_mirror_main_matches_python_path(pkg, gpu, scene_id, name, tmp_path):
     """The replacement main (host/rtw_main.cpp: reference constructors -> flatten -> rtw_render -> write_color -> P3)
