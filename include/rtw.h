@@ -77,6 +77,7 @@ typedef struct rtw_render_params {
 #define RTW_FLAG_KERNEL_MEGA 2  /* force the one-path-per-lane megakernel */
 #define RTW_FLAG_NO_TILE_CULL 8 /* diagnostic: skip the per-tile candidate lists, primary rays traverse the BVH (same image) */
 #define RTW_FLAG_KERNEL_POOL 4  /* force the warp-pool (shared-memory wavefront) kernel; default: chosen by measurement */
+#define RTW_FLAG_KERNEL_WAVEFRONT 16 /* force the global-memory wavefront pipeline (path pool in HBM, dynamic ray fetch) */
 
 typedef struct rtw_stats {
     double ms_render;           /* CUDA-event time of the render kernels, max over devices */

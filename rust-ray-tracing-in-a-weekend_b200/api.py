@@ -24,6 +24,7 @@ RTW_FLAG_DEVICE_OUT = 1
 RTW_FLAG_KERNEL_MEGA = 2     # one path per lane (default: measured faster)
 RTW_FLAG_KERNEL_POOL = 4     # warp-pool / shared-memory wavefront variant
 RTW_FLAG_NO_TILE_CULL = 8    # diagnostic: no per-tile candidate lists
+RTW_FLAG_KERNEL_WAVEFRONT = 16   # global-memory wavefront pipeline (path pool in HBM, dynamic ray fetch)
 
 STATUS = {0: "OK", -1: "INVALID_ARG", -2: "UNSUPPORTED_NESTING", -3: "CUDA_ERROR", -4: "OOM",
           -5: "NO_DEVICE", -6: "NOT_COMMITTED"}

@@ -15,12 +15,14 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rtw.h"
 #include "bvh_build.hpp"
 #include "rtw_device.cuh"
 #include "rtw_pool.cuh"
+#include "rtw_wavefront.cuh"
 #include "scene_host.hpp"
 
 using namespace rtwd;
@@ -459,6 +461,9 @@ struct Replica {
     int pool_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // warp-pool kernel grids for POOL = 64/128/192/256, binary then wide (lazy)
     int sms = 0;
     rtwb::BuildOutput built;                // device-built BVH + primitive records (own allocations, outside the blob)
+    WfPool wf{};                            // wavefront path pool (lazy; rtw_wavefront.cuh)
+    uint8_t* wf_mem = nullptr;
+    int wf_grid[4] = {0, 0, 0, 0};          // trace kernel grids: [F != 0][W]
 };
 
 struct SharedFb {          // framebuffer + unit counter reachable by every GPU / rank
@@ -496,6 +501,7 @@ void free_replicas(rtw_scene* s) {
         cudaSetDevice(r.device);
         if (r.blob) cudaFree(r.blob);
         rtwb::free_output(r.built);
+        if (r.wf_mem) cudaFree(r.wf_mem);
         if (r.stats) cudaFree(r.stats);
         if (r.ev0) cudaEventDestroy(r.ev0);
         if (r.ev1) cudaEventDestroy(r.ev1);
@@ -660,8 +666,10 @@ int kernel_mode(int flags) {
             else if (!strcmp(e, "pool128")) env_mode = 2;
             else if (!strcmp(e, "pool192")) env_mode = 3;
             else if (!strcmp(e, "pool256")) env_mode = 4;
+            else if (!strcmp(e, "wavefront")) env_mode = 5;
         }
     }
+    if (flags & RTW_FLAG_KERNEL_WAVEFRONT) return 5;
     if (flags & RTW_FLAG_KERNEL_MEGA) return 0;
     if (flags & RTW_FLAG_KERNEL_POOL) return RTW_DEFAULT_POOL_MODE;
     if (env_mode >= 0) return env_mode;
@@ -686,6 +694,103 @@ int launch_pool(Replica& r, int slot, bool wide, const DCamera& dc, const DParam
     return wide ? launch_pool_w<POOL, 1>(r, slot + 4, dc, dp, counter, fb) : launch_pool_w<POOL, 0>(r, slot, dc, dp, counter, fb);
 }
 
+// ---- wavefront pipeline (rtw_wavefront.cuh): pool allocation + the iteration loop -------------------------------------
+int wf_ensure_pool(Replica& r, long long want_slots) {
+    long long P = 8ll << 20;                                         // slots in flight per GPU (RTW_WF_POOL overrides)
+    if (const char* e = getenv("RTW_WF_POOL")) P = std::max(1024ll, atoll(e));
+    P = std::min(P, std::max(1024ll, want_slots));
+    P = (P + RTW_WF_BLOCK - 1) / RTW_WF_BLOCK * RTW_WF_BLOCK;
+    if (r.wf_mem && r.wf.P == (int)P) return 0;
+    if (r.wf_mem) { CUDA_TRY(cudaFree(r.wf_mem)); r.wf_mem = nullptr; }
+    const int max_chunks = 1 << 16;                                  // 2^16 chunks x 2^20 paths: more than spp <= 2^20 at 8K needs
+    const size_t per_slot = 4 * sizeof(float4) + 2 * sizeof(uint2);
+    const size_t bytes = (size_t)P * per_slot + 256 + (size_t)max_chunks * 8;
+    CUDA_TRY(cudaMalloc(&r.wf_mem, bytes));
+    uint8_t* p = r.wf_mem;
+    r.wf.od0 = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
+    r.wf.od1 = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
+    r.wf.thr = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
+    r.wf.rad = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
+    r.wf.id = reinterpret_cast<uint2*>(p); p += (size_t)P * 8;
+    r.wf.hit = reinterpret_cast<uint2*>(p); p += (size_t)P * 8;
+    r.wf.ctr = reinterpret_cast<unsigned long long*>(p); p += 256;
+    r.wf.chunk_base = reinterpret_cast<unsigned long long*>(p);
+    r.wf.P = (int)P; r.wf.max_chunks = max_chunks;
+    return 0;
+}
+
+template <int F, int W>
+int wf_run(rtw_scene* s, Replica& r, const DCamera& dc, const DParams& dp, unsigned long long* path_counter, unsigned long long total_paths, float* fb) {
+    int& grid = r.wf_grid[(F ? 2 : 0) + W];
+    if (!grid) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<F, W>, 128, 0));
+        grid = r.sms * std::max(per_sm, 1);
+    }
+    const WfPool pool = r.wf;
+    CUDA_TRY(cudaMemsetAsync(pool.rad, 0, (size_t)pool.P * sizeof(float4), r.stream));     // every slot EMPTY
+    CUDA_TRY(cudaMemsetAsync(pool.ctr, 0, 256, r.stream));
+    const int lgrid = pool.P / RTW_WF_BLOCK;
+    unsigned long long h[8];
+    for (long long it = 0;; ++it) {
+        // a batch of iterations, then one look at the counters (the only host round trip)
+        for (int k = 0; k < 8; ++k) {
+            wf_reserve_kernel<<<1, 1, 0, r.stream>>>(pool, path_counter, total_paths);
+            wf_logic_kernel<F><<<lgrid, RTW_WF_BLOCK, 0, r.stream>>>(r.ds, dc, dp, pool, total_paths, fb);
+            wf_trace_kernel<F, W><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(h, pool.ctr, sizeof(h), cudaMemcpyDeviceToHost, r.stream));
+        CUDA_TRY(cudaStreamSynchronize(r.stream));
+        // done: no slot holds a ray, the shared counter is exhausted and every reserved path number was handed out
+        if (h[1] == 0 && h[6] && h[0] >= (h[4] << RTW_WF_CHUNK_LOG2)) break;
+        if (it > (1ll << 24)) return fail(RTW_ERR_CUDA, "wavefront loop did not terminate");
+    }
+    (void)s;
+    return 0;
+}
+
+int wf_render_replica(rtw_scene* s, Replica& r, const DCamera& dc, const DParams& dp, unsigned int* counter, float* fb, double& ms, uint64_t& rays, uint64_t& paths) {
+    CUDA_TRY(cudaSetDevice(r.device));
+    const unsigned long long total = (unsigned long long)dp.tiles_x * dp.tiles_y * 32ull * (unsigned long long)dp.spp;
+    TRY(wf_ensure_pool(r, (long long)std::min<unsigned long long>(total, 1ull << 40)));
+    unsigned long long* path_counter = reinterpret_cast<unsigned long long*>(counter) + 1;     // second word of the zeroed header
+    CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
+    const bool plain = s->flat.features == 0;
+    int rc;
+    if (s->flat.wide) rc = plain ? wf_run<0, 1>(s, r, dc, dp, path_counter, total, fb) : wf_run<FEAT_ALL, 1>(s, r, dc, dp, path_counter, total, fb);
+    else rc = plain ? wf_run<0, 0>(s, r, dc, dp, path_counter, total, fb) : wf_run<FEAT_ALL, 0>(s, r, dc, dp, path_counter, total, fb);
+    if (rc < 0) return rc;
+    CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
+    CUDA_TRY(cudaStreamSynchronize(r.stream));
+    float e = 0; CUDA_TRY(cudaEventElapsedTime(&e, r.ev0, r.ev1));
+    unsigned long long h[8];
+    CUDA_TRY(cudaMemcpy(h, r.wf.ctr, sizeof(h), cudaMemcpyDeviceToHost));
+    ms = e; rays = h[3]; paths = h[5];
+    return 0;
+}
+
+int launch_wavefront(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp, unsigned int* counter, float* fb, rtw_stats* st) {
+    const DCamera dc = to_dcamera(*cam);
+    std::vector<double> ms(n_rep, 0.0); std::vector<uint64_t> rays(n_rep, 0), paths(n_rep, 0); std::vector<int> rc(n_rep, 0);
+    std::vector<std::string> errs(n_rep);
+    if (n_rep == 1) rc[0] = wf_render_replica(s, s->reps[0], dc, dp, counter, fb, ms[0], rays[0], paths[0]);
+    else {                                       // one host thread per GPU: each drives its own iteration loop
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_rep; ++i)
+            th.emplace_back([&, i]() { rc[i] = wf_render_replica(s, s->reps[i], dc, dp, counter, fb, ms[i], rays[i], paths[i]); if (rc[i] < 0) errs[i] = g_err; });
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < n_rep; ++i) if (rc[i] < 0) return fail(rc[i], errs[i].empty() ? g_err : errs[i]);
+    if (st) {
+        double m = 0; uint64_t r = 0;
+        for (int i = 0; i < n_rep; ++i) { m = std::max(m, ms[i]); r += rays[i]; if (i < 8) st->units_per_device[i] = paths[i]; }
+        st->ms_render = m; st->rays = r; st->n_devices = n_rep;
+        st->kernel_launches += n_rep;       // (three small kernels per iteration; counted as one render per device)
+    }
+    return 0;
+}
+
 // Launch the render kernel on replicas [0, n) against (counter, fb); sync; fill stats.
 // Everything a launch needs (scene pointers, camera, the Philox key schedule) travels in its kernel parameters: renders
 // on different scene handles share no mutable state and may run concurrently from different host threads.
@@ -694,6 +799,7 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
     // time outside that interval could be culled where the reference's flat world list would still hit: refuse it.
     if (std::min(cam->time0, cam->time1) < s->flat.mov_t0 || std::max(cam->time0, cam->time1) > s->flat.mov_t1)
         return fail(RTW_ERR_INVALID_ARG, "camera shutter [time0, time1] exceeds the [time0, time1] of a MovingSphere in the scene");
+    if (mode == 5) return launch_wavefront(s, n_rep, cam, dp, counter, fb, st);
     DCamera dc = to_dcamera(*cam);
     for (int i = 0; i < n_rep; ++i) {
         Replica& r = s->reps[i];
@@ -1107,7 +1213,7 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     TRY(ensure_fb(s->local, r0.device, dev_out ? 1 : p->width, dev_out ? 1 : p->height));
     float* fb = dev_out ? out : s->local.fb();
     CUDA_TRY(cudaSetDevice(r0.device));
-    dp.accumulate = (n_rep > 1 || dp.chunks + dp.chunks_b > 1) ? 1 : 0;
+    dp.accumulate = (n_rep > 1 || dp.chunks + dp.chunks_b > 1 || kernel_mode(p->flags) == 5) ? 1 : 0;   // (wavefront: finished paths are ADDED)
     CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
     if (dp.accumulate) CUDA_TRY(cudaMemsetAsync(fb, 0, fb_bytes, r0.stream));
     if (n_rep > 1) CUDA_TRY(cudaStreamSynchronize(r0.stream));   // peers must see the zeroed buffers

@@ -943,3 +943,57 @@ def test_device_bvh_build_equals_host_build(pkg, gpu, monkeypatch, name, width):
     assert sa["rays"] == sb["rays"] or abs(sa["rays"] - sb["rays"]) <= 1e-4 * sa["rays"]
     assert np.abs(ia - ib).max() <= 1e-3 * max(1.0, np.abs(ia).max())
     assert sb["n_nodes"] > 0 and sb["n_prims"] == sa["n_prims"]
+
+
+@pytest.mark.parametrize("width", [2, 8])
+@pytest.mark.parametrize("name", list(PATH_BARS) + ["sweep_30000"])
+def test_wavefront_pipeline_equals_megakernel(pkg, gpu, monkeypatch, name, width):
+    """The wavefront pipeline (csrc/rtw_wavefront.cuh: path pool in HBM, logic kernel = shade + regenerate, persistent trace
+    kernel with dynamic ray fetch) schedules the SAME per-(pixel, sample) paths as the megakernel — same Philox
+    coordinates, same device functions for ray_color's stages (src/main.rs:19-38) — so the images agree up to f32 summation
+    order and the ray counts are equal.  Both node formats, every scene, ragged image sizes, a pool smaller than the image
+    (several regeneration rounds) and a progressive pass with a sample offset."""
+    monkeypatch.setenv("RTW_BVH", str(width))
+    monkeypatch.setenv("RTW_WF_POOL", "20000")          # far fewer slots than paths: regeneration is exercised
+    if name.startswith("sweep_"):
+        sc = pkg.Scene(gpu)
+        spec = pkg.scenes.sweep_scene(sc, int(name[6:]), seed=4)
+    else:
+        sc, spec = pkg.scenes.build(gpu, name)
+    sc.commit(1, 0)
+    W, H, spp = 101, 67, 24                             # ragged tiles on both axes
+    cam = spec.camera(gpu, W, H)
+    mega, sm = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=6, flags=pkg.api.RTW_FLAG_KERNEL_MEGA))
+    wave, sw = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=6, flags=pkg.api.RTW_FLAG_KERNEL_WAVEFRONT))
+    assert sw["rays"] == sm["rays"] and sw["paths"] == W * H * spp
+    assert sum(sw["units_per_device"]) == W * H * spp                       # (wavefront: paths started per device)
+    assert np.isfinite(wave).all()
+    assert np.abs(wave - mega).max() <= 2e-4 * max(1.0, np.abs(mega).max())
+    # max_depth 0 / 1 corner cases
+    for depth in (0, 1):
+        a, _ = sc.render(cam, pkg.make_params(W, H, 4, max_depth=depth, background=spec.background, flags=pkg.api.RTW_FLAG_KERNEL_MEGA))
+        b, _ = sc.render(cam, pkg.make_params(W, H, 4, max_depth=depth, background=spec.background, flags=pkg.api.RTW_FLAG_KERNEL_WAVEFRONT))
+        assert np.abs(a - b).max() <= 2e-4 * max(1.0, np.abs(a).max())
+
+
+def test_wavefront_progressive_and_two_gpus(pkg, gpu, monkeypatch):
+    """Progressive passes (absolute sample index = Philox coordinate) and, when a second GPU is there, path chunks taken by
+    two GPUs from the one shared counter: the image is the one-shot single-GPU image."""
+    monkeypatch.setenv("RTW_WF_POOL", "50000")
+    sc, spec = pkg.scenes.build(gpu, "random_scene")
+    n = 2 if gpu.f("device_count")() >= 2 else 1
+    sc.commit(n, 0)
+    W, H, spp = 320, 200, 48
+    cam = spec.camera(gpu, W, H)
+    F = pkg.api.RTW_FLAG_KERNEL_WAVEFRONT
+    one, s1 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=3, n_gpus=1, flags=F))
+    prog, s2 = sc.render_progressive(cam, pkg.make_params(W, H, spp, background=spec.background, seed=3, n_gpus=1, flags=F), samples_per_pass=20)
+    assert np.abs(prog - one).max() <= 2e-4 * one.max() and s2["paths"] == W * H * spp
+    if n == 2:
+        monkeypatch.setenv("RTW_WF_POOL", "400000")
+        W, H, spp = 1200, 800, 16                      # 15.4 M paths = 15 chunks of 2^20: both GPUs get some
+        cam = spec.camera(gpu, W, H)
+        a, sa = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=3, n_gpus=1, flags=F))
+        b, sb = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=3, n_gpus=2, flags=F))
+        assert sa["rays"] == sb["rays"] and min(sb["units_per_device"][:2]) > 0
+        assert np.abs(a - b).max() <= 2e-4 * a.max()
