@@ -192,7 +192,7 @@ struct W4 { uint32_t x, y, z, w; };              // one 16-byte word of a node (
 struct WRay {
     float ix, iy, iz;                            // 1 / d (zero components replaced, rtw_device.cuh slab_dir)
     float oix, oiy, oiz;                         // o / d
-    float slack;                                 // absolute slack for the rounding of o / d (slab_slack)
+    float sx, sy, sz;                            // per-axis absolute slack for the rounding of o / d: 4 ulp of |o/d| (slab_setup_wide)
     uint32_t k;                                  // 7 ^ octant, octant bit a = (d[a] < 0)
     uint32_t one;                                // 0x3F800000 held in a REGISTER: PRMT takes one immediate, and it must be
                                                  // the byte selector (with the constant as immediate every PRMT needs a MOV)
@@ -218,14 +218,14 @@ template <int C> RTW_HD float wide_plane_f(uint32_t word, uint32_t one) {
 // A plane at p + q step is at ray parameter  t = (p - o) / d + q step / d.  With f = 1 + q 2^-15 taken straight from
 // the byte (wide_plane_f), t = f A + B,  A = 2^15 step / d,  B = (p - o) / d - A: ONE FFMA per plane, no integer ->
 // float conversion.  Rounding: B carries 2^-24 |A| = 2^-9 step / d (covered by RTW_WIDE_PADQ at build time) plus errors
-// relative to t and to o / d (covered by the 10-ulp exit padding and `slack`, like the BVH2 slab test).
+// relative to t (covered by the 10-ulp exit padding) and to o / d (covered per axis by sx, sy, sz, like the BVH2 slab test).
 // Near / far planes are picked per AXIS for four children at a time (the sign of d selects the lo or the hi word).
 template <int C> RTW_HD uint32_t wide_child_hit(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t fx, uint32_t fy, uint32_t fz, float Ax, float Ay,
-                                               float Az, float Bx, float By, float Bz, float slack, float t_lo, float t_hi, uint32_t one) {
-    const float tnx = fmaf(wide_plane_f<C>(nx, one), Ax, Bx), tny = fmaf(wide_plane_f<C>(ny, one), Ay, By), tnz = fmaf(wide_plane_f<C>(nz, one), Az, Bz);
-    const float tfx = fmaf(wide_plane_f<C>(fx, one), Ax, Bx), tfy = fmaf(wide_plane_f<C>(fy, one), Ay, By), tfz = fmaf(wide_plane_f<C>(fz, one), Az, Bz);
+                                               float Az, float Bnx, float Bny, float Bnz, float Bfx, float Bfy, float Bfz, float t_lo, float t_hi, uint32_t one) {
+    const float tnx = fmaf(wide_plane_f<C>(nx, one), Ax, Bnx), tny = fmaf(wide_plane_f<C>(ny, one), Ay, Bny), tnz = fmaf(wide_plane_f<C>(nz, one), Az, Bnz);
+    const float tfx = fmaf(wide_plane_f<C>(fx, one), Ax, Bfx), tfy = fmaf(wide_plane_f<C>(fy, one), Ay, Bfy), tfz = fmaf(wide_plane_f<C>(fz, one), Az, Bfz);
     const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, t_lo));
-    const float tf = fmaf(fminf(fminf(tfx, tfy), fminf(tfz, t_hi)), 1.0000012f, slack);
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, t_hi)) * 1.0000012f;
     return tn <= tf ? 1u : 0u;
 }
 RTW_HD uint32_t wide_node_hits(const W4& h, const W4& qa, const W4& qb, const W4& qc, const WRay& r, float t_lo, float t_hi) {
@@ -234,20 +234,21 @@ RTW_HD uint32_t wide_node_hits(const W4& h, const W4& qa, const W4& qb, const W4
     const float Ay = r.iy * wide_bits_to_float((((h.w >> 8) & 0xffu) + 15u) << 23);
     const float Az = r.iz * wide_bits_to_float((((h.w >> 16) & 0xffu) + 15u) << 23);
     const float Bx = fmaf(px, r.ix, -r.oix) - Ax, By = fmaf(py, r.iy, -r.oiy) - Ay, Bz = fmaf(pz, r.iz, -r.oiz) - Az;
+    const float Bnx = Bx - r.sx, Bny = By - r.sy, Bnz = Bz - r.sz, Bfx = Bx + r.sx, Bfy = By + r.sy, Bfz = Bz + r.sz;   // near planes earlier, far planes later
     const bool gx = r.ix < 0.0f, gy = r.iy < 0.0f, gz = r.iz < 0.0f;
     // words: qa = lox[0-3] lox[4-7] loy[0-3] loy[4-7];  qb = loz[0-3] loz[4-7] hix[0-3] hix[4-7];  qc = hiy hiy hiz hiz
     const uint32_t nx0 = gx ? qb.z : qa.x, nx1 = gx ? qb.w : qa.y, fx0 = gx ? qa.x : qb.z, fx1 = gx ? qa.y : qb.w;
     const uint32_t ny0 = gy ? qc.x : qa.z, ny1 = gy ? qc.y : qa.w, fy0 = gy ? qa.z : qc.x, fy1 = gy ? qa.w : qc.y;
     const uint32_t nz0 = gz ? qc.z : qb.x, nz1 = gz ? qc.w : qb.y, fz0 = gz ? qb.x : qc.z, fz1 = gz ? qb.y : qc.w;
     uint32_t hits = 0;
-    hits |= wide_child_hit<0>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one);
-    hits |= wide_child_hit<1>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one) << 1;
-    hits |= wide_child_hit<2>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one) << 2;
-    hits |= wide_child_hit<3>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one) << 3;
-    hits |= wide_child_hit<0>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one) << 4;
-    hits |= wide_child_hit<1>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one) << 5;
-    hits |= wide_child_hit<2>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one) << 6;
-    hits |= wide_child_hit<3>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bx, By, Bz, r.slack, t_lo, t_hi, r.one) << 7;
+    hits |= wide_child_hit<0>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one);
+    hits |= wide_child_hit<1>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one) << 1;
+    hits |= wide_child_hit<2>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one) << 2;
+    hits |= wide_child_hit<3>(nx0, ny0, nz0, fx0, fy0, fz0, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one) << 3;
+    hits |= wide_child_hit<0>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one) << 4;
+    hits |= wide_child_hit<1>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one) << 5;
+    hits |= wide_child_hit<2>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one) << 6;
+    hits |= wide_child_hit<3>(nx1, ny1, nz1, fx1, fy1, fz1, Ax, Ay, Az, Bnx, Bny, Bnz, Bfx, Bfy, Bfz, t_lo, t_hi, r.one) << 7;
     return hits;
 }
 

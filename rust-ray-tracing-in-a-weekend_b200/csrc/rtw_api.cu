@@ -9,6 +9,7 @@
 // kernel).  Replaces src/main.rs:497-589.  DESIGN.md 4.1 has the measurements behind each choice.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -377,10 +378,10 @@ __global__ void aabb_kernel(int n, const double* __restrict__ bmin, const double
     if (i >= n) return;
     V3 ro = mk((float)o[3 * i], (float)o[3 * i + 1], (float)o[3 * i + 2]);
     V3 rd = mk((float)d[3 * i], (float)d[3 * i + 1], (float)d[3 * i + 2]);
-    V3 inv, oi; float slack, e;
-    slab_setup(ro, rd, inv, oi, slack);
+    V3 inv, cmn, cmx; float e;
+    slab_setup(ro, rd, inv, cmn, cmx);
     hit[i] = slab((float)bmin[3 * i], (float)bmax[3 * i], (float)bmin[3 * i + 1], (float)bmax[3 * i + 1], (float)bmin[3 * i + 2],
-                  (float)bmax[3 * i + 2], inv, oi, slack, t_min, t_max, e) ? 1 : 0;
+                  (float)bmax[3 * i + 2], inv, cmn, cmx, t_min, t_max, e) ? 1 : 0;
 }
 
 __global__ void scatter_kernel(DScene sc, int mat, int n, const double* __restrict__ ro, const double* __restrict__ rd, const double* __restrict__ rt,
@@ -704,7 +705,7 @@ int wf_ensure_pool(Replica& r, long long want_slots) {
     if (r.wf_mem) { CUDA_TRY(cudaFree(r.wf_mem)); r.wf_mem = nullptr; }
     const int max_chunks = 1 << 16;                                  // 2^16 chunks x 2^20 paths: more than spp <= 2^20 at 8K needs
     const size_t per_slot = 4 * sizeof(float4) + 2 * sizeof(uint2);
-    const size_t bytes = (size_t)P * per_slot + 256 + (size_t)max_chunks * 8;
+    const size_t bytes = (size_t)P * per_slot + 256 + (size_t)max_chunks * 8 + 3 * 8192 * 8;
     CUDA_TRY(cudaMalloc(&r.wf_mem, bytes));
     uint8_t* p = r.wf_mem;
     r.wf.od0 = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
@@ -714,7 +715,8 @@ int wf_ensure_pool(Replica& r, long long want_slots) {
     r.wf.id = reinterpret_cast<uint2*>(p); p += (size_t)P * 8;
     r.wf.hit = reinterpret_cast<uint2*>(p); p += (size_t)P * 8;
     r.wf.ctr = reinterpret_cast<unsigned long long*>(p); p += 256;
-    r.wf.chunk_base = reinterpret_cast<unsigned long long*>(p);
+    r.wf.chunk_base = reinterpret_cast<unsigned long long*>(p); p += (size_t)max_chunks * 8;
+    r.wf.dbg = reinterpret_cast<unsigned long long*>(p);
     r.wf.P = (int)P; r.wf.max_chunks = max_chunks;
     return 0;
 }
@@ -727,6 +729,7 @@ int wf_run(rtw_scene* s, Replica& r, const DCamera& dc, const DParams& dp, unsig
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<F, W>, 128, 0));
         grid = r.sms * std::max(per_sm, 1);
     }
+    static const bool lockstep = !(getenv("RTW_WF_TRACE") && !strcmp(getenv("RTW_WF_TRACE"), "whilewhile"));
     const WfPool pool = r.wf;
     CUDA_TRY(cudaMemsetAsync(pool.rad, 0, (size_t)pool.P * sizeof(float4), r.stream));     // every slot EMPTY
     CUDA_TRY(cudaMemsetAsync(pool.ctr, 0, 256, r.stream));
@@ -737,13 +740,31 @@ int wf_run(rtw_scene* s, Replica& r, const DCamera& dc, const DParams& dp, unsig
         for (int k = 0; k < 8; ++k) {
             wf_reserve_kernel<<<1, 1, 0, r.stream>>>(pool, path_counter, total_paths);
             wf_logic_kernel<F><<<lgrid, RTW_WF_BLOCK, 0, r.stream>>>(r.ds, dc, dp, pool, total_paths, fb);
-            wf_trace_kernel<F, W><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
+            if (lockstep && W) wf_trace2w_kernel<F><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
+            else if (lockstep) wf_trace2_kernel<F><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
+            else wf_trace_kernel<F, W><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
         }
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(h, pool.ctr, sizeof(h), cudaMemcpyDeviceToHost, r.stream));
         CUDA_TRY(cudaStreamSynchronize(r.stream));
+#ifdef RTW_INSTRUMENT
+        if (getenv("RTW_WF_TIMELINE") && it < 4) {
+            std::vector<unsigned long long> d(3 * 8192);
+            cudaMemcpy(d.data(), pool.dbg, d.size() * 8, cudaMemcpyDeviceToHost);
+            const int nw = std::min(8192, grid * 4);
+            unsigned long long t0 = ~0ull, t1 = 0; for (int w = 0; w < nw; ++w) { t0 = std::min(t0, d[w]); t1 = std::max(t1, d[8192 + w]); }
+            std::vector<double> ends; unsigned long long rmin = ~0ull, rmax = 0, rsum = 0;
+            for (int w = 0; w < nw; ++w) { ends.push_back((d[8192 + w] - t0) * 1e-6); rmin = std::min(rmin, d[16384 + w]); rmax = std::max(rmax, d[16384 + w]); rsum += d[16384 + w]; }
+            std::sort(ends.begin(), ends.end());
+            fprintf(stderr, "[wf timeline] launch after %lld iterations: %d warps, end times ms: min %.3f p10 %.3f p50 %.3f p90 %.3f p99 %.3f max %.3f; rays per warp min %llu mean %.0f max %llu\n",
+                    (it + 1) * 8, nw, ends.front(), ends[nw / 10], ends[nw / 2], ends[nw * 9 / 10], ends[nw * 99 / 100], ends.back(), rmin, (double)rsum / nw, rmax);
+        }
+#endif
         // done: no slot holds a ray, the shared counter is exhausted and every reserved path number was handed out
-        if (h[1] == 0 && h[6] && h[0] >= (h[4] << RTW_WF_CHUNK_LOG2)) break;
+        if (h[1] == 0 && h[6] && h[0] >= (h[4] << RTW_WF_CHUNK_LOG2)) {
+            if (getenv("RTW_TIMING")) fprintf(stderr, "[wavefront] %lld iterations, %llu rays, %llu paths, pool %d\n", (it + 1) * 8, h[3], h[5], pool.P);
+            break;
+        }
         if (it > (1ll << 24)) return fail(RTW_ERR_CUDA, "wavefront loop did not terminate");
     }
     (void)s;

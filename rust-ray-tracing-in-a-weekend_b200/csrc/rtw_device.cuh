@@ -487,54 +487,44 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
 }
 
 // AABB::hit (src/aabb.rs:77-103) for the two children of a node, with precomputed 1/d and o/d.  Conservative: closed
-// interval, boxes rounded outward, and the exit distance padded by 5 ulp (Ize, "Robust BVH ray traversal": 2 ulp for
-// correctly rounded 1/d; 3 more for MUFU.RCP) PLUS an absolute slack of 4 ulp of max|o/d| — the fma form t = p*inv - o*inv carries the rounding of o*inv, which is not
-// relative to t when the origin is far from the box.  The f32 test can then never cull a primitive the f64 reference
-// would hit; the primitive tests decide.  `slack` is per ray (see slab_slack), folded into one FFMA.
-RTW_DEV float slab_slack(V3 oi) { return 2.384185791015625e-07f * fmaxf(fmaxf(fabsf(oi.x), fabsf(oi.y)), fabsf(oi.z)); }
-// Per-ray constants of the slab test.  1/d from MUFU.RCP (relative error <= 2^-23): the SAME inv feeds o*inv, so the
-// error is purely relative on every plane distance and is covered by widening Ize's 2-ulp exit padding to 5 ulp.
+// interval, boxes rounded outward, the exit distance padded by 5 ulp (Ize, "Robust BVH ray traversal": 2 ulp for
+// correctly rounded 1/d; 3 more for MUFU.RCP) and the rounding of o/d covered per axis (slab_setup).  The f32 test can
+// then never cull a primitive the f64 reference would hit; the primitive tests decide.
+// Per-ray constants of the slab test.  1/d from MUFU.RCP (relative error <= 2^-23): the SAME inv feeds o*inv, so that error
+// is purely relative on every plane distance and is covered by widening Ize's 2-ulp exit padding to 5 ulp.  The ABSOLUTE
+// error — the rounding of o/d, 2^-24 |o/d| on a plane distance of ANY size — is covered per axis by folding 4 ulp of
+// |o_k/d_k| into the addends of the two FFMAs of that axis: cmn (used with a box's min plane) and cmx (max plane) are
+// -o/d moved outward — the near plane's distance shrinks, the far plane's grows, whichever sign d has.  No extra
+// instruction per box; and no term shared between axes: a shared slack taken from an axis along which the ray hardly
+// moves (|d_k| = 1e-7 |d|: o_k/d_k is 1e7 times the other axes' distances) opened every box on the other two axes, and such
+// a ray walked a whole slice of a 1 M-sphere scene (found as multi-millisecond straggler rays in the wavefront trace kernel).
 // A direction component of exactly +-0 (axis-parallel test rays; 2^-24 of the scatter draws) would give inv = +-inf and
 // plane distances inf - inf = NaN for a box that straddles the origin's coordinate — fmaxf/fminf drop the NaN and the
 // test MISSES a box the ray runs inside of (the reference's AABB::hit handles the infinities, src/aabb.rs:77-103).
 // Such a component is replaced by +-1e-20: every plane distance stays finite, the origin's side of each slab decides.
-// Its o/d (~1e20 |o|) is kept out of the shared slack term, which would otherwise open every box on the other two axes.
 RTW_DEV float slab_dir(float d) { return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; }
-RTW_DEV void slab_setup(V3 o, V3 d, V3& inv, V3& oi, float& slack) {
+RTW_DEV void slab_setup(V3 o, V3 d, V3& inv, V3& cmn, V3& cmx) {
     inv = mk(rcp_approx(slab_dir(d.x)), rcp_approx(slab_dir(d.y)), rcp_approx(slab_dir(d.z)));
-    oi = mk(o.x * inv.x, o.y * inv.y, o.z * inv.z);
-    slack = slab_slack(mk(fabsf(d.x) < 1e-20f ? 0.f : oi.x, fabsf(d.y) < 1e-20f ? 0.f : oi.y, fabsf(d.z) < 1e-20f ? 0.f : oi.z));
+    const V3 oi = mk(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    const float k = 2.384185791015625e-07f;                                  // 4 ulp
+    const V3 s = mk(copysignf(k * fabsf(oi.x), inv.x), copysignf(k * fabsf(oi.y), inv.y), copysignf(k * fabsf(oi.z), inv.z));
+    cmn = mk(-oi.x - s.x, -oi.y - s.y, -oi.z - s.z);
+    cmx = mk(-oi.x + s.x, -oi.y + s.y, -oi.z + s.z);
 }
-RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
-    float x0 = fmaf(mnx, inv.x, -oi.x), x1 = fmaf(mxx, inv.x, -oi.x);
-    float y0 = fmaf(mny, inv.y, -oi.y), y1 = fmaf(mxy, inv.y, -oi.y);
-    float z0 = fmaf(mnz, inv.z, -oi.z), z1 = fmaf(mxz, inv.z, -oi.z);
+// the same for the wide node test (bvh_wide.h): o/d and the per-axis absolute slack
+RTW_DEV void slab_setup_wide(V3 o, V3 d, rtww::WRay& wr) {
+    wr.ix = rcp_approx(slab_dir(d.x)); wr.iy = rcp_approx(slab_dir(d.y)); wr.iz = rcp_approx(slab_dir(d.z));
+    wr.oix = o.x * wr.ix; wr.oiy = o.y * wr.iy; wr.oiz = o.z * wr.iz;
+    const float k = 2.384185791015625e-07f;
+    wr.sx = k * fabsf(wr.oix); wr.sy = k * fabsf(wr.oiy); wr.sz = k * fabsf(wr.oiz);
+    wr.k = ((wr.ix < 0.0f ? 1u : 0u) | (wr.iy < 0.0f ? 2u : 0u) | (wr.iz < 0.0f ? 4u : 0u)) ^ 7u;
+}
+RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 cmn, V3 cmx, float t_lo, float t_hi, float& t_enter) {
+    float x0 = fmaf(mnx, inv.x, cmn.x), x1 = fmaf(mxx, inv.x, cmx.x);
+    float y0 = fmaf(mny, inv.y, cmn.y), y1 = fmaf(mxy, inv.y, cmx.y);
+    float z0 = fmaf(mnz, inv.z, cmn.z), z1 = fmaf(mxz, inv.z, cmx.z);
     float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
-    float tf = fmaf(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)), 1.0000006f, slack);
-    t_enter = tn;
-    return tn <= tf;
-}
-
-// The same test with the near / far plane of each axis picked by ARITHMETIC instead of min / max: per ray and axis two
-// weights (inv, 0) or (0, inv) by the sign of the direction, so t_near = mn * w0 + mx * w1 - o/d (two FFMA, the zero
-// term is exact).  Moves 6 FMNMX per box from the ALU pipe (the busy one: ncu 60 %) to the FMA pipe (25 %).
-// Boxes must be finite (0 * inf); the builders never emit an infinite box into a reachable slot.
-#ifndef RTW_SLAB_FMA
-#define RTW_SLAB_FMA 0
-#endif
-struct SlabW { V3 w0, w1; };                       // w0 multiplies the min plane for t_near (and the max plane for t_far)
-RTW_DEV SlabW slab_weights(V3 inv) {
-    SlabW w;
-    w.w0 = mk(inv.x >= 0.f ? inv.x : 0.f, inv.y >= 0.f ? inv.y : 0.f, inv.z >= 0.f ? inv.z : 0.f);
-    w.w1 = mk(inv.x >= 0.f ? 0.f : inv.x, inv.y >= 0.f ? 0.f : inv.y, inv.z >= 0.f ? 0.f : inv.z);
-    return w;
-}
-RTW_DEV bool slab_w(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, const SlabW& w, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
-    const float nx = fmaf(mnx, w.w0.x, fmaf(mxx, w.w1.x, -oi.x)), fx = fmaf(mnx, w.w1.x, fmaf(mxx, w.w0.x, -oi.x));
-    const float ny = fmaf(mny, w.w0.y, fmaf(mxy, w.w1.y, -oi.y)), fy = fmaf(mny, w.w1.y, fmaf(mxy, w.w0.y, -oi.y));
-    const float nz = fmaf(mnz, w.w0.z, fmaf(mxz, w.w1.z, -oi.z)), fz = fmaf(mnz, w.w1.z, fmaf(mxz, w.w0.z, -oi.z));
-    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, t_lo));
-    const float tf = fmaf(fminf(fminf(fx, fy), fminf(fz, t_hi)), 1.0000006f, slack);
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)) * 1.0000006f;
     t_enter = tn;
     return tn <= tf;
 }
@@ -564,11 +554,8 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
 #endif
                          ) {
     if (sc.n_bvh_prims == 0) return;
-    V3 inv, oi; float slack;
-    slab_setup(r.o, r.d, inv, oi, slack);
-#if RTW_SLAB_FMA
-    const SlabW sw = slab_weights(inv);
-#endif
+    V3 inv, cmn, cmx;
+    slab_setup(r.o, r.d, inv, cmn, cmx);
     int stack[RTW_STACK];
     stack[0] = RTW_SENTINEL;
     int* sp = stack + 1;                          // points at the next free entry
@@ -588,13 +575,8 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
             float e0, e1;
-#if RTW_SLAB_FMA
-            const bool h0 = slab_w(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, sw, oi, slack, t_min, t_best, e0);
-            const bool h1 = slab_w(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, sw, oi, slack, t_min, t_best, e1);
-#else
-            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, t_min, t_best, e0);
-            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, t_min, t_best, e1);
-#endif
+            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, cmn, cmx, t_min, t_best, e0);
+            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, cmn, cmx, t_min, t_best, e1);
             // straight-line child selection: nearer hit child next, the other one pushed
             const bool closer1 = e1 < e0;
             const bool second = h1 & (!h0 | closer1);
@@ -648,11 +630,9 @@ RTW_DEV void bvh8_closest(const DScene& sc, const TRay& r, float t_min, float& t
 #endif
                           ) {
     if (sc.n_bvh_prims <= 0) return;
-    V3 inv, oi; rtww::WRay wr;
-    slab_setup(r.o, r.d, inv, oi, wr.slack);
-    wr.ix = inv.x; wr.iy = inv.y; wr.iz = inv.z; wr.oix = oi.x; wr.oiy = oi.y; wr.oiz = oi.z;
-    const uint32_t k = ((inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u)) ^ 7u;
-    wr.k = k;
+    rtww::WRay wr;
+    slab_setup_wide(r.o, r.d, wr);
+    const uint32_t k = wr.k;
     wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31);           // = 0x3F800000, but opaque to the compiler (see WRay::one)
     uint2 stack[RTW_WIDE_STACK];
     int sp = 0;

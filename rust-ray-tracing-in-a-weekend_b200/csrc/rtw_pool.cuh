@@ -114,11 +114,11 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
     int q_next = 0;
     bool active = false;
     int slot = 0;
-    TRay r; V3 inv = mk(0, 0, 0), oi = mk(0, 0, 0); float slack = 0.f;
+    TRay r; V3 inv = mk(0, 0, 0), cmn = mk(0, 0, 0), cmx = mk(0, 0, 0);
     float t_best = 0.f; int prim_best = -1, skip = -1;
     // binary: stack of node ids (sentinel at the bottom); wide: stack of (base, group) pairs
     uint32_t stack[RTW_STACK]; int sp = 1, node = RTW_SENTINEL, leaf = 0;
-    uint32_t wbase = 0, wgrp = 0; rtww::WRay wr; wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31); wr.k = 0; wr.slack = 0.f;
+    uint32_t wbase = 0, wgrp = 0; rtww::WRay wr; wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31); wr.k = 0; wr.sx = wr.sy = wr.sz = 0.f;
     wr.ix = wr.iy = wr.iz = wr.oix = wr.oiy = wr.oiz = 0.f;
     bool done = true;
     stack[0] = (uint32_t)RTW_SENTINEL;
@@ -131,11 +131,10 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                     slot = P.trav[k];
                     Ray ray; ray.o = mk(P.ox[slot], P.oy[slot], P.oz[slot]); ray.d = mk(P.dx[slot], P.dy[slot], P.dz[slot]); ray.time = P.tm[slot];
                     r = make_tray(ray);
-                    slab_setup(r.o, r.d, inv, oi, slack);
+                    slab_setup(r.o, r.d, inv, cmn, cmx);
                     t_best = CUDART_INF_F; prim_best = -1; skip = P.last[slot];
                     if (W) {
-                        wr.ix = inv.x; wr.iy = inv.y; wr.iz = inv.z; wr.oix = oi.x; wr.oiy = oi.y; wr.oiz = oi.z; wr.slack = slack;
-                        wr.k = ((inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u)) ^ 7u;
+                        slab_setup_wide(r.o, r.d, wr);
                         sp = 0; wbase = 0; wgrp = sc.n_bvh_prims ? ((1u << 8) | (1u << wr.k)) : 0u; done = false;
                     } else { sp = 1; leaf = 0; node = sc.n_bvh_prims ? 0 : RTW_SENTINEL; }
                     active = true; ++rays;
@@ -185,8 +184,8 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                     float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
                     int4 n3 = __ldg(reinterpret_cast<const int4*>(np + 3));
                     float e0, e1;
-                    bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, prm.t_min, t_best, e0);
-                    bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, prm.t_min, t_best, e1);
+                    bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, cmn, cmx, prm.t_min, t_best, e0);
+                    bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, cmn, cmx, prm.t_min, t_best, e1);
                     if (!h0 && !h1) node = (int)stack[--sp];
                     else {
                         node = h0 ? n3.x : n3.y;

@@ -39,6 +39,7 @@ struct WfPool {                 // device pointers, P slots each
     // [3] rays traced, [4] chunks reserved, [5] paths started, [6] global counter exhausted (flag)
     unsigned long long* ctr;
     unsigned long long* chunk_base;   // chunk table: local chunk c covers global paths [chunk_base[c], + 2^20)
+    unsigned long long* dbg;          // instrumented build: per-warp (start, end, rays) of the last trace launch, 3 x 8192
     int P, max_chunks;
 };
 
@@ -158,10 +159,10 @@ wf_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPara
     unsigned long long rays = 0;
     bool active = false, exhausted = false;
     int slot = 0;
-    TRay r; V3 inv = mk(0, 0, 0), oi = mk(0, 0, 0); float slack = 0.f;
+    TRay r; V3 inv = mk(0, 0, 0), cmn = mk(0, 0, 0), cmx = mk(0, 0, 0);
     float t_best = 0.f; int prim_best = -1, skip = -1;
     uint32_t stack[RTW_STACK]; int sp = 1, node = RTW_SENTINEL, leaf = 0;
-    uint32_t wbase = 0, wgrp = 0; rtww::WRay wr; wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31); wr.k = 0; wr.slack = 0.f;
+    uint32_t wbase = 0, wgrp = 0; rtww::WRay wr; wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31); wr.k = 0; wr.sx = wr.sy = wr.sz = 0.f;
     wr.ix = wr.iy = wr.iz = wr.oix = wr.oiy = wr.oiz = 0.f;
     bool done = true;
     stack[0] = (uint32_t)RTW_SENTINEL;
@@ -182,11 +183,10 @@ wf_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPara
                         const float4 a = pool.od0[k], b = pool.od1[k];
                         Ray ray; ray.o = mk(a.x, a.y, a.z); ray.d = mk(b.x, b.y, b.z); ray.time = a.w;
                         r = make_tray(ray);
-                        slab_setup(r.o, r.d, inv, oi, slack);
+                        slab_setup(r.o, r.d, inv, cmn, cmx);
                         t_best = CUDART_INF_F; prim_best = -1; skip = __float_as_int(b.w);
                         if (W) {
-                            wr.ix = inv.x; wr.iy = inv.y; wr.iz = inv.z; wr.oix = oi.x; wr.oiy = oi.y; wr.oiz = oi.z; wr.slack = slack;
-                            wr.k = ((inv.x < 0.0f ? 1u : 0u) | (inv.y < 0.0f ? 2u : 0u) | (inv.z < 0.0f ? 4u : 0u)) ^ 7u;
+                            slab_setup_wide(r.o, r.d, wr);
                             sp = 0; wbase = 0; wgrp = sc.n_bvh_prims ? ((1u << 8) | (1u << wr.k)) : 0u; done = false;
                         } else { sp = 1; leaf = 0; node = sc.n_bvh_prims ? 0 : RTW_SENTINEL; }
                         active = true; ++rays;
@@ -236,8 +236,8 @@ wf_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPara
                         const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
                         const int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
                         float e0, e1;
-                        const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, oi, slack, prm.t_min, t_best, e0);
-                        const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, oi, slack, prm.t_min, t_best, e1);
+                        const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, cmn, cmx, prm.t_min, t_best, e0);
+                        const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, cmn, cmx, prm.t_min, t_best, e1);
                         if (!h0 && !h1) node = (int)stack[--sp];
                         else {
                             node = h0 ? ch.x : ch.y;
@@ -269,6 +269,194 @@ wf_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPara
         }
     }
     for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0 && rays) atomicAdd(&pool.ctr[3], rays);
+}
+
+// The same stage as a LOCKSTEP loop over binary nodes: every iteration all lanes that hold an inner node visit it (one
+// two-box test), lanes that reached a leaf keep it pending (and go on speculatively until they reach a second one), and the
+// pending leaves are intersected together once LEAF_T lanes wait or nobody can descend any more.  With the speculative
+// while-while loop above a lane that holds two leaves sits out the rest of the node phase: ncu shows 9 of 32 lanes in the node
+// test although dynamic fetch keeps 20-32 rays per warp in flight.  Here the node test runs with every lane that has a node.
+#ifndef RTW_WF_LEAF_T
+#define RTW_WF_LEAF_T 8
+#endif
+#ifndef RTW_WF_REFILL_T
+#define RTW_WF_REFILL_T 8
+#endif
+template <int F>
+__global__ void __launch_bounds__(128, 6)
+wf_trace2_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DParams prm, WfPool pool) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long rays = 0;
+    bool active = false, exhausted = false;
+    int slot = 0;
+    TRay r; V3 inv = mk(0, 0, 0), cmn = mk(0, 0, 0), cmx = mk(0, 0, 0);
+    float t_best = 0.f; int prim_best = -1, skip = -1;
+    int stack[RTW_STACK]; int sp = 1, node = RTW_SENTINEL, leaf = 0;
+    stack[0] = RTW_SENTINEL;
+    for (;;) {
+        // ---- (1) refill
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (__popc(idle) >= RTW_WF_REFILL_T)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&pool.ctr[2], (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= (unsigned long long)pool.P) exhausted = true;
+            if (!active) {
+                const unsigned long long k = base + __popc(idle & lt_mask);
+                if (k < (unsigned long long)pool.P) {
+                    const float4 rd = pool.rad[k];
+                    if (__float_as_int(rd.w) == WF_TRACE) {
+                        slot = (int)k;
+                        const float4 a = pool.od0[k], b = pool.od1[k];
+                        Ray ray; ray.o = mk(a.x, a.y, a.z); ray.d = mk(b.x, b.y, b.z); ray.time = a.w;
+                        r = make_tray(ray);
+                        slab_setup(r.o, r.d, inv, cmn, cmx);
+                        t_best = CUDART_INF_F; prim_best = -1; skip = __float_as_int(b.w);
+                        sp = 1; leaf = 0; node = sc.n_bvh_prims ? 0 : RTW_SENTINEL;
+                        active = true; ++rays;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) { if (exhausted) break; else continue; }
+        // ---- (2) node step
+        const bool can_node = active && node >= 0 && node != RTW_SENTINEL;
+        if (can_node) {
+            const float4* np = reinterpret_cast<const float4*>(sc.nodes + node);
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            const int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
+            float e0, e1;
+            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, cmn, cmx, prm.t_min, t_best, e0);
+            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, cmn, cmx, prm.t_min, t_best, e1);
+            const bool second = h1 & (!h0 | (e1 < e0));
+            const int nearc = second ? ch.y : ch.x, farc = second ? ch.x : ch.y;
+            node = nearc;
+            if (h0 && h1) { stack[sp] = farc; ++sp; }
+            if (!(h0 || h1)) { --sp; node = stack[sp]; }
+            if (node < 0 && leaf == 0) { leaf = node; --sp; node = stack[sp]; }     // first leaf: keep it pending, go on
+        }
+        // ---- (3) leaf step: when enough lanes wait, or nobody can descend
+        const bool want_leaf = active && leaf < 0;
+        const unsigned ml = __ballot_sync(0xffffffffu, want_leaf);
+        const unsigned mn = __ballot_sync(0xffffffffu, active && node >= 0 && node != RTW_SENTINEL);
+        if (ml && (__popc(ml) >= RTW_WF_LEAF_T || mn == 0u)) {
+            if (want_leaf) {
+                const int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
+#pragma unroll 1
+                for (int q = 0; q < count; ++q) {
+                    const float t = prim_root<F>(sc, first + q, r, prm.t_min, t_best, skip);
+                    if (t == t) { t_best = t; prim_best = first + q; }
+                }
+                leaf = 0;
+                if (node < 0) { leaf = node; --sp; node = stack[sp]; }                // the second leaf reached meanwhile
+            }
+        }
+        // ---- (4) rays that are done
+        if (active && node == RTW_SENTINEL && leaf == 0) {
+            pool.hit[slot] = make_uint2(__float_as_uint(t_best), (unsigned)prim_best);
+            active = false;
+        }
+    }
+    for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+    if (lane == 0 && rays) atomicAdd(&pool.ctr[3], rays);
+}
+
+// Lockstep loop over the 8-WIDE compressed nodes: the node test (the long, ALU-heavy part: ~245 instructions) runs with
+// every lane that has a node group to descend; the leaves a visit yields stay pending as a group until LEAF_T lanes hold one.
+template <int F>
+__global__ void __launch_bounds__(128, 6)
+wf_trace2w_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DParams prm, WfPool pool) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    unsigned long long rays = 0;
+    bool active = false, exhausted = false;
+    int slot = 0;
+    TRay r;
+    float t_best = 0.f; int prim_best = -1, skip = -1;
+    uint32_t stack[2 * RTW_WIDE_STACK]; int sp = 0;
+    uint32_t wbase = 0, wgrp = 0, lbase = 0, lgrp = 0;       // node group; pending leaf group (lmask << 8 | permuted hit bits)
+    rtww::WRay wr; wr.one = 0x3F800000u | ((uint32_t)sc.n_nodes >> 31); wr.k = 0; wr.sx = wr.sy = wr.sz = 0.f;
+    wr.ix = wr.iy = wr.iz = wr.oix = wr.oiy = wr.oiz = 0.f;
+#ifdef RTW_INSTRUMENT
+    unsigned long long dbg_t0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+#endif
+    for (;;) {
+        // ---- (1) refill
+        const unsigned idle = __ballot_sync(0xffffffffu, !active);
+        if (!exhausted && (__popc(idle) >= RTW_WF_REFILL_T)) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&pool.ctr[2], (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= (unsigned long long)pool.P) exhausted = true;
+            if (!active) {
+                const unsigned long long k = base + __popc(idle & lt_mask);
+                if (k < (unsigned long long)pool.P) {
+                    const float4 rd = pool.rad[k];
+                    if (__float_as_int(rd.w) == WF_TRACE) {
+                        slot = (int)k;
+                        const float4 a = pool.od0[k], b = pool.od1[k];
+                        Ray ray; ray.o = mk(a.x, a.y, a.z); ray.d = mk(b.x, b.y, b.z); ray.time = a.w;
+                        r = make_tray(ray);
+                        slab_setup_wide(r.o, r.d, wr);
+                        t_best = CUDART_INF_F; prim_best = -1; skip = __float_as_int(b.w);
+                        sp = 0; wbase = 0; wgrp = sc.n_bvh_prims ? ((1u << 8) | (1u << wr.k)) : 0u; lgrp = 0;
+                        active = true; ++rays;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) { if (exhausted) break; else continue; }
+        // ---- (2) node step: one wide node per lane that has a group to descend and no leaves pending
+        const bool can_node = active && !(lgrp & 0xffu) && ((wgrp & 0xffu) || sp > 0);
+        if (can_node) {
+            if (!(wgrp & 0xffu)) { sp -= 2; wbase = stack[sp]; wgrp = stack[sp + 1]; }
+            const int j = 31 - __clz(wgrp & 0xffu);
+            wgrp ^= 1u << j;
+            const uint32_t sl = (uint32_t)j ^ wr.k;
+            const uint32_t nd = wbase + __popc((wgrp >> 8) & ((1u << sl) - 1u));
+            if (wgrp & 0xffu) { stack[sp] = wbase; stack[sp + 1] = wgrp; sp += 2; }
+            const uint4* np = reinterpret_cast<const uint4*>(sc.wnodes + nd);
+            const uint4 h = __ldg(np), m = __ldg(np + 1), qa = __ldg(np + 2), qb = __ldg(np + 3), qc = __ldg(np + 4);
+            const uint32_t imask = h.w >> 24, lmask = m.z & 0xffu;
+            uint32_t hits = rtww::wide_node_hits(*reinterpret_cast<const rtww::W4*>(&h), *reinterpret_cast<const rtww::W4*>(&qa),
+                                                 *reinterpret_cast<const rtww::W4*>(&qb), *reinterpret_cast<const rtww::W4*>(&qc), wr, prm.t_min, t_best);
+            hits &= imask | lmask;
+            const uint32_t m16 = rtww::wide_perm16((hits & imask) | ((hits & lmask) << 8), wr.k);
+            wbase = m.x; wgrp = (imask << 8) | (m16 & 0xffu);
+            lbase = m.y; lgrp = (lmask << 8) | (m16 >> 8);
+        }
+        // ---- (3) leaf step
+        const bool want_leaf = active && (lgrp & 0xffu);
+        const unsigned ml = __ballot_sync(0xffffffffu, want_leaf);
+        const unsigned mn = __ballot_sync(0xffffffffu, active && !(lgrp & 0xffu) && ((wgrp & 0xffu) || sp > 0));
+        if (ml && (__popc(ml) >= RTW_WF_LEAF_T || mn == 0u)) {
+            while (__any_sync(0xffffffffu, active && (lgrp & 0xffu))) {
+                if (active && (lgrp & 0xffu)) {
+                    const int jj = 31 - __clz(lgrp & 0xffu);
+                    lgrp ^= 1u << jj;
+                    const uint32_t s2 = (uint32_t)jj ^ wr.k;
+                    const int pi = (int)(lbase + __popc((lgrp >> 8) & ((1u << s2) - 1u)));
+                    const float t = prim_root<F>(sc, pi, r, prm.t_min, t_best, skip);
+                    if (t == t) { t_best = t; prim_best = pi; }
+                }
+            }
+        }
+        // ---- (4) rays that are done
+        if (active && !(wgrp & 0xffu) && sp == 0 && !(lgrp & 0xffu)) {
+            pool.hit[slot] = make_uint2(__float_as_uint(t_best), (unsigned)prim_best);
+            active = false;
+        }
+    }
+    for (int o = 16; o; o >>= 1) rays += __shfl_xor_sync(0xffffffffu, rays, o);
+#ifdef RTW_INSTRUMENT
+    if (lane == 0) {
+        unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if (w < 8192u) { pool.dbg[w] = dbg_t0; pool.dbg[8192 + w] = t1; pool.dbg[16384 + w] = rays; }
+    }
+#endif
     if (lane == 0 && rays) atomicAdd(&pool.ctr[3], rays);
 }
 

@@ -869,8 +869,7 @@ bool check_wide_traversal(const FlatScene& f, int n_rays, uint64_t seed, uint64_
         auto sdir = [](float v) { return std::fabs(v) < 1e-20f ? std::copysign(1e-20f, v) : v; };
         r.ix = 1.0f / sdir(d[0]); r.iy = 1.0f / sdir(d[1]); r.iz = 1.0f / sdir(d[2]);
         r.oix = o[0] * r.ix; r.oiy = o[1] * r.iy; r.oiz = o[2] * r.iz;
-        const float sx = std::fabs(d[0]) < 1e-20f ? 0.f : std::fabs(r.oix), sy = std::fabs(d[1]) < 1e-20f ? 0.f : std::fabs(r.oiy), sz = std::fabs(d[2]) < 1e-20f ? 0.f : std::fabs(r.oiz);
-        r.slack = 2.384185791015625e-07f * std::max(sx, std::max(sy, sz));
+        r.sx = 2.384185791015625e-07f * std::fabs(r.oix); r.sy = 2.384185791015625e-07f * std::fabs(r.oiy); r.sz = 2.384185791015625e-07f * std::fabs(r.oiz);
         const uint32_t oct = (r.ix < 0 ? 1u : 0u) | (r.iy < 0 ? 2u : 0u) | (r.iz < 0 ? 4u : 0u);
         r.k = oct ^ 7u; r.one = 0x3F800000u;
         std::fill(reached.begin(), reached.end(), 0);
