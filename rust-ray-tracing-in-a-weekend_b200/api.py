@@ -184,6 +184,7 @@ class Lib:
         f("debug_flatten").argtypes = [vp, ip, dp]
         f("debug_flatten2").argtypes = [vp, ip, dp]
         f("debug_wide").argtypes = [vp, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64)]
+        f("debug_wide_cost").argtypes = [vp, C.c_int32, C.c_uint64, C.POINTER(C.c_uint64)]
         f("rotate_y_sincos").argtypes = [vp, C.c_double, C.c_double, C.c_int]
         f("rotate_y_sincos").restype = C.c_int
 
@@ -386,6 +387,13 @@ class Scene:
         out = np.zeros(8, np.uint64)
         self._c("debug_wide", n_rays, seed, _p(out, C.c_uint64))
         keys = ("rays", "node_visits", "leaves_reached", "boxes_crossed", "missed", "wide_nodes", "wide_depth", "bvh_prims")
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def debug_wide_cost(self, n_rays=20000, seed=1):
+        """Host-only tuning aid: closest-hit cost of secondary-like rays through the 8-wide tree, traversed on the CPU."""
+        out = np.zeros(8, np.uint64)
+        self._c("debug_wide_cost", n_rays, seed, _p(out, C.c_uint64))
+        keys = ("rays", "node_visits", "prim_tests", "occupied_slots", "hits", "wide_nodes", "wide_depth", "bvh_prims")
         return dict(zip(keys, (int(x) for x in out)))
 
     def render(self, cam, params, out=None):

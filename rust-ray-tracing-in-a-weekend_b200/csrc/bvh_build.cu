@@ -137,7 +137,8 @@ __global__ void karras_kernel(int n, const unsigned long long* __restrict__ keys
 
 // leaf boxes, then up: the second thread to reach an inner node finds both children complete
 __global__ void refit_kernel(int n, const unsigned* __restrict__ sorted_idx, const float* __restrict__ prim_boxes, const int* __restrict__ left,
-                             const int* __restrict__ right, const int* __restrict__ parent, float* __restrict__ box, int* __restrict__ flags) {
+                             const int* __restrict__ right, const int* __restrict__ parent, float* __restrict__ box, int* __restrict__ flags,
+                             int* __restrict__ count /* leaves under each inner node (the wide collapse absorbs small subtrees whole) */) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const int n_inner = n - 1;
@@ -153,6 +154,10 @@ __global__ void refit_kernel(int n, const unsigned* __restrict__ sorted_idx, con
         const volatile float* rb = box + (size_t)right[cur] * 6;
         for (int a = 0; a < 3; ++a) { b[a] = fminf(lb[a], rb[a]); b[3 + a] = fmaxf(lb[3 + a], rb[3 + a]); }
         for (int a = 0; a < 6; ++a) box[(size_t)cur * 6 + a] = b[a];
+        {
+            const int l = left[cur], r = right[cur];
+            count[cur] = (l < n_inner ? ((const volatile int*)count)[l] : 1) + (r < n_inner ? ((const volatile int*)count)[r] : 1);
+        }
         cur = parent[cur];
     }
 }
@@ -275,7 +280,7 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
     const int T = 256, G = (n + T - 1) / T;
     prim_boxes_kernel<<<G, T, 0, st>>>(n, in.n_host, d_hboxes.as<float>(), d_bulk.as<BulkSphereD>(), d_boxes.as<float>(), d_bounds.as<unsigned>());
     BCUDA(cudaGetLastError());
-    Buf d_wnodes_scratch, d_order, d_q0, d_q1, d_counters, d_left, d_right, d_parent, d_box2, d_flags;
+    Buf d_wnodes_scratch, d_order, d_q0, d_q1, d_counters, d_left, d_right, d_parent, d_box2, d_flags, d_count;
     BCUDA(cudaMalloc(&d_order.p, (size_t)n * 4));
     BCUDA(cudaMalloc(&d_counters.p, 64));
     DWNode* wn = nullptr;
@@ -324,9 +329,10 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
         BCUDA(cudaMalloc(&d_box2.p, (size_t)(n_inner + n) * 24));
         BCUDA(cudaMalloc(&d_flags.p, (size_t)n_inner * 4));
         BCUDA(cudaMemsetAsync(d_flags.p, 0, (size_t)n_inner * 4, st));
+        BCUDA(cudaMalloc(&d_count.p, (size_t)n_inner * 4));
         karras_kernel<<<(n_inner + T - 1) / T, T, 0, st>>>(n, keys, d_left.as<int>(), d_right.as<int>(), d_parent.as<int>());
         BCUDA(cudaGetLastError());
-        refit_kernel<<<G, T, 0, st>>>(n, sorted_idx, d_boxes.as<float>(), d_left.as<int>(), d_right.as<int>(), d_parent.as<int>(), d_box2.as<float>(), d_flags.as<int>());
+        refit_kernel<<<G, T, 0, st>>>(n, sorted_idx, d_boxes.as<float>(), d_left.as<int>(), d_right.as<int>(), d_parent.as<int>(), d_box2.as<float>(), d_flags.as<int>(), d_count.as<int>());
         BCUDA(cudaGetLastError());
         mark();
         if (in.width == 2) {
@@ -355,7 +361,8 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
             BCUDA(cudaMemcpyAsync(d_counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
             BCUDA(cudaMemcpyAsync(d_q0.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
         }
-        rtww::B2View view{d_box2.as<float>(), d_left.as<int>(), d_right.as<int>(), n_inner, n};
+        static const bool fill = !(getenv("RTW_WIDE_FILL") && atoi(getenv("RTW_WIDE_FILL")) == 0);
+        rtww::B2View view{d_box2.as<float>(), d_left.as<int>(), d_right.as<int>(), n_inner, n, fill ? d_count.as<int>() : nullptr};
         rtww::WideItem* cur = d_q0.as<rtww::WideItem>();
         rtww::WideItem* next = d_q1.as<rtww::WideItem>();
         int n_cur = 1, levels = 0;

@@ -53,6 +53,9 @@ __device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; 
 #ifndef RTW_DEFAULT_MODE
 #define RTW_DEFAULT_MODE 0
 #endif
+#ifndef RTW_WF_DEFAULT_POOLS
+#define RTW_WF_DEFAULT_POOLS 1
+#endif
 #ifndef RTW_DEFAULT_POOL_MODE
 #define RTW_DEFAULT_POOL_MODE 2
 #endif
@@ -462,7 +465,10 @@ struct Replica {
     int pool_grid[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // warp-pool kernel grids for POOL = 64/128/192/256, binary then wide (lazy)
     int sms = 0;
     rtwb::BuildOutput built;                // device-built BVH + primitive records (own allocations, outside the blob)
-    WfPool wf{};                            // wavefront path pool (lazy; rtw_wavefront.cuh)
+    WfPool wf[4] = {};                      // wavefront path pools (lazy; rtw_wavefront.cuh): wf_pools independent pools, one stream each
+    int wf_pools = 0; long long wf_slots = 0;
+    cudaStream_t wf_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] = stream
+    cudaEvent_t wf_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t* wf_mem = nullptr;
     int wf_grid[4] = {0, 0, 0, 0};          // trace kernel grids: [F != 0][W]
 };
@@ -503,6 +509,8 @@ void free_replicas(rtw_scene* s) {
         if (r.blob) cudaFree(r.blob);
         rtwb::free_output(r.built);
         if (r.wf_mem) cudaFree(r.wf_mem);
+        for (int k = 1; k < 4; ++k) if (r.wf_stream[k]) cudaStreamDestroy(r.wf_stream[k]);
+        for (int k = 0; k < 4; ++k) if (r.wf_ev[k]) cudaEventDestroy(r.wf_ev[k]);
         if (r.stats) cudaFree(r.stats);
         if (r.ev0) cudaEventDestroy(r.ev0);
         if (r.ev1) cudaEventDestroy(r.ev1);
@@ -656,8 +664,16 @@ int ensure_fb(SharedFb& fb, int device, int w, int h) {
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// kernel choice: 0 = megakernel (one path per lane), 1..4 = warp-pool kernel with 64/128/192/256 slots per warp
-int kernel_mode(int flags) {
+// kernel choice: 0 = megakernel (one path per lane), 1..4 = warp-pool kernel with 64/128/192/256 slots per warp, 5 = wavefront
+// pipeline (path pool in HBM).  Chosen by measurement: the megakernel wins wherever the scene
+// sits in L1 / L2 (C1 - C4: the wavefront pipeline is 2x slower there), the wavefront pipeline over the 8-wide tree wins on
+// scenes beyond the caches (1 M / 4 M spheres: 1.32x / 1.38x).  Flags and RTW_KERNEL override.
+long long big_scene_min() {
+    static long long v = -1;
+    if (v < 0) { v = 1ll << 20; if (const char* e = getenv("RTW_BIG_MIN")) v = std::max(1ll, atoll(e)); }
+    return v;
+}
+int kernel_mode(const rtw_scene* s, int flags) {
     static int env_mode = -2;
     if (env_mode == -2) {
         env_mode = -1;
@@ -674,6 +690,7 @@ int kernel_mode(int flags) {
     if (flags & RTW_FLAG_KERNEL_MEGA) return 0;
     if (flags & RTW_FLAG_KERNEL_POOL) return RTW_DEFAULT_POOL_MODE;
     if (env_mode >= 0) return env_mode;
+    if (s && s->flat.wide && std::max<long long>(s->flat.n_bvh_prims, s->n_prims_dev) >= big_scene_min()) return 5;
     return RTW_DEFAULT_MODE;
 }
 
@@ -700,55 +717,78 @@ int wf_ensure_pool(Replica& r, long long want_slots) {
     long long P = 8ll << 20;                                         // slots in flight per GPU (RTW_WF_POOL overrides)
     if (const char* e = getenv("RTW_WF_POOL")) P = std::max(1024ll, atoll(e));
     P = std::min(P, std::max(1024ll, want_slots));
-    P = (P + RTW_WF_BLOCK - 1) / RTW_WF_BLOCK * RTW_WF_BLOCK;
-    if (r.wf_mem && r.wf.P == (int)P) return 0;
+    // K independent pools, each with its own stream: the logic pass and the end of the trace pass of one pool overlap with
+    // the trace pass of another (the trace kernel is persistent: its last rays leave most of the GPU idle)
+    int K = RTW_WF_DEFAULT_POOLS;
+    if (const char* e = getenv("RTW_WF_POOLS")) K = std::min(4, std::max(1, atoi(e)));
+    if (P < (1ll << 20)) K = 1;
+    r.wf_stream[0] = r.stream;
+    const long long per = ((P + K - 1) / K + RTW_WF_BLOCK - 1) / RTW_WF_BLOCK * RTW_WF_BLOCK;
+    if (r.wf_mem && r.wf_slots == per && r.wf_pools == K) return 0;
     if (r.wf_mem) { CUDA_TRY(cudaFree(r.wf_mem)); r.wf_mem = nullptr; }
     const int max_chunks = 1 << 16;                                  // 2^16 chunks x 2^20 paths: more than spp <= 2^20 at 8K needs
     const size_t per_slot = 4 * sizeof(float4) + 2 * sizeof(uint2);
-    const size_t bytes = (size_t)P * per_slot + 256 + (size_t)max_chunks * 8 + 3 * 8192 * 8;
-    CUDA_TRY(cudaMalloc(&r.wf_mem, bytes));
-    uint8_t* p = r.wf_mem;
-    r.wf.od0 = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
-    r.wf.od1 = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
-    r.wf.thr = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
-    r.wf.rad = reinterpret_cast<float4*>(p); p += (size_t)P * 16;
-    r.wf.id = reinterpret_cast<uint2*>(p); p += (size_t)P * 8;
-    r.wf.hit = reinterpret_cast<uint2*>(p); p += (size_t)P * 8;
-    r.wf.ctr = reinterpret_cast<unsigned long long*>(p); p += 256;
-    r.wf.chunk_base = reinterpret_cast<unsigned long long*>(p); p += (size_t)max_chunks * 8;
-    r.wf.dbg = reinterpret_cast<unsigned long long*>(p);
-    r.wf.P = (int)P; r.wf.max_chunks = max_chunks;
+    const size_t per_pool = align_up((size_t)per * per_slot + 256 + (size_t)max_chunks * 8 + 3 * 8192 * 8, 256);
+    CUDA_TRY(cudaMalloc(&r.wf_mem, per_pool * K));
+    for (int k = 0; k < K; ++k) {
+        uint8_t* p = r.wf_mem + per_pool * k;
+        WfPool& w = r.wf[k];
+        w.od0 = reinterpret_cast<float4*>(p); p += (size_t)per * 16;
+        w.od1 = reinterpret_cast<float4*>(p); p += (size_t)per * 16;
+        w.thr = reinterpret_cast<float4*>(p); p += (size_t)per * 16;
+        w.rad = reinterpret_cast<float4*>(p); p += (size_t)per * 16;
+        w.id = reinterpret_cast<uint2*>(p); p += (size_t)per * 8;
+        w.hit = reinterpret_cast<uint2*>(p); p += (size_t)per * 8;
+        w.ctr = reinterpret_cast<unsigned long long*>(p); p += 256;
+        w.chunk_base = reinterpret_cast<unsigned long long*>(p); p += (size_t)max_chunks * 8;
+        w.dbg = reinterpret_cast<unsigned long long*>(p);
+        w.P = (int)per; w.max_chunks = max_chunks;
+        if (k && !r.wf_stream[k]) CUDA_TRY(cudaStreamCreateWithFlags(&r.wf_stream[k], cudaStreamNonBlocking));
+        if (!r.wf_ev[k]) CUDA_TRY(cudaEventCreateWithFlags(&r.wf_ev[k], cudaEventDisableTiming));
+    }
+    r.wf_pools = K; r.wf_slots = per;
     return 0;
 }
 
 template <int F, int W>
 int wf_run(rtw_scene* s, Replica& r, const DCamera& dc, const DParams& dp, unsigned long long* path_counter, unsigned long long total_paths, float* fb) {
+    static const bool lockstep = !(getenv("RTW_WF_TRACE") && !strcmp(getenv("RTW_WF_TRACE"), "whilewhile"));
+    // the trace stage: lockstep loop (default) or the speculative while-while loop, over binary or 8-wide nodes
+    void (*trace)(const DScene, const DParams, WfPool) = lockstep ? (W ? wf_trace2w_kernel<F> : wf_trace2_kernel<F>) : wf_trace_kernel<F, W>;
     int& grid = r.wf_grid[(F ? 2 : 0) + W];
     if (!grid) {
         int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_kernel<F, W>, 128, 0));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace, 128, 0));
         grid = r.sms * std::max(per_sm, 1);
     }
-    static const bool lockstep = !(getenv("RTW_WF_TRACE") && !strcmp(getenv("RTW_WF_TRACE"), "whilewhile"));
-    const WfPool pool = r.wf;
-    CUDA_TRY(cudaMemsetAsync(pool.rad, 0, (size_t)pool.P * sizeof(float4), r.stream));     // every slot EMPTY
-    CUDA_TRY(cudaMemsetAsync(pool.ctr, 0, 256, r.stream));
-    const int lgrid = pool.P / RTW_WF_BLOCK;
-    unsigned long long h[8];
+    const int K = r.wf_pools;
+    const bool timing = getenv("RTW_TIMING") != nullptr;
+    CUDA_TRY(cudaEventRecord(r.wf_ev[0], r.stream));                                        // the pools start after whatever precedes on the replica's stream
+    for (int k = 0; k < K; ++k) {
+        const WfPool& pool = r.wf[k];
+        if (k) CUDA_TRY(cudaStreamWaitEvent(r.wf_stream[k], r.wf_ev[0], 0));
+        CUDA_TRY(cudaMemsetAsync(pool.rad, 0, (size_t)pool.P * sizeof(float4), r.wf_stream[k]));     // every slot EMPTY
+        CUDA_TRY(cudaMemsetAsync(pool.ctr, 0, 256, r.wf_stream[k]));
+    }
+    unsigned long long h[4][8];
+    bool done[4] = {false, false, false, false};
+    const double t_begin = now_ms();
     for (long long it = 0;; ++it) {
-        // a batch of iterations, then one look at the counters (the only host round trip)
-        for (int k = 0; k < 8; ++k) {
-            wf_reserve_kernel<<<1, 1, 0, r.stream>>>(pool, path_counter, total_paths);
-            wf_logic_kernel<F><<<lgrid, RTW_WF_BLOCK, 0, r.stream>>>(r.ds, dc, dp, pool, total_paths, fb);
-            if (lockstep && W) wf_trace2w_kernel<F><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
-            else if (lockstep) wf_trace2_kernel<F><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
-            else wf_trace_kernel<F, W><<<grid, 128, 0, r.stream>>>(r.ds, dp, pool);
-        }
+        // a batch of iterations per pool, then one look at the counters (the only host round trip)
+        for (int j = 0; j < 8; ++j)
+            for (int k = 0; k < K; ++k) {
+                if (done[k]) continue;
+                const WfPool& pool = r.wf[k];
+                wf_reserve_kernel<<<1, 1, 0, r.wf_stream[k]>>>(pool, path_counter, total_paths);
+                wf_logic_kernel<F><<<pool.P / RTW_WF_BLOCK, RTW_WF_BLOCK, 0, r.wf_stream[k]>>>(r.ds, dc, dp, pool, total_paths, fb);
+                trace<<<grid, 128, 0, r.wf_stream[k]>>>(r.ds, dp, pool);
+            }
         CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaMemcpyAsync(h, pool.ctr, sizeof(h), cudaMemcpyDeviceToHost, r.stream));
-        CUDA_TRY(cudaStreamSynchronize(r.stream));
+        for (int k = 0; k < K; ++k) if (!done[k]) CUDA_TRY(cudaMemcpyAsync(h[k], r.wf[k].ctr, sizeof(h[k]), cudaMemcpyDeviceToHost, r.wf_stream[k]));
+        for (int k = 0; k < K; ++k) if (!done[k]) CUDA_TRY(cudaStreamSynchronize(r.wf_stream[k]));
 #ifdef RTW_INSTRUMENT
         if (getenv("RTW_WF_TIMELINE") && it < 4) {
+            const WfPool& pool = r.wf[0];
             std::vector<unsigned long long> d(3 * 8192);
             cudaMemcpy(d.data(), pool.dbg, d.size() * 8, cudaMemcpyDeviceToHost);
             const int nw = std::min(8192, grid * 4);
@@ -760,12 +800,22 @@ int wf_run(rtw_scene* s, Replica& r, const DCamera& dc, const DParams& dp, unsig
                     (it + 1) * 8, nw, ends.front(), ends[nw / 10], ends[nw / 2], ends[nw * 9 / 10], ends[nw * 99 / 100], ends.back(), rmin, (double)rsum / nw, rmax);
         }
 #endif
-        // done: no slot holds a ray, the shared counter is exhausted and every reserved path number was handed out
-        if (h[1] == 0 && h[6] && h[0] >= (h[4] << RTW_WF_CHUNK_LOG2)) {
-            if (getenv("RTW_TIMING")) fprintf(stderr, "[wavefront] %lld iterations, %llu rays, %llu paths, pool %d\n", (it + 1) * 8, h[3], h[5], pool.P);
-            break;
+        // a pool is done when none of its slots holds a ray, the shared counter is exhausted and every reserved path number was handed out
+        bool all = true;
+        for (int k = 0; k < K; ++k) {
+            if (!done[k] && h[k][1] == 0 && h[k][6] && h[k][0] >= (h[k][4] << RTW_WF_CHUNK_LOG2)) done[k] = true;
+            all = all && done[k];
         }
+        if (timing && (it < 3 || all)) {
+            unsigned long long rays = 0, paths = 0; for (int k = 0; k < K; ++k) { rays += h[k][3]; paths += h[k][5]; }
+            fprintf(stderr, "[wavefront] after %lld iterations (%d pools of %d): %.2f ms, %llu rays, %llu paths%s\n", (it + 1) * 8, K, r.wf[0].P, now_ms() - t_begin, rays, paths, all ? " (done)" : "");
+        }
+        if (all) break;
         if (it > (1ll << 24)) return fail(RTW_ERR_CUDA, "wavefront loop did not terminate");
+    }
+    for (int k = 1; k < K; ++k) {                                                            // whatever follows on the replica's stream follows every pool
+        CUDA_TRY(cudaEventRecord(r.wf_ev[k], r.wf_stream[k]));
+        CUDA_TRY(cudaStreamWaitEvent(r.stream, r.wf_ev[k], 0));
     }
     (void)s;
     return 0;
@@ -785,9 +835,12 @@ int wf_render_replica(rtw_scene* s, Replica& r, const DCamera& dc, const DParams
     CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
     CUDA_TRY(cudaStreamSynchronize(r.stream));
     float e = 0; CUDA_TRY(cudaEventElapsedTime(&e, r.ev0, r.ev1));
-    unsigned long long h[8];
-    CUDA_TRY(cudaMemcpy(h, r.wf.ctr, sizeof(h), cudaMemcpyDeviceToHost));
-    ms = e; rays = h[3]; paths = h[5];
+    ms = e; rays = 0; paths = 0;
+    for (int k = 0; k < r.wf_pools; ++k) {
+        unsigned long long h[8];
+        CUDA_TRY(cudaMemcpy(h, r.wf[k].ctr, sizeof(h), cudaMemcpyDeviceToHost));
+        rays += h[3]; paths += h[5];
+    }
     return 0;
 }
 
@@ -1115,14 +1168,15 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     if (first_device < 0 || n_gpus < 1 || first_device + n_gpus > ndev || n_gpus > 8) return fail(RTW_ERR_INVALID_ARG, "device range not available");
     double t0 = now_ms();
     std::string err;
-    // Where the BVH is built.  Big scenes (RTW_DEVICE_BUILD_MIN primitives, default 2 Mi) are built ON THE DEVICE from what the
-    // constructors were given (bvh_build.cu): 16 M spheres commit in 0.24 s instead of 5.1 s; the LBVH renders ~6 % slower than
-    // the host's binned-SAH tree, which pays from ~2 M primitives on at 256 spp (profiles/r2_c_sweep_device_build.log).  Small
+    // Where the BVH is built.  Big scenes (RTW_BIG_MIN primitives, default 1 Mi; RTW_DEVICE_BUILD_MIN overrides) are built ON THE
+    // DEVICE from what the constructors were given (bvh_build.cu): 16 M spheres commit in 0.24 s instead of 5.1 s.  As 8-wide
+    // nodes under the wavefront pipeline the LBVH renders as fast as the host's binned-SAH tree (1 M: 378 vs 382, 4 M: 306 vs
+    // 304 Mpaths/s, profiles/r2_v_wavefront_variants.log; as binary nodes under the megakernel it was ~6 % slower).  Small
     // scenes keep the host SAH builder (C1: 1 ms, better trees).  RTW_DEVICE_BUILD=0 / 1 forces either.
     rtw::FlattenOptions fo;
     {
         long long n_guess = (long long)s->g.bulk.size() + (long long)s->g.nodes.size();
-        long long dev_min = 2 << 20;
+        long long dev_min = big_scene_min();
         if (const char* e = getenv("RTW_DEVICE_BUILD_MIN")) dev_min = atoll(e);
         fo.emit_only = n_guess >= dev_min;
         if (const char* e = getenv("RTW_DEVICE_BUILD")) fo.emit_only = atoi(e) != 0;
@@ -1234,11 +1288,11 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     TRY(ensure_fb(s->local, r0.device, dev_out ? 1 : p->width, dev_out ? 1 : p->height));
     float* fb = dev_out ? out : s->local.fb();
     CUDA_TRY(cudaSetDevice(r0.device));
-    dp.accumulate = (n_rep > 1 || dp.chunks + dp.chunks_b > 1 || kernel_mode(p->flags) == 5) ? 1 : 0;   // (wavefront: finished paths are ADDED)
+    dp.accumulate = (n_rep > 1 || dp.chunks + dp.chunks_b > 1 || kernel_mode(s, p->flags) == 5) ? 1 : 0;   // (wavefront: finished paths are ADDED)
     CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
     if (dp.accumulate) CUDA_TRY(cudaMemsetAsync(fb, 0, fb_bytes, r0.stream));
     if (n_rep > 1) CUDA_TRY(cudaStreamSynchronize(r0.stream));   // peers must see the zeroed buffers
-    TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, st, kernel_mode(p->flags)));
+    TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, st, kernel_mode(s, p->flags)));
     if (!dev_out) {
         CUDA_TRY(cudaSetDevice(r0.device));
         CUDA_TRY(cudaMemcpy(out, fb, fb_bytes, cudaMemcpyDeviceToHost));
@@ -1284,7 +1338,7 @@ int rtw_render_progressive(rtw_scene* s, const rtw_camera* cam, const rtw_render
         CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
         CUDA_TRY(cudaStreamSynchronize(r0.stream));               // peers (and the next pass) must see counter + sums
         rtw_stats ps; std::memset(&ps, 0, sizeof(ps));
-        TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, &ps, kernel_mode(p->flags)));
+        TRY(launch_all(s, n_rep, cam, dp, s->local.counter(), fb, &ps, kernel_mode(s, p->flags)));
         ms_render += ps.ms_render; rays += ps.rays; launches += ps.kernel_launches;
         for (int i = 0; i < 8; ++i) units[i] += ps.units_per_device[i];
         done += pass.spp;
@@ -1381,7 +1435,7 @@ int rtw_render_shared_epoch(rtw_scene* s, const rtw_camera* cam, const rtw_rende
         CUDA_TRY(cudaMemsetAsync(s->shared.counter(half ^ 1), 0, 128, s->shared.side));
         CUDA_TRY(cudaMemsetAsync(s->shared.fb(half ^ 1), 0, s->shared.fb_bytes(), s->shared.side));
     }
-    TRY(launch_all(s, 1, cam, dp, s->shared.counter(half), s->shared.fb(half), st, kernel_mode(p->flags)));
+    TRY(launch_all(s, 1, cam, dp, s->shared.counter(half), s->shared.fb(half), st, kernel_mode(s, p->flags)));
     if (st) { st->paths = (uint64_t)p->width * p->height * p->spp; st->ms_total = now_ms() - t0; }
     return RTW_OK;
 }
@@ -1400,7 +1454,7 @@ int rtw_render_shared(rtw_scene* s, const rtw_camera* cam, const rtw_render_para
     DParams dp; TRY(make_params(*p, world * s->reps[0].grid * RTW_WARPS, dp));
     dp.accumulate = 1;
     if (st) { std::memset(st, 0, sizeof(*st)); fill_scene_stats(s, st); }
-    TRY(launch_all(s, 1, cam, dp, s->shared.counter(), s->shared.fb(), st, kernel_mode(p->flags)));
+    TRY(launch_all(s, 1, cam, dp, s->shared.counter(), s->shared.fb(), st, kernel_mode(s, p->flags)));
     if (st) { st->paths = (uint64_t)p->width * p->height * p->spp; st->ms_total = now_ms() - t0; }
     return RTW_OK;
 }
@@ -1574,6 +1628,20 @@ int rtw_debug_wide(rtw_scene* s, int32_t n_rays, uint64_t seed, uint64_t* out) {
     for (int i = 0; i < 5; ++i) out[i] = st[i];
     out[5] = f.wnodes.size(); out[6] = (uint64_t)f.wide_depth; out[7] = (uint64_t)f.n_bvh_prims;
     if (!ok) return fail(RTW_ERR_INVALID_ARG, err);
+    return RTW_OK;
+}
+// tuning aid (host-only): cost of secondary-like rays through the wide tree; out[8]: rays, node visits, primitive tests,
+// occupied slots of the visited nodes, hits, wide nodes, wide depth, bvh prims
+int rtw_debug_wide_cost(rtw_scene* s, int32_t n_rays, uint64_t seed, uint64_t* out) {
+    if (!s || !out || n_rays < 0) return fail(RTW_ERR_INVALID_ARG, "bad argument");
+    rtw::FlatScene f; std::string err;
+    rtw::FlattenOptions opt; opt.bvh_width = 8;
+    int rc = rtw::flatten(s->g, s->g.world, f, err, opt);
+    if (rc) return fail(rc, err);
+    uint64_t st[5];
+    rtw::wide_cost_probe(f, n_rays, seed, st);
+    for (int i = 0; i < 5; ++i) out[i] = st[i];
+    out[5] = f.wnodes.size(); out[6] = (uint64_t)f.wide_depth; out[7] = (uint64_t)f.n_bvh_prims;
     return RTW_OK;
 }
 // same, with room to grow: out_counts[16] = the 8 above, [8] BvhNode members dropped as clones of an earlier member

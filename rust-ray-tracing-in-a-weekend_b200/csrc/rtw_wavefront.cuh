@@ -283,6 +283,9 @@ wf_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPara
 #ifndef RTW_WF_REFILL_T
 #define RTW_WF_REFILL_T 8
 #endif
+#ifndef RTW_WF_MIN_BLOCKS
+#define RTW_WF_MIN_BLOCKS 6
+#endif
 template <int F>
 __global__ void __launch_bounds__(128, 6)
 wf_trace2_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DParams prm, WfPool pool) {
@@ -366,7 +369,7 @@ wf_trace2_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPar
 // Lockstep loop over the 8-WIDE compressed nodes: the node test (the long, ALU-heavy part: ~245 instructions) runs with
 // every lane that has a node group to descend; the leaves a visit yields stay pending as a group until LEAF_T lanes hold one.
 template <int F>
-__global__ void __launch_bounds__(128, 6)
+__global__ void __launch_bounds__(128, RTW_WF_MIN_BLOCKS)
 wf_trace2w_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DParams prm, WfPool pool) {
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;

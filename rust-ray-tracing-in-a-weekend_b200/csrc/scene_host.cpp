@@ -583,12 +583,13 @@ int collapse_to_wide(const rtww::B2View& v, std::vector<DWNode>& wnodes, std::ve
     return alloc.max_depth;
 }
 
-int kWideMinPrims = 0x7fffffff;          // binary nodes everywhere unless RTW_BVH=8 / RTW_WIDE_MIN say otherwise
+int kWideMinPrims = 1 << 20;             // 8-wide nodes from 1 Mi primitives (the wavefront pipeline's range); RTW_BIG_MIN / RTW_WIDE_MIN / RTW_BVH override
 int choose_bvh_width(long long n, int requested) {
     int width = requested;
     if (width == 0) { if (const char* e = getenv("RTW_BVH")) width = atoi(e); }
     if (width != 2 && width != 8) {
         long long wide_min = kWideMinPrims;
+        if (const char* e = getenv("RTW_BIG_MIN")) wide_min = std::max(1ll, atoll(e));
         if (const char* e = getenv("RTW_WIDE_MIN")) wide_min = std::max(1, atoi(e));
         width = n >= wide_min ? 8 : 2;
     }
@@ -724,17 +725,18 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         int n_inner = 0;
         for (size_t i = 0; i < nb; ++i) if (b.nodes[i].left >= 0) inner_of[i] = n_inner++;
         std::vector<float> box((size_t)(n_inner + n) * 6);
-        std::vector<int> left((size_t)std::max(n_inner, 1)), right((size_t)std::max(n_inner, 1));
+        std::vector<int> left((size_t)std::max(n_inner, 1)), right((size_t)std::max(n_inner, 1)), count((size_t)std::max(n_inner, 1));
         auto put_box = [&](size_t ref, const FBox& fb) { for (int a = 0; a < 3; ++a) { box[ref * 6 + a] = fb.mn[a]; box[ref * 6 + 3 + a] = fb.mx[a]; } };
         auto ref_of = [&](int bi) { const BuildNode& c = b.nodes[bi]; return c.left >= 0 ? inner_of[bi] : n_inner + c.first; };
         parallel_chunks(nb, 1 << 16, [&](int, size_t i0, size_t i1) {
             for (size_t i = i0; i < i1; ++i) {
                 const BuildNode& bn = b.nodes[i];
-                if (bn.left >= 0) { put_box((size_t)inner_of[i], bn.box); left[inner_of[i]] = ref_of(bn.left); right[inner_of[i]] = ref_of(bn.right); }
+                if (bn.left >= 0) { put_box((size_t)inner_of[i], bn.box); left[inner_of[i]] = ref_of(bn.left); right[inner_of[i]] = ref_of(bn.right); count[inner_of[i]] = bn.count; }
                 else put_box((size_t)(n_inner + bn.first), bn.box);
             }
         });
-        rtww::B2View view{box.data(), left.data(), right.data(), n_inner, n};
+        static const bool fill = !(getenv("RTW_WIDE_FILL") && atoi(getenv("RTW_WIDE_FILL")) == 0);     // A/B switch
+        rtww::B2View view{box.data(), left.data(), right.data(), n_inner, n, fill ? count.data() : nullptr};
         std::vector<int> order;
         out.wide_depth = collapse_to_wide(view, out.wnodes, order);
         std::vector<DPrim> reordered((size_t)n);
@@ -930,6 +932,73 @@ bool check_wide_traversal(const FlatScene& f, int n_rays, uint64_t seed, uint64_
         out[0]++;
     }
     if (out[4]) { err = "the quantised traversal missed a primitive box the ray crosses"; return false; }
+    return true;
+}
+
+// Cost probe for the wide tree (host-only, tuning aid for the collapse heuristic): closest-hit traversal ON THE CPU of
+// Lambertian-like secondary rays (origin on a random sphere, direction = normal + unit vector) through the quantised
+// nodes; spheres are intersected in f64.  out: rays, node visits, primitive tests, occupied slots of the visited nodes, hits.
+bool wide_cost_probe(const FlatScene& f, int n_rays, uint64_t seed, uint64_t out[5]) {
+    for (int i = 0; i < 5; ++i) out[i] = 0;
+    const int n = f.n_bvh_prims;
+    if (n == 0 || f.wnodes.empty()) return true;
+    uint64_t st = seed * 0x9E3779B97F4A7C15ull + 777;
+    auto rnd = [&]() { st = st * 6364136223846793005ull + 1442695040888963407ull; return (double)((st >> 11) & ((1ull << 53) - 1)) / (double)(1ull << 53); };
+    auto unit = [&](double v[3]) { for (;;) { double l = 0; for (int a = 0; a < 3; ++a) { v[a] = 2 * rnd() - 1; l += v[a] * v[a]; } if (l < 1 && l > 1e-6) { l = std::sqrt(l); for (int a = 0; a < 3; ++a) v[a] /= l; return; } } };
+    for (int ri = 0; ri < n_rays; ++ri) {
+        int pa; do { pa = (int)(rnd() * n) % n; } while (f.prims[pa].type != PRIM_SPHERE || f.prims[pa].s.r > 100.0);
+        const DPrim& sp = f.prims[pa];
+        double nrm[3], u[3]; unit(nrm); if (nrm[1] < 0) nrm[1] = -nrm[1]; unit(u);
+        float o[3], d[3];
+        const double c[3] = {sp.s.cx, sp.s.cy, sp.s.cz};
+        for (int a = 0; a < 3; ++a) { o[a] = (float)(c[a] + sp.s.r * nrm[a]); d[a] = (float)(nrm[a] + u[a]); }
+        rtww::WRay r;
+        auto sdir = [](float v) { return std::fabs(v) < 1e-20f ? std::copysign(1e-20f, v) : v; };
+        r.ix = 1.0f / sdir(d[0]); r.iy = 1.0f / sdir(d[1]); r.iz = 1.0f / sdir(d[2]);
+        r.oix = o[0] * r.ix; r.oiy = o[1] * r.iy; r.oiz = o[2] * r.iz;
+        r.sx = 2.384185791015625e-07f * std::fabs(r.oix); r.sy = 2.384185791015625e-07f * std::fabs(r.oiy); r.sz = 2.384185791015625e-07f * std::fabs(r.oiz);
+        const uint32_t oct = (r.ix < 0 ? 1u : 0u) | (r.iy < 0 ? 2u : 0u) | (r.iz < 0 ? 4u : 0u);
+        r.k = oct ^ 7u; r.one = 0x3F800000u;
+        float t_best = INFINITY;
+        struct Grp { uint32_t base, g; };
+        Grp stack[RTW_WIDE_STACK + 1]; int sp_ = 0;
+        uint32_t base = 0, grp = (1u << 8) | (1u << (0u ^ r.k));
+        for (;;) {
+            if (!(grp & 0xffu)) { if (!sp_) break; --sp_; base = stack[sp_].base; grp = stack[sp_].g; continue; }
+            const int j = 31 - __builtin_clz(grp & 0xffu);
+            grp ^= 1u << j;
+            const uint32_t slot = (uint32_t)j ^ r.k, imask = grp >> 8;
+            const uint32_t node = base + (uint32_t)__builtin_popcount(imask & ((1u << slot) - 1u));
+            if (grp & 0xffu) { stack[sp_].base = base; stack[sp_].g = grp; ++sp_; }
+            const DWNode& w = f.wnodes[node];
+            rtww::W4 q[5]; std::memcpy(q, &w, 80);
+            uint32_t hits = rtww::wide_node_hits(q[0], q[2], q[3], q[4], r, 0.001f, t_best);
+            hits &= (uint32_t)(w.imask | w.lmask);
+            out[1]++; out[3] += (uint64_t)__builtin_popcount(w.imask | w.lmask);
+            const uint32_t m16 = rtww::wide_perm16((hits & w.imask) | ((hits & w.lmask) << 8), r.k);
+            uint32_t pl = m16 >> 8;
+            while (pl) {
+                const int jj = 31 - __builtin_clz(pl); pl ^= 1u << jj;
+                const uint32_t s2 = (uint32_t)jj ^ r.k;
+                const int pi = (int)(w.prim_base + (uint32_t)__builtin_popcount(w.lmask & ((1u << s2) - 1u)));
+                out[2]++;
+                const DPrim& q2 = f.prims[pi];
+                if (q2.type != PRIM_SPHERE || pi == pa) continue;
+                const double oc[3] = {o[0] - q2.s.cx, o[1] - q2.s.cy, o[2] - q2.s.cz};
+                const double a_ = (double)d[0] * d[0] + (double)d[1] * d[1] + (double)d[2] * d[2];
+                const double hb = oc[0] * d[0] + oc[1] * d[1] + oc[2] * d[2];
+                const double cc = oc[0] * oc[0] + oc[1] * oc[1] + oc[2] * oc[2] - q2.s.r * q2.s.r;
+                const double disc = hb * hb - a_ * cc;
+                if (disc < 0) continue;
+                const double sq = std::sqrt(disc);
+                double t = (-hb - sq) / a_;
+                if (t < 0.001 || t > t_best) { t = (-hb + sq) / a_; if (t < 0.001 || t > t_best) continue; }
+                t_best = (float)t;
+            }
+            base = w.child_base; grp = ((uint32_t)w.imask << 8) | (m16 & 0xffu);
+        }
+        out[0]++; if (t_best < INFINITY) out[4]++;
+    }
     return true;
 }
 

@@ -109,6 +109,8 @@ bool validate_wide(const FlatScene& f, std::string& err);
 // for `n_rays` seeded rays the leaves the traversal reaches must include every primitive whose box the ray really
 // crosses.  out: [0] rays, [1] node visits, [2] leaves reached, [3] boxes really crossed, [4] MISSED (must be 0).
 bool check_wide_traversal(const FlatScene& f, int n_rays, uint64_t seed, uint64_t out[5], std::string& err);
+// tuning aid: closest-hit cost of secondary-like rays through the wide tree on the CPU (rays, node visits, primitive tests, occupied slots, hits)
+bool wide_cost_probe(const FlatScene& f, int n_rays, uint64_t seed, uint64_t out[5]);
 
 // Structural check used by the CPU tests: every BVH prim referenced exactly once and inside its ancestors' boxes.
 bool validate_bvh(const FlatScene& f, std::string& err);
