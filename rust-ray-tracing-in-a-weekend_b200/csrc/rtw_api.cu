@@ -181,8 +181,9 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
 #pragma unroll 1
                     for (int i = 0; i < list_n; ++i) {
                         const int pi = tlist[warp][i];
-                        const float t = prim_root<F>(sc, pi, tr, prm.t_min, t_best, -1);
-                        if (t == t) { t_best = t; prim_best = pi; }
+                        int hp;
+                        const float t = prim_root<F>(sc, pi, tr, prm.t_min, t_best, -1, hp);
+                        if (t == t) { t_best = t; prim_best = hp; }
                     }
                 } else {
 #ifdef RTW_INSTRUMENT

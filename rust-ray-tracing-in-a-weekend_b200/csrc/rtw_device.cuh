@@ -466,14 +466,41 @@ RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, floa
     return okk ? t : CUDART_NAN_F;
 }
 
+// Box (new_box src/hittable.rs:132-145: a list of six rects, hit = hit_hittables over them, :43-55) as ONE test: the six
+// plane distances are the rects' own t = (k - o_k) / d_k; the line crosses the box between the last near plane (entry) and
+// the first far plane (exit).  Closest-of-six = the entry face if its t lies in [t_lo, t_hi], else the exit face — and a ray
+// never re-hits the face it starts on (`self_face`, the rects' rule).  Same values as six rect tests except ON an edge,
+// where the rect's closed (a, b) interval and the slab comparison may round differently (both are f32).
+// Returns t (or NaN) and the face 0..5 in new_box order: z max, z min, y max, y min, x max, x min.
+RTW_DEV float box_root(const DPrim* __restrict__ pp, V3 o, V3 d, float t_lo, float t_hi, int self_face, int& face) {
+    const float4* q = reinterpret_cast<const float4*>(pp);
+    const float4 xy = __ldg(q); const float2 z = __ldg(reinterpret_cast<const float2*>(q + 1));
+    const float rx = rcp_approx(d.x), ry = rcp_approx(d.y), rz = rcp_approx(d.z);          // (k - o) * rcp(d): rect_root's __fdividef
+    const float x0 = (xy.x - o.x) * rx, x1 = (xy.y - o.x) * rx;
+    const float y0 = (xy.z - o.y) * ry, y1 = (xy.w - o.y) * ry;
+    const float z0 = (z.x - o.z) * rz, z1 = (z.y - o.z) * rz;
+    const float nx = fminf(x0, x1), fx = fmaxf(x0, x1), ny = fminf(y0, y1), fy = fmaxf(y0, y1), nz = fminf(z0, z1), fz = fmaxf(z0, z1);
+    const float tn = fmaxf(fmaxf(nx, ny), nz), tf = fminf(fminf(fx, fy), fz);
+    // entering through the min plane when d > 0; leaving through the max plane when d > 0
+    const int fn = tn == nx ? (d.x > 0.f ? 5 : 4) : (tn == ny ? (d.y > 0.f ? 3 : 2) : (d.z > 0.f ? 1 : 0));
+    const int ff = tf == fx ? (d.x > 0.f ? 4 : 5) : (tf == fy ? (d.y > 0.f ? 2 : 3) : (d.z > 0.f ? 0 : 1));
+    const bool on = tn <= tf;
+    const bool n_ok = on && tn >= t_lo && tn <= t_hi && fn != self_face;
+    const bool f_ok = on && tf >= t_lo && tf <= t_hi && ff != self_face;
+    face = n_ok ? fn : ff;
+    return n_ok ? tn : (f_ok ? tf : CUDART_NAN_F);
+}
+
 // Any primitive: accepted root in [t_lo, t_hi] or NaN.  `skip` = primitive the ray starts on (-1: none): a planar
 // rect cannot be re-hit by a ray leaving it (exact geometry; the reference's f64 gets t ~ 1e-13 < t_min).
+// `hit` = the primitive record that describes the hit: `pi` itself, or the face rect of a box.
 // object-space ray of the last instance transform used: the faces of a Box share one (ConstantMedium boundary scans)
 struct XfCache { int xf; V3 o, d; };
 template <int F = FEAT_ALL>
-RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip, float* far_root = nullptr, XfCache* xc = nullptr) {
+RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, float t_hi, int skip, int& hit, float* far_root = nullptr, XfCache* xc = nullptr) {
     const DPrim* pp = sc.prims + pi;
     int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 3);      // type, mat, xform, 1/dt (moving sphere)
+    hit = pi;
     if (!(F & FEAT_RECT) || meta.x <= PRIM_MOVING_SPHERE) return sphere_root(pp, meta.x, __int_as_float(meta.w), r, t_lo, t_hi, pi == skip, far_root);
     if (pi == skip) return CUDART_NAN_F;
     V3 o = r.o, d = r.d;
@@ -482,6 +509,13 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
             if (xc->xf != meta.z) { xform_ray(sc, meta.z, r, xc->o, xc->d); xc->xf = meta.z; }
             o = xc->o; d = xc->d;
         } else xform_ray(sc, meta.z, r, o, d);                 // xform 0 is the identity: no branch, one instruction stream
+    }
+    if (meta.x == PRIM_BOX) {
+        const int first = __ldg(reinterpret_cast<const int*>(pp) + 6);
+        int face;
+        const float t = box_root(pp, o, d, t_lo, t_hi, skip - first, face);
+        hit = first + face;
+        return t;
     }
     return rect_root(pp, meta.x, o, d, t_lo, t_hi);
 }
@@ -607,8 +641,9 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
 #pragma unroll 1                                    // one copy of the primitive tests (the compiler unrolls by 2 when the body is small)
             for (int i = 0; i < count; ++i) {
                 RTW_DBG_PRIM();
-                float t = prim_root<F>(sc, first + i, r, t_min, t_best, skip);
-                if (t == t) { t_best = t; prim_best = first + i; }       // not NaN: accepted, t <= t_best
+                int hp;
+                float t = prim_root<F>(sc, first + i, r, t_min, t_best, skip, hp);
+                if (t == t) { t_best = t; prim_best = hp; }              // not NaN: accepted, t <= t_best
             }
             leaf = node;                                                  // a second leaf was reached meanwhile
             if (node < 0) { node = sp[-1]; --sp; }
@@ -663,8 +698,9 @@ RTW_DEV void bvh8_closest(const DScene& sc, const TRay& r, float t_min, float& t
             const uint32_t s = (uint32_t)jj ^ k;
             const int pi = (int)(m.y + __popc(lmask & ((1u << s) - 1u)));
             RTW_DBG_PRIM();
-            const float t = prim_root<F>(sc, pi, r, t_min, t_best, skip);
-            if (t == t) { t_best = t; prim_best = pi; }
+            int hp;
+            const float t = prim_root<F>(sc, pi, r, t_min, t_best, skip, hp);
+            if (t == t) { t_best = t; prim_best = hp; }
         }
         base = m.x; grp = (imask << 8) | (m16 & 0xffu);
     }
@@ -781,7 +817,8 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
             if (keep && pass == 1) { t = ts[i]; if (!(t >= lo)) t = tfar[i]; }
             else {
                 float fr = CUDART_NAN_F;                             // stays NaN for rects
-                t = prim_root(sc, md.x + i, r, keep ? -inf : lo, keep ? inf : hi, -1, &fr, &xc);
+                int hp;                                              // (boundaries keep their six rects: no box records here)
+                t = prim_root(sc, md.x + i, r, keep ? -inf : lo, keep ? inf : hi, -1, hp, &fr, &xc);
                 if (keep) { ts[i] = t; tfar[i] = fr; }
                 if (one_sphere) far_root = fr;
             }

@@ -169,8 +169,9 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                         pl ^= 1u << jj;
                         const uint32_t s2 = (uint32_t)jj ^ wr.k;
                         const int pi = (int)(m.y + __popc(lmask & ((1u << s2) - 1u)));
-                        const float t = prim_root(sc, pi, r, prm.t_min, t_best, skip);
-                        if (t == t) { t_best = t; prim_best = pi; }
+                        int hp;
+                        const float t = prim_root(sc, pi, r, prm.t_min, t_best, skip, hp);
+                        if (t == t) { t_best = t; prim_best = hp; }
                     }
                     wbase = m.x; wgrp = (imask << 8) | (m16 & 0xffu);
                     if (q_next < n_trav && __popc(__activemask()) < RTW_FETCH_THRESHOLD) break;   // refill idle lanes
@@ -201,8 +202,9 @@ RTW_DEV unsigned long long traverse_stage(PoolSmem<POOL>& P, int lane, unsigned 
                 while (leaf < 0) {
                     int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
                     for (int i = 0; i < count; ++i) {
-                        float t = prim_root(sc, first + i, r, prm.t_min, t_best, skip);
-                        if (t == t) { t_best = t; prim_best = first + i; }
+                        int hp;
+                        float t = prim_root(sc, first + i, r, prm.t_min, t_best, skip, hp);
+                        if (t == t) { t_best = t; prim_best = hp; }
                     }
                     leaf = node;
                     if (node < 0) node = (int)stack[--sp];

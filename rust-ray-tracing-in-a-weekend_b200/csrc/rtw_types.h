@@ -28,7 +28,9 @@ enum : int32_t {
     PRIM_MOVING_SPHERE = 1,  // Hittable::MovingSphere  src/hittable.rs:32
     PRIM_XY = 2,             // XYRect :34  (normal +z; a = x, b = y)
     PRIM_XZ = 3,             // XZRect :35  (normal +y; a = x, b = z)
-    PRIM_YZ = 4              // YZRect :36  (normal +x; a = y, b = z)
+    PRIM_YZ = 4,             // YZRect :36  (normal +x; a = y, b = z)
+    PRIM_BOX = 5             // Box :37 as ONE BVH leaf: slab test in object space -> entry / exit face; the six rect records of
+                             // new_box (src/hittable.rs:132-145) live behind the BVH primitives and describe the hit (first_face + face)
 };
 
 enum : int32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3, MAT_ISOTROPIC = 4 };
@@ -42,6 +44,8 @@ struct RTW_ALIGN(16) DPrim {
     union {
         struct { double cx, cy, cz, r; } s;       // sphere: centre at time0 (world space, xform baked), radius
         struct { float a0, a1, b0, b1, k, pad0, pad1, pad2; } q;   // rect (object space)
+        struct { float lox, hix, loy, hiy, loz, hiz; int32_t first_face, pad; } b;   // box (object space); faces in new_box order:
+                                                                   // z max, z min, y max, y min, x max, x min
     };
     float dcx, dcy, dcz;                          // moving sphere: centre1 - centre0
     float t0;                                     // moving sphere: time0

@@ -221,8 +221,9 @@ wf_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPara
                         pl ^= 1u << jj;
                         const uint32_t s2 = (uint32_t)jj ^ wr.k;
                         const int pi = (int)(m.y + __popc(lmask & ((1u << s2) - 1u)));
-                        const float t = prim_root<F>(sc, pi, r, prm.t_min, t_best, skip);
-                        if (t == t) { t_best = t; prim_best = pi; }
+                        int hp;
+                        const float t = prim_root<F>(sc, pi, r, prm.t_min, t_best, skip, hp);
+                        if (t == t) { t_best = t; prim_best = hp; }
                     }
                     wbase = m.x; wgrp = (imask << 8) | (m16 & 0xffu);
                     if (!exhausted && __popc(__activemask()) < RTW_WF_FETCH_THRESHOLD) break;       // let the idle lanes refill
@@ -253,8 +254,9 @@ wf_trace_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPara
                     while (leaf < 0) {
                         const int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
                         for (int q = 0; q < count; ++q) {
-                            const float t = prim_root<F>(sc, first + q, r, prm.t_min, t_best, skip);
-                            if (t == t) { t_best = t; prim_best = first + q; }
+                            int hp;
+                            const float t = prim_root<F>(sc, first + q, r, prm.t_min, t_best, skip, hp);
+                            if (t == t) { t_best = t; prim_best = hp; }
                         }
                         leaf = node;
                         if (node < 0) node = (int)stack[--sp];
@@ -349,8 +351,9 @@ wf_trace2_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPar
                 const int code = ~leaf, first = code >> 3, count = (code & 7) + 1;
 #pragma unroll 1
                 for (int q = 0; q < count; ++q) {
-                    const float t = prim_root<F>(sc, first + q, r, prm.t_min, t_best, skip);
-                    if (t == t) { t_best = t; prim_best = first + q; }
+                    int hp;
+                    const float t = prim_root<F>(sc, first + q, r, prm.t_min, t_best, skip, hp);
+                    if (t == t) { t_best = t; prim_best = hp; }
                 }
                 leaf = 0;
                 if (node < 0) { leaf = node; --sp; node = stack[sp]; }                // the second leaf reached meanwhile
@@ -441,8 +444,9 @@ wf_trace2w_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DPa
                     lgrp ^= 1u << jj;
                     const uint32_t s2 = (uint32_t)jj ^ wr.k;
                     const int pi = (int)(lbase + __popc((lgrp >> 8) & ((1u << s2) - 1u)));
-                    const float t = prim_root<F>(sc, pi, r, prm.t_min, t_best, skip);
-                    if (t == t) { t_best = t; prim_best = pi; }
+                    int hp;
+                    const float t = prim_root<F>(sc, pi, r, prm.t_min, t_best, skip, hp);
+                    if (t == t) { t_best = t; prim_best = hp; }
                 }
             }
         }

@@ -221,9 +221,35 @@ struct Flattener {
         switch (h.kind) {
         case H_SPHERE: case H_MOVING_SPHERE: return emit_sphere(h, ch, boundary);
         case H_XY: case H_XZ: case H_YZ: return emit_rect(h, ch, boundary);
-        case H_BOX:
-            for (int c : h.children) { int rc = emit(c, ch, boundary, depth + 1); if (rc) return rc; }
+        case H_BOX: {
+            // As a surface: ONE BVH leaf (PRIM_BOX: slab test -> entry / exit face) in front of the six rect records, which
+            // stay behind the BVH primitives and describe the hit.  As a ConstantMedium boundary, or when the box is flat
+            // (a slab needs an extent), or with RTW_BOX_PRIM=0: the six rects of new_box themselves.
+            const char* ebp = getenv("RTW_BOX_PRIM");                      // (read per flatten: the tests compare both forms in one process)
+            const bool box_prim = !(ebp && atoi(ebp) == 0);
+            const bool solid = h.bmax.x > h.bmin.x && h.bmax.y > h.bmin.y && h.bmax.z > h.bmin.z && h.children.size() == 6;
+            if (boundary || !box_prim || !solid) {
+                for (int c : h.children) { int rc = emit(c, ch, boundary, depth + 1); if (rc) return rc; }
+                return 0;
+            }
+            DPrim p; std::memset(&p, 0, sizeof(p));
+            p.b.lox = (float)h.bmin.x; p.b.hix = (float)h.bmax.x; p.b.loy = (float)h.bmin.y; p.b.hiy = (float)h.bmax.y; p.b.loz = (float)h.bmin.z; p.b.hiz = (float)h.bmax.z;
+            p.b.first_face = (int)boundary_prims.size();          // relative to the section behind the BVH primitives (flatten adds its offset)
+            p.type = PRIM_BOX; p.mat = h.mat - 1; p.xform = intern(ch);
+            Box3 bb;
+            const size_t nb0 = bvh_prims.size();
+            for (int c : h.children) {                           // the faces: records to the back section, their boxes joined
+                if (c < 0 || c >= (int)g.nodes.size()) return fail(RTW_ERR_INVALID_ARG, "hittable id out of range");
+                const HNode& f = g.nodes[c];
+                if (f.kind != H_XY && f.kind != H_XZ && f.kind != H_YZ) return fail(RTW_ERR_INVALID_ARG, "a Box side is not a rect");
+                int rc = emit_rect(f, ch, false); if (rc) return rc;
+                boundary_prims.push_back(bvh_prims.back()); bb.grow(bvh_boxes.back().mn); bb.grow(bvh_boxes.back().mx);
+                bvh_prims.pop_back(); bvh_boxes.pop_back();
+            }
+            (void)nb0;
+            push_prim(p, bb, false);
             return 0;
+        }
         case H_BVH_NODE: {
             std::unordered_map<uint64_t, std::vector<int>> seen;       // structural hash -> members already emitted
             for (int c : h.children) {
@@ -628,6 +654,7 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         if (!out.media.empty()) out.features |= 4;
         for (const DTex& t : out.texs) { if (t.kind == TEX_NOISE) out.features |= 8; if (t.kind == TEX_IMAGE) out.features |= 16; }
         for (DMedium& m : out.media) m.first += (int)n_all;
+        for (DPrim& p : fl.bvh_prims) if (p.type == PRIM_BOX) p.b.first_face += (int)n_all;
         out.prims.swap(fl.bvh_prims);
         out.boundary.swap(fl.boundary_prims);
         return 0;
@@ -756,8 +783,9 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
     for (const DPrim& p : fl.boundary_prims) { if (p.type >= PRIM_XY) out.features |= 1; if (p.xform) out.features |= p.type >= PRIM_XY ? 2 | 32 : 2; }
     if (!out.media.empty()) out.features |= 4;
     for (const DTex& t : out.texs) { if (t.kind == TEX_NOISE) out.features |= 8; if (t.kind == TEX_IMAGE) out.features |= 16; }
-    // boundary prims follow; shift media ranges
+    // boundary prims (and the face rects of boxes) follow; shift media ranges and the boxes' face indices
     for (DMedium& m : out.media) m.first += n;
+    for (int i = 0; i < n; ++i) if (out.prims[i].type == PRIM_BOX) out.prims[i].b.first_face += n;
     out.prims.insert(out.prims.end(), fl.boundary_prims.begin(), fl.boundary_prims.end());
     if (out.max_depth > 60) { err = "BVH deeper than the traversal stack"; return RTW_ERR_UNSUPPORTED_NESTING; }
     return 0;

@@ -997,3 +997,64 @@ def test_wavefront_progressive_and_two_gpus(pkg, gpu, monkeypatch):
         b, sb = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=3, n_gpus=2, flags=F))
         assert sa["rays"] == sb["rays"] and min(sb["units_per_device"][:2]) > 0
         assert np.abs(a - b).max() <= 2e-4 * a.max()
+
+
+def _box_mix_scene(pkg, lib):
+    """Boxes in every role the reference gives them: plain, translated, rotated + translated (src/main.rs:198-210), inside a
+    BvhNode (:399-407), with a dielectric material (rays travel INSIDE the box and leave through a face) and as the boundary
+    of a ConstantMedium (those stay six rects)."""
+    sc = pkg.Scene(lib)
+    white = sc.lambertian(sc.tex_solid((0.73, 0.73, 0.73))); red = sc.lambertian(sc.tex_solid((0.65, 0.05, 0.05)))
+    glass = sc.dielectric(1.5); metal = sc.metal((0.8, 0.85, 0.88), 0.1); light = sc.diffuse_light(sc.tex_solid((7, 7, 7)))
+    iso = sc.isotropic(sc.tex_solid((0.9, 0.9, 0.9)))
+    sc.push(sc.xz_rect(white, -400, 400, -400, 400, 0.0))
+    sc.push(sc.xz_rect(light, -150, 150, -150, 150, 500.0))
+    sc.push(sc.box((-250, 0, -80), (-150, 120, 20), red))
+    sc.push(sc.translate(sc.box((0, 0, 0), (90, 60, 90), glass), (-60.0, 0.001, -200.0)))
+    sc.push(sc.translate(sc.rotate_y(25.0, sc.box((0, 0, 0), (100, 200, 100), white)), (120.0, 0.0, 40.0)))
+    sc.push(sc.translate(sc.rotate_y(-18.0, sc.box((0, 0, 0), (80, 80, 80), metal)), (-40.0, 0.0, 90.0)))
+    rs = np.random.RandomState(5)
+    members = []
+    for i in range(9):
+        lo = np.array([rs.uniform(-300, 250), 0.0, rs.uniform(150, 330)])
+        members.append(sc.box(tuple(lo), tuple(lo + rs.uniform(20, 60, 3)), white if i % 2 else red))
+    sc.push(sc.bvh_node(members, 0.0, 1.0))
+    sc.push(sc.constant_medium(sc.translate(sc.rotate_y(40.0, sc.box((0, 0, 0), (70, 140, 70), white)), (230.0, 0.0, -150.0)), 0.01, iso))
+    cam = lambda W, H: lib.camera_new((0.0, 260.0, -750.0), (0.0, 100.0, 0.0), (0.0, 1.0, 0.0), 42.0, W / H, 0.0, 10.0, 0.0, 1.0)
+    return sc, cam
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "final_scene", "box_mix"])
+@pytest.mark.parametrize("width", [2, 8])
+def test_box_as_one_leaf_equals_six_rects(pkg, gpu, monkeypatch, name, width):
+    """A surface Box is ONE BVH leaf (PRIM_BOX: a slab test in object space gives the entry / exit face, whose rect record
+    then describes the hit) instead of the six rects of new_box (src/hittable.rs:132-145) as six leaves.  Both forms compute
+    the rects' own plane distances t = (k - o_k) / d_k, so the same paths come out — except where a ray crosses a box
+    EDGE within rounding (rect: closed (a, b) interval on the hit point; slab: comparison of plane distances).  Path by
+    path: >= 99.9 % bit-equal, the rest statistically irrelevant; equal ray counts to 1e-3; images agree in the mean."""
+    monkeypatch.setenv("RTW_BVH", str(width))
+    W, H, spp = 96, 96, 16
+    res = {}
+    for form in ("1", "0"):
+        monkeypatch.setenv("RTW_BOX_PRIM", form)
+        if name == "box_mix":
+            sc, camf = _box_mix_scene(pkg, gpu); cam = camf(W, H); bg = (0.05, 0.05, 0.08)
+        else:
+            sc, spec = pkg.scenes.build(gpu, name); cam = spec.camera(gpu, W, H); bg = spec.background
+        d = sc.debug_flatten()
+        sc.commit(1, 0)
+        p = pkg.make_params(W, H, spp, background=bg, seed=9, flags=pkg.api.RTW_FLAG_KERNEL_MEGA)
+        img, st = sc.render(cam, p)
+        ys, xs, ss = np.meshgrid(np.arange(H), np.arange(W), np.arange(spp), indexing="ij")
+        rgb, seg = sc.trace_paths(cam, p, xs.ravel(), ys.ravel(), ss.ravel())
+        res[form] = (img, st, rgb, seg, d)
+        sc.close()
+    (ia, sa, ra, ga, da), (ib, sb, rb, gb, db) = res["1"], res["0"]
+    assert da["bvh_prims"] < db["bvh_prims"] and da["prims"] > db["prims"]            # one leaf per box + its six face records
+    same = np.mean((ra == rb).all(1) & (ga == gb))
+    assert same >= 0.999, same
+    assert abs(sa["rays"] - sb["rays"]) <= 1e-3 * sb["rays"]
+    assert np.isfinite(ia).all() and abs(ia.mean() - ib.mean()) <= 0.01 * ib.mean()
+    # the render kernel traced what trace_paths traced (tile lists, ring, self-intersection rule with face indices)
+    ref = ra.reshape(H, W, spp, 3).sum(2)[::-1]
+    assert np.abs(ia - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())

@@ -144,14 +144,14 @@ def test_bvh_node_members_cloned_by_the_reference_builder_are_emitted_once(pkg, 
     sc.push(register(sc, m, reference_tree(list(range(37))), sphere))
     d = sc.debug_flatten()
     assert d["prims"] == 37 and d["dedup"] > 0, d          # prim count = object count
-    # boxes (six rects each) and moving spheres dedupe the same way; a repeated id counts as a clone too
+    # boxes (one BVH leaf + six face records each) and moving spheres dedupe the same way; a repeated id counts as a clone too
     sc = pkg.Scene(rtw)
     m = sc.lambertian(sc.tex_solid((0.7, 0.7, 0.7)))
     b1 = sc.box((0, 0, 0), (1, 1, 1), m); b2 = sc.box((0, 0, 0), (1, 1, 1), m); b3 = sc.box((0, 0, 0), (1, 1, 2), m)
     ms1 = sc.moving_sphere(m, (5, 0, 0), (5, 1, 0), 0.0, 1.0, 0.5); ms2 = sc.moving_sphere(m, (5, 0, 0), (5, 1, 0), 0.0, 1.0, 0.5)
     sc.push(sc.bvh_node([b1, b2, b3, ms1, ms2, b1], 0.0, 1.0))
     d = sc.debug_flatten()
-    assert d["prims"] == 6 + 6 + 1 and d["dedup"] == 3, d
+    assert d["bvh_prims"] == 1 + 1 + 1 and d["prims"] == 7 + 7 + 1 and d["dedup"] == 3, d
     # world-level repeats are NOT merged (the reference's world list tests both), nor are ConstantMedium members
     sc = pkg.Scene(rtw)
     m = sc.lambertian(sc.tex_solid((0.7, 0.7, 0.7))); iso = sc.isotropic(sc.tex_solid((1, 1, 1)))
@@ -190,15 +190,17 @@ def test_unsupported_nesting_is_reported(pkg, rtw):
     assert e.value.code == -2
 
 
-@pytest.mark.parametrize("name,prims,media,xforms", [
-    ("random_scene", None, 0, 1), ("two_spheres", 2, 0, 1), ("two_perlin_spheres", 2, 0, 1), ("earth", 1, 0, 1),
-    ("simple_light", 3, 0, 1), ("cornell_box", 18, 0, 3), ("cornell_box_smoke", 18, 2, 3),
-    ("final_scene", 400 * 6 + 1 + 1 + 2 + 1 + 2 + 1000 + 2, 2, 2)])
-def test_flatten_reference_compositions(pkg, rtw, name, prims, media, xforms):
+# (records, BVH leaves): a surface Box is ONE leaf (PRIM_BOX) + its six face records behind the BVH primitives; the boxes of
+# cornell_box_smoke are ConstantMedium boundaries and stay six rects each
+@pytest.mark.parametrize("name,prims,bvh_prims,media,xforms", [
+    ("random_scene", None, None, 0, 1), ("two_spheres", 2, 2, 0, 1), ("two_perlin_spheres", 2, 2, 0, 1), ("earth", 1, 1, 0, 1),
+    ("simple_light", 3, 3, 0, 1), ("cornell_box", 6 + 2 * 7, 6 + 2, 0, 3), ("cornell_box_smoke", 18, 6, 2, 3),
+    ("final_scene", 400 * 7 + 1 + 1 + 2 + 1 + 2 + 1000 + 2, 400 + 1 + 1 + 2 + 1 + 2 + 1000, 2, 2)])
+def test_flatten_reference_compositions(pkg, rtw, name, prims, bvh_prims, media, xforms):
     sc, spec = pkg.scenes.build(rtw, name)
     d = sc.debug_flatten()                 # also runs the structural BVH validation
     if prims is not None:
-        assert d["prims"] == prims
+        assert d["prims"] == prims and d["bvh_prims"] == bvh_prims
     else:
         assert d["prims"] == 1 + sum(spec.info.values()) + 3
     assert d["media"] == media and d["xforms"] == xforms and d["depth"] <= 60
@@ -361,7 +363,8 @@ def test_wide_bvh_structure_and_conservative_traversal(pkg, rtw, name):
 def test_flatten_random_scene_graphs(pkg, rtw):
     """Random compositions of the reference's Hittable variants (src/hittable.rs:29-41): spheres, moving spheres,
     rects, boxes, Translate / RotateY wrappers up to the supported depth, BvhNodes of mixed members, media over
-    spheres and (instanced) boxes.  Flatten must account for every surface primitive (a Box is 6 rects), count media,
+    spheres and (instanced) boxes.  Flatten must account for every surface primitive (a surface Box is one BVH leaf in
+    front of its six face records; a Box that bounds a medium is six boundary rects), count media,
     and produce a BVH that passes the structural validation; deeper wrapper chains are refused with
     RTW_ERR_UNSUPPORTED_NESTING, never mis-flattened."""
     rs = np.random.RandomState(2024)
@@ -369,7 +372,7 @@ def test_flatten_random_scene_graphs(pkg, rtw):
         sc = pkg.Scene(rtw)
         mat = sc.lambertian(sc.tex_solid((0.5, 0.5, 0.5)))
         iso = sc.isotropic(sc.tex_solid((1.0, 1.0, 1.0)))
-        n_surface = n_boundary = n_media = 0
+        n_surface = n_boundary = n_media = n_faces = 0
         too_deep = False
 
         def leaf():
@@ -397,26 +400,26 @@ def test_flatten_random_scene_graphs(pkg, rtw):
             if kind == 0:                                            # wrapped leaf
                 h, n = leaf()
                 too_deep |= depth > 4
-                sc.push(wrap(h, depth)); n_surface += n
+                sc.push(wrap(h, depth)); n_surface += 1; n_faces += 6 if n == 6 else 0
             elif kind == 1:                                          # BvhNode of leaves, possibly wrapped as a whole
                 members = [leaf() for _ in range(rs.randint(1, 9))]
                 node = sc.bvh_node([m[0] for m in members], 0.0, 1.0)
                 too_deep |= depth > 4
-                sc.push(wrap(node, depth)); n_surface += sum(m[1] for m in members)
+                sc.push(wrap(node, depth)); n_surface += len(members); n_faces += sum(6 for m in members if m[1] == 6)
             elif kind == 2:                                          # medium over a sphere or an instanced box
                 h, n = leaf()
                 d = min(depth, 4)
                 sc.push(sc.constant_medium(wrap(h, d), float(rs.uniform(0.001, 0.5)), iso)); n_boundary += n; n_media += 1
             else:
                 h, n = leaf()
-                sc.push(h); n_surface += n
+                sc.push(h); n_surface += 1; n_faces += 6 if n == 6 else 0
         if too_deep:
             with pytest.raises(pkg.RtwError) as e:
                 sc.debug_flatten()
             assert e.value.code == -2
         else:
             d = sc.debug_flatten()                                   # flatten + BVH + validate_bvh
-            assert d["bvh_prims"] == n_surface and d["prims"] == n_surface + n_boundary and d["media"] == n_media, trial
+            assert d["bvh_prims"] == n_surface and d["prims"] == n_surface + n_faces + n_boundary and d["media"] == n_media, trial
             if d["bvh_width"] == 2:
                 assert d["nodes"] == max(1, n_surface - 1)           # one primitive per leaf
             else:
