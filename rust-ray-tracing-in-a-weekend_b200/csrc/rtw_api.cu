@@ -668,10 +668,11 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 // kernel choice: 0 = megakernel (one path per lane), 1..4 = warp-pool kernel with 64/128/192/256 slots per warp, 5 = wavefront
 // pipeline (path pool in HBM).  Chosen by measurement: the megakernel wins wherever the scene
 // sits in L1 / L2 (C1 - C4: the wavefront pipeline is 2x slower there), the wavefront pipeline over the 8-wide tree wins on
-// scenes beyond the caches (1 M / 4 M spheres: 1.32x / 1.38x).  Flags and RTW_KERNEL override.
+// scenes beyond the caches (256 Ki / 512 Ki / 1 M / 4 M / 16 M spheres: 1.24x / 1.24x / 1.30x / 1.38x / 1.52x); the switch
+// sits at 256 Ki primitives, the smallest size measured.  Flags and RTW_KERNEL override.
 long long big_scene_min() {
     static long long v = -1;
-    if (v < 0) { v = 1ll << 20; if (const char* e = getenv("RTW_BIG_MIN")) v = std::max(1ll, atoll(e)); }
+    if (v < 0) { v = 1ll << 18; if (const char* e = getenv("RTW_BIG_MIN")) v = std::max(1ll, atoll(e)); }
     return v;
 }
 int kernel_mode(const rtw_scene* s, int flags) {
@@ -1169,7 +1170,7 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     if (first_device < 0 || n_gpus < 1 || first_device + n_gpus > ndev || n_gpus > 8) return fail(RTW_ERR_INVALID_ARG, "device range not available");
     double t0 = now_ms();
     std::string err;
-    // Where the BVH is built.  Big scenes (RTW_BIG_MIN primitives, default 1 Mi; RTW_DEVICE_BUILD_MIN overrides) are built ON THE
+    // Where the BVH is built.  Big scenes (RTW_BIG_MIN primitives, default 256 Ki; RTW_DEVICE_BUILD_MIN overrides) are built ON THE
     // DEVICE from what the constructors were given (bvh_build.cu): 16 M spheres commit in 0.24 s instead of 5.1 s.  As 8-wide
     // nodes under the wavefront pipeline the LBVH renders as fast as the host's binned-SAH tree (1 M: 378 vs 382, 4 M: 306 vs
     // 304 Mpaths/s, profiles/r2_v_wavefront_variants.log; as binary nodes under the megakernel it was ~6 % slower).  Small

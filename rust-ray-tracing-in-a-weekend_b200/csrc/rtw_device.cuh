@@ -472,7 +472,7 @@ RTW_DEV float rect_root(const DPrim* __restrict__ pp, int type, V3 o, V3 d, floa
 // never re-hits the face it starts on (`self_face`, the rects' rule).  Same values as six rect tests except ON an edge,
 // where the rect's closed (a, b) interval and the slab comparison may round differently (both are f32).
 // Returns t (or NaN) and the face 0..5 in new_box order: z max, z min, y max, y min, x max, x min.
-RTW_DEV float box_root(const DPrim* __restrict__ pp, V3 o, V3 d, float t_lo, float t_hi, int self_face, int& face) {
+RTW_DEV float box_root(const DPrim* __restrict__ pp, V3 o, V3 d, float t_lo, float t_hi, int self_face, int& face, float* far_root = nullptr) {
     const float4* q = reinterpret_cast<const float4*>(pp);
     const float4 xy = __ldg(q); const float2 z = __ldg(reinterpret_cast<const float2*>(q + 1));
     const float rx = rcp_approx(d.x), ry = rcp_approx(d.y), rz = rcp_approx(d.z);          // (k - o) * rcp(d): rect_root's __fdividef
@@ -488,6 +488,7 @@ RTW_DEV float box_root(const DPrim* __restrict__ pp, V3 o, V3 d, float t_lo, flo
     const bool n_ok = on && tn >= t_lo && tn <= t_hi && fn != self_face;
     const bool f_ok = on && tf >= t_lo && tf <= t_hi && ff != self_face;
     face = n_ok ? fn : ff;
+    if (far_root) *far_root = on ? tf : CUDART_NAN_F;          // the other crossing (ConstantMedium boundary: the second probe's hit)
     return n_ok ? tn : (f_ok ? tf : CUDART_NAN_F);
 }
 
@@ -513,7 +514,7 @@ RTW_DEV float prim_root(const DScene& sc, int pi, const TRay& r, float t_lo, flo
     if (meta.x == PRIM_BOX) {
         const int first = __ldg(reinterpret_cast<const int*>(pp) + 6);
         int face;
-        const float t = box_root(pp, o, d, t_lo, t_hi, skip - first, face);
+        const float t = box_root(pp, o, d, t_lo, t_hi, skip >= 0 ? skip - first : -1, face, far_root);
         hit = first + face;
         return t;
     }
@@ -817,7 +818,7 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
             if (keep && pass == 1) { t = ts[i]; if (!(t >= lo)) t = tfar[i]; }
             else {
                 float fr = CUDART_NAN_F;                             // stays NaN for rects
-                int hp;                                              // (boundaries keep their six rects: no box records here)
+                int hp;                                              // (a Box boundary is ONE record: its slab test yields both crossings)
                 t = prim_root(sc, md.x + i, r, keep ? -inf : lo, keep ? inf : hi, -1, hp, &fr, &xc);
                 if (keep) { ts[i] = t; tfar[i] = fr; }
                 if (one_sphere) far_root = fr;

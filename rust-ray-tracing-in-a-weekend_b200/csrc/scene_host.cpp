@@ -223,12 +223,13 @@ struct Flattener {
         case H_XY: case H_XZ: case H_YZ: return emit_rect(h, ch, boundary);
         case H_BOX: {
             // As a surface: ONE BVH leaf (PRIM_BOX: slab test -> entry / exit face) in front of the six rect records, which
-            // stay behind the BVH primitives and describe the hit.  As a ConstantMedium boundary, or when the box is flat
-            // (a slab needs an extent), or with RTW_BOX_PRIM=0: the six rects of new_box themselves.
+            // stay behind the BVH primitives and describe the hit.  As a ConstantMedium boundary: ONE record, the slab test
+            // yields both crossings.  When the box is flat (a slab needs an extent), or with RTW_BOX_PRIM=0: the six rects
+            // of new_box themselves.
             const char* ebp = getenv("RTW_BOX_PRIM");                      // (read per flatten: the tests compare both forms in one process)
             const bool box_prim = !(ebp && atoi(ebp) == 0);
             const bool solid = h.bmax.x > h.bmin.x && h.bmax.y > h.bmin.y && h.bmax.z > h.bmin.z && h.children.size() == 6;
-            if (boundary || !box_prim || !solid) {
+            if (!box_prim || !solid) {
                 for (int c : h.children) { int rc = emit(c, ch, boundary, depth + 1); if (rc) return rc; }
                 return 0;
             }
@@ -236,6 +237,11 @@ struct Flattener {
             p.b.lox = (float)h.bmin.x; p.b.hix = (float)h.bmax.x; p.b.loy = (float)h.bmin.y; p.b.hiy = (float)h.bmax.y; p.b.loz = (float)h.bmin.z; p.b.hiz = (float)h.bmax.z;
             p.b.first_face = (int)boundary_prims.size();          // relative to the section behind the BVH primitives (flatten adds its offset)
             p.type = PRIM_BOX; p.mat = h.mat - 1; p.xform = intern(ch);
+            if (boundary) {                  // a medium only needs the two crossings (hit_constant_medium :417-473): no face records
+                p.b.first_face = -(1 << 30);
+                boundary_prims.push_back(p);
+                return 0;
+            }
             Box3 bb;
             const size_t nb0 = bvh_prims.size();
             for (int c : h.children) {                           // the faces: records to the back section, their boxes joined
@@ -609,7 +615,7 @@ int collapse_to_wide(const rtww::B2View& v, std::vector<DWNode>& wnodes, std::ve
     return alloc.max_depth;
 }
 
-int kWideMinPrims = 1 << 20;             // 8-wide nodes from 1 Mi primitives (the wavefront pipeline's range); RTW_BIG_MIN / RTW_WIDE_MIN / RTW_BVH override
+int kWideMinPrims = 1 << 18;             // 8-wide nodes from 256 Ki primitives (the wavefront pipeline's range); RTW_BIG_MIN / RTW_WIDE_MIN / RTW_BVH override
 int choose_bvh_width(long long n, int requested) {
     int width = requested;
     if (width == 0) { if (const char* e = getenv("RTW_BVH")) width = atoi(e); }
@@ -654,7 +660,7 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         if (!out.media.empty()) out.features |= 4;
         for (const DTex& t : out.texs) { if (t.kind == TEX_NOISE) out.features |= 8; if (t.kind == TEX_IMAGE) out.features |= 16; }
         for (DMedium& m : out.media) m.first += (int)n_all;
-        for (DPrim& p : fl.bvh_prims) if (p.type == PRIM_BOX) p.b.first_face += (int)n_all;
+        for (DPrim& p : fl.bvh_prims) if (p.type == PRIM_BOX) p.b.first_face += (int)n_all;       // (boundary boxes have no faces)
         out.prims.swap(fl.bvh_prims);
         out.boundary.swap(fl.boundary_prims);
         return 0;
