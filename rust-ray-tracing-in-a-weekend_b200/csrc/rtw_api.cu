@@ -471,6 +471,7 @@ struct Replica {
     cudaStream_t wf_stream[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] = stream
     cudaEvent_t wf_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     uint8_t* wf_mem = nullptr;
+    float* wf_fb = nullptr; size_t wf_fb_floats = 0;      // local framebuffer of a GPU that does not own the shared one (merged once per frame)
     int wf_grid[4] = {0, 0, 0, 0};          // trace kernel grids: [F != 0][W]
 };
 
@@ -510,6 +511,7 @@ void free_replicas(rtw_scene* s) {
         if (r.blob) cudaFree(r.blob);
         rtwb::free_output(r.built);
         if (r.wf_mem) cudaFree(r.wf_mem);
+        if (r.wf_fb) cudaFree(r.wf_fb);
         for (int k = 1; k < 4; ++k) if (r.wf_stream[k]) cudaStreamDestroy(r.wf_stream[k]);
         for (int k = 0; k < 4; ++k) if (r.wf_ev[k]) cudaEventDestroy(r.wf_ev[k]);
         if (r.stats) cudaFree(r.stats);
@@ -828,12 +830,29 @@ int wf_render_replica(rtw_scene* s, Replica& r, const DCamera& dc, const DParams
     const unsigned long long total = (unsigned long long)dp.tiles_x * dp.tiles_y * 32ull * (unsigned long long)dp.spp;
     TRY(wf_ensure_pool(r, (long long)std::min<unsigned long long>(total, 1ull << 40)));
     unsigned long long* path_counter = reinterpret_cast<unsigned long long*>(counter) + 1;     // second word of the zeroed header
+    // the framebuffer of another GPU (in-process peer or IPC mapping): accumulate locally, merge once at the end of the frame
+    float* target = fb;
+    const size_t n_floats = (size_t)dp.width * dp.height * 3;
+    {
+        cudaPointerAttributes at{};
+        const bool remote = cudaPointerGetAttributes(&at, fb) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != r.device;
+        cudaGetLastError();
+        if (remote) {
+            if (r.wf_fb_floats < n_floats) {
+                if (r.wf_fb) { CUDA_TRY(cudaFree(r.wf_fb)); r.wf_fb = nullptr; }
+                CUDA_TRY(cudaMalloc(&r.wf_fb, n_floats * sizeof(float))); r.wf_fb_floats = n_floats;
+                CUDA_TRY(cudaMemsetAsync(r.wf_fb, 0, n_floats * sizeof(float), r.stream));
+            }
+            target = r.wf_fb;
+        }
+    }
     CUDA_TRY(cudaEventRecord(r.ev0, r.stream));
     const bool plain = s->flat.features == 0;
     int rc;
-    if (s->flat.wide) rc = plain ? wf_run<0, 1>(s, r, dc, dp, path_counter, total, fb) : wf_run<FEAT_ALL, 1>(s, r, dc, dp, path_counter, total, fb);
-    else rc = plain ? wf_run<0, 0>(s, r, dc, dp, path_counter, total, fb) : wf_run<FEAT_ALL, 0>(s, r, dc, dp, path_counter, total, fb);
+    if (s->flat.wide) rc = plain ? wf_run<0, 1>(s, r, dc, dp, path_counter, total, target) : wf_run<FEAT_ALL, 1>(s, r, dc, dp, path_counter, total, target);
+    else rc = plain ? wf_run<0, 0>(s, r, dc, dp, path_counter, total, target) : wf_run<FEAT_ALL, 0>(s, r, dc, dp, path_counter, total, target);
     if (rc < 0) return rc;
+    if (target != fb) { wf_merge_kernel<<<r.sms * 8, 256, 0, r.stream>>>(target, fb, n_floats); CUDA_TRY(cudaGetLastError()); }
     CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
     CUDA_TRY(cudaStreamSynchronize(r.stream));
     float e = 0; CUDA_TRY(cudaEventElapsedTime(&e, r.ev0, r.ev1));

@@ -148,6 +148,16 @@ wf_logic_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCame
     if (lane == 0 && ma) atomicAdd(&pool.ctr[1], (unsigned long long)__popc(ma));
 }
 
+// Multi-GPU: a GPU that does not own the framebuffer accumulates its paths in a LOCAL framebuffer and adds it to the owner's
+// once, at the end of the frame (the north star's "final framebuffer gathered to GPU 0 over NVLink"; src/main.rs:542-547) —
+// instead of three remote atomics per finished path.  Only pixels this GPU touched travel; the local buffer is left zeroed.
+__global__ void wf_merge_kernel(float* __restrict__ local, float* __restrict__ remote, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = local[i];
+        if (v != 0.f) { atomicAdd_system(remote + i, v); local[i] = 0.f; }
+    }
+}
+
 // Persistent trace kernel: closest surface hit (hit_hittables src/hittable.rs:43-55 over the whole world) for every slot
 // that holds a ray.  Lanes fetch slots dynamically; W = 0 binary nodes, W = 1 8-wide compressed nodes.
 #define RTW_WF_FETCH_THRESHOLD 20
