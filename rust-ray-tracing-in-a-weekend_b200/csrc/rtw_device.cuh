@@ -564,6 +564,32 @@ RTW_DEV bool slab(float mnx, float mxx, float mny, float mxy, float mnz, float m
     return tn <= tf;
 }
 
+// The megakernel's variant with ONE slack term shared by the three axes (4 ulp of the largest |o_k/d_k|, folded into the exit
+// distance's padding FFMA): two registers fewer than the per-axis form in a kernel that sits at its register cap.  Equally
+// conservative; the price is that a ray with |d_k| ~ 1e-7 |d| opens every box on the other two axes — harmless where a warp
+// only loses a few hundred node visits to such a ray (scenes below RTW_BIG_MIN under the megakernel), fatal for the
+// persistent trace kernel of the wavefront pipeline, where one such ray holds a whole launch (rtw_wavefront.cuh).
+// Measured (profiles/r2_z_slab_ab.log): C1 101.65 -> 100.80 ms with the shared term, cornell_box 147.5 -> 148.9, final_scene
+// 454.7 -> 456.2: it pays only in the spheres-only variant (F == 0), which is where it is used (-1 = that rule; 0 / 1 force).
+#ifndef RTW_SLAB_SHARED
+#define RTW_SLAB_SHARED -1
+#endif
+RTW_DEV void slab_setup_shared(V3 o, V3 d, V3& inv, V3& oi, float& slack) {
+    inv = mk(rcp_approx(slab_dir(d.x)), rcp_approx(slab_dir(d.y)), rcp_approx(slab_dir(d.z)));
+    oi = mk(o.x * inv.x, o.y * inv.y, o.z * inv.z);
+    const float ax = fabsf(d.x) < 1e-20f ? 0.f : fabsf(oi.x), ay = fabsf(d.y) < 1e-20f ? 0.f : fabsf(oi.y), az = fabsf(d.z) < 1e-20f ? 0.f : fabsf(oi.z);
+    slack = 2.384185791015625e-07f * fmaxf(fmaxf(ax, ay), az);
+}
+RTW_DEV bool slab_shared(float mnx, float mxx, float mny, float mxy, float mnz, float mxz, V3 inv, V3 oi, float slack, float t_lo, float t_hi, float& t_enter) {
+    float x0 = fmaf(mnx, inv.x, -oi.x), x1 = fmaf(mxx, inv.x, -oi.x);
+    float y0 = fmaf(mny, inv.y, -oi.y), y1 = fmaf(mxy, inv.y, -oi.y);
+    float z0 = fmaf(mnz, inv.z, -oi.z), z1 = fmaf(mxz, inv.z, -oi.z);
+    float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), t_lo));
+    float tf = fmaf(fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_hi)), 1.0000006f, slack);
+    t_enter = tn;
+    return tn <= tf;
+}
+
 #define RTW_STACK 64
 #ifndef RTW_SPECULATIVE
 #define RTW_SPECULATIVE 1
@@ -589,8 +615,10 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
 #endif
                          ) {
     if (sc.n_bvh_prims == 0) return;
-    V3 inv, cmn, cmx;
-    slab_setup(r.o, r.d, inv, cmn, cmx);
+    constexpr bool SH = RTW_SLAB_SHARED < 0 ? (F == 0) : (RTW_SLAB_SHARED != 0);
+    V3 inv, cmn, cmx; float slack = 0.f;                 // shared form: cmn = o / d, cmx unused
+    if (SH) { slab_setup_shared(r.o, r.d, inv, cmn, slack); cmx = cmn; }
+    else slab_setup(r.o, r.d, inv, cmn, cmx);
     int stack[RTW_STACK];
     stack[0] = RTW_SENTINEL;
     int* sp = stack + 1;                          // points at the next free entry
@@ -610,8 +638,10 @@ RTW_DEV void bvh_closest(const DScene& sc, const TRay& r, float t_min, float& t_
             float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             int2 ch = __ldg(reinterpret_cast<const int2*>(np + 3));
             float e0, e1;
-            const bool h0 = slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, cmn, cmx, t_min, t_best, e0);
-            const bool h1 = slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, cmn, cmx, t_min, t_best, e1);
+            const bool h0 = SH ? slab_shared(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, cmn, slack, t_min, t_best, e0)
+                               : slab(n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, inv, cmn, cmx, t_min, t_best, e0);
+            const bool h1 = SH ? slab_shared(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, cmn, slack, t_min, t_best, e1)
+                               : slab(n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, inv, cmn, cmx, t_min, t_best, e1);
             // straight-line child selection: nearer hit child next, the other one pushed
             const bool closer1 = e1 < e0;
             const bool second = h1 & (!h0 | closer1);
