@@ -768,7 +768,8 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
                 else put_box((size_t)(n_inner + bn.first), bn.box);
             }
         });
-        static const bool fill = !(getenv("RTW_WIDE_FILL") && atoi(getenv("RTW_WIDE_FILL")) == 0);     // A/B switch
+        const char* efill = getenv("RTW_WIDE_FILL");                              // A/B switch, read per flatten
+        const bool fill = !(efill && atoi(efill) == 0);
         rtww::B2View view{box.data(), left.data(), right.data(), n_inner, n, fill ? count.data() : nullptr};
         std::vector<int> order;
         out.wide_depth = collapse_to_wide(view, out.wnodes, order);

@@ -452,3 +452,48 @@ def test_public_header_is_plain_c(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True, cwd=tmp_path)
     assert r.returncode == 0 and r.stdout.split() == ["1", "1", "1", "0", "0"], (r.stdout, r.stderr)
     assert (tmp_path / "o.ppm").read_text() == "P3\n2 1\n255\n\n1 2 3\n4 5 6\n"
+
+
+def test_wide_collapse_absorbs_small_subtrees(pkg, rtw, monkeypatch):
+    """Collapse heuristic of the 8-wide tree (csrc/bvh_wide.h collapse_one): subtrees of more than 8 leaves are opened by
+    surface area, a subtree of at most 8 leaves is either absorbed whole (all its leaves become slots of the node) or left
+    as one child — never opened half-way.  Against the plain area-greedy collapse (RTW_WIDE_FILL=0) that removes the 2-3-leaf
+    nodes at the bottom of the tree: fewer nodes, the same conservative traversal, and no more work per ray (host-only cost
+    probe: closest-hit traversal of secondary-like rays on the CPU with the device's node test)."""
+    res = {}
+    for fill in ("0", "1"):
+        monkeypatch.setenv("RTW_WIDE_FILL", fill)
+        sc = pkg.Scene(rtw)
+        pkg.scenes.sweep_scene(sc, 60000, seed=8)
+        d = sc.debug_wide(300, seed=4)                       # validates the structure and the conservative traversal
+        c = sc.debug_wide_cost(4000, seed=2)
+        assert d["missed"] == 0 and c["rays"] == 4000 and c["hits"] > 0
+        res[fill] = (d, c)
+        sc.close()
+    (d0, c0), (d1, c1) = res["0"], res["1"]
+    n = d1["bvh_prims"]
+    assert d1["wide_nodes"] < 0.7 * d0["wide_nodes"] and d1["wide_nodes"] < n / 4         # measured: 24 822 -> 11 064 nodes (5.4 primitives per node)
+    # (the probe aims its rays at primitives by index, and the leaf order differs between the two trees: same distribution, not the same rays)
+    assert c1["node_visits"] <= 1.05 * c0["node_visits"] and c1["prim_tests"] <= 1.05 * c0["prim_tests"]
+    assert abs(c0["hits"] - c1["hits"]) <= 0.03 * c0["hits"]
+
+
+def test_box_flattens_to_one_leaf_and_six_face_records(pkg, rtw, monkeypatch):
+    """new_box (src/hittable.rs:132-145) on the device: ONE PRIM_BOX leaf in the BVH, its six rects as face records behind the
+    BVH primitives (they describe the hit), ONE record when the box bounds a ConstantMedium; a flat box (no extent on one axis)
+    and RTW_BOX_PRIM=0 keep the six rects as leaves."""
+    def counts(build):
+        sc = pkg.Scene(rtw)
+        m = sc.lambertian(sc.tex_solid((0.5, 0.5, 0.5))); iso = sc.isotropic(sc.tex_solid((1, 1, 1)))
+        build(sc, m, iso)
+        d = sc.debug_flatten(); sc.close()
+        return d["bvh_prims"], d["prims"], d["media"]
+    solid = lambda sc, m, iso: sc.push(sc.translate(sc.rotate_y(15.0, sc.box((0, 0, 0), (1, 2, 3), m)), (1.0, 0.0, 0.0)))
+    flat = lambda sc, m, iso: sc.push(sc.box((0, 0, 0), (1, 0, 3), m))
+    fog = lambda sc, m, iso: sc.push(sc.constant_medium(sc.box((0, 0, 0), (1, 2, 3), m), 0.1, iso))
+    assert counts(solid) == (1, 7, 0)
+    assert counts(flat) == (6, 6, 0)
+    assert counts(fog) == (0, 1, 1)
+    monkeypatch.setenv("RTW_BOX_PRIM", "0")
+    assert counts(solid) == (6, 6, 0)
+    assert counts(fog) == (0, 6, 1)
