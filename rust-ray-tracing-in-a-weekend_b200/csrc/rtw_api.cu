@@ -851,7 +851,7 @@ int wf_render_replica(rtw_scene* s, Replica& r, const DCamera& dc, const DParams
     int rc;
     if (s->flat.wide) rc = plain ? wf_run<0, 1>(s, r, dc, dp, path_counter, total, target) : wf_run<FEAT_ALL, 1>(s, r, dc, dp, path_counter, total, target);
     else rc = plain ? wf_run<0, 0>(s, r, dc, dp, path_counter, total, target) : wf_run<FEAT_ALL, 0>(s, r, dc, dp, path_counter, total, target);
-    if (rc < 0) return rc;
+    if (rc < 0) { if (target != fb) cudaMemsetAsync(target, 0, n_floats * sizeof(float), r.stream); return rc; }     // (the local framebuffer is always left zeroed)
     if (target != fb) { wf_merge_kernel<<<r.sms * 8, 256, 0, r.stream>>>(target, fb, n_floats); CUDA_TRY(cudaGetLastError()); }
     CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
     CUDA_TRY(cudaStreamSynchronize(r.stream));
