@@ -11,12 +11,15 @@
 //               counter (src/main.rs:517-520), so the pool stays full until the image runs out of samples.
 //   wf_trace  : persistent warps with DYNAMIC RAY FETCH: a lane that finishes its ray stores (t, primitive) and takes the
 //               next slot from a cursor, so all 32 lanes keep traversing whatever the spread of traversal lengths; the
-//               queue is millions of rays long, there is no per-stage tail.  Binary or 8-wide nodes (template W).
+//               queue is millions of rays long, there is no per-stage tail.  Default: the LOCKSTEP loop over 8-wide nodes
+//               (wf_trace2w_kernel); the speculative while-while loop (wf_trace_kernel<F, W>) and the lockstep loop over
+//               binary nodes (wf_trace2_kernel) are the measured alternatives.
 //
 // Queue traffic per ray segment: 48 B read + 8 B written by the trace kernel, 72 B read + 64 B written by the logic kernel,
 // all float4 / uint2, slot-indexed (coalesced).  Paths are numbered so that 32 consecutive ones are the 32 pixels of a tile at
 // one sample; path numbers are handed out in chunks of 2^20 from ONE counter that all GPUs share (dynamic balance, ~2 000
-// remote atomics per frame), finished paths are added to the framebuffer on the first GPU with red.global.add.f32.
+// remote atomics per frame); finished paths are added to the framebuffer — directly on the GPU that owns it, through a local
+// framebuffer merged once per frame on the others (wf_merge_kernel).
 #ifndef RTW_WAVEFRONT_CUH
 #define RTW_WAVEFRONT_CUH
 

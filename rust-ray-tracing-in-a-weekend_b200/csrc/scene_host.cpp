@@ -1,7 +1,8 @@
 // scene_host.cpp — flatten the reference-shaped scene graph into SoA device records + a linearised BVH.
 //
 // What is mirrored (semantics) and what is deliberately not (structure):
-//  * Box = its 6 rects in new_box order (src/hittable.rs:132-145); closest-of-six == six rects in the BVH.
+//  * Box = its 6 rects in new_box order (src/hittable.rs:132-145); closest-of-six == ONE slab test that names the entry / exit
+//    face (PRIM_BOX leaf; the six rect records stay behind the BVH primitives and describe the hit).  Flat boxes keep six rect leaves.
 //  * Translate / RotateY wrap a subtree (src/hittable.rs:232-247, :386-415): the chain of wrappers above a
 //    primitive is composed into one DXform; spheres are baked to world space (a rigid motion of a sphere is a
 //    sphere), rects keep object coordinates and the ray is moved into object space at test time.
