@@ -64,6 +64,15 @@ __device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; 
 #ifndef RTW_MIN_BLOCKS
 #define RTW_MIN_BLOCKS 7
 #endif
+// Carry-over of the last rays of a work unit into the next one (1): when a unit has no more paths to start and its ring can no
+// longer fill the idle lanes, the warp does not run the rest of the unit under-occupied (the "drain": 3.4 % of C1 at the
+// 8-GPU unit sizes, profiles/r2_ab_units_tile_list_share.log) — it flushes the tile, keeps the rays that are still in flight
+// (lanes + ring) as ORPHANS of the old tile and starts the next unit's primary batches around them.  Orphans carry one bit in
+// their pixel field and add their radiance straight to the framebuffer (global atomics: a few dozen paths per unit) instead of
+// the tile accumulator; at most one generation of orphans is in flight per warp (a counter in shared memory).
+#ifndef RTW_CARRY
+#define RTW_CARRY 1
+#endif
 #ifndef RTW_COOP
 #define RTW_COOP 1          // unit-ball samples drawn by the whole warp (coop_unit_sphere); 0 = every lane loops on its own
 #endif
@@ -76,6 +85,10 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
     __shared__ float ring[RTW_WARPS][12][64];             // secondary-ray ring: o(3) d(3) time T(3) last_prim meta, 64 per warp
     __shared__ int tlist[RTW_WARPS][RTW_TILE_LIST];       // primitives the tile's primary rays can touch
     __shared__ int coop_scr[RTW_WARPS][32];               // coop_unit_sphere: failed-lane directory
+#if RTW_CARRY
+    __shared__ int carry_s[RTW_WARPS][4];                 // orphans in flight, tile x / y of their unit
+    __shared__ int tl_scratch[RTW_WARPS][136];            // build_tile_list scratch (the ring is in use across units)
+#endif
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     unsigned long long rays = 0, units = 0;
@@ -87,27 +100,44 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
 #ifdef RTW_INSTRUMENT
     if (lane == 0) { const unsigned long long t = dbg_now(); atomicMin(&g_dbg_time[0], t); atomicMax(&g_dbg_time[1], t); }
 #endif
+    // (measured per variant, profiles/r2_ac_carry.log: it pays where the kernel has registers to spare — C1 at the 8-GPU unit
+    // sizes -2 %, at full-frame small units 105.7 -> 102.1 ms, two_spheres -5 %, two_perlin_spheres -3 %, cornell_box -1 % — and
+    // costs in the variants that carry the media code: final_scene +2.7 %, cornell_box_smoke +7 %: off there)
+    constexpr bool kCarry = RTW_CARRY != 0 && !(F & FEAT_MEDIA) && F != FEAT_IMAGE;       // (earth, 1.3 rays per path, 2.3 ms: +5 % with it)
+    int pix = 0, ring_head = 0, ring_count = 0;                // (carry: these survive from unit to unit)
+    bool alive = false, no_more = false;
+#if RTW_CARRY
+    if (lane == 0) carry_s[warp][0] = 0;
+    __syncwarp();
+#endif
     for (;;) {
         unsigned unit = 0;
-        if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0) * prm.unit_stride;
-        if (unit >= prm.n_units) break;
-        ++units;
-        int tile, s0, s1;
-        decode_unit(prm, unit, tile, s0, s1);
+        int tile = 0, s0 = 0, s1 = 0;
+        if (!no_more) {
+            if (lane == 0) unit = atomicAdd_system(unit_counter, 1u);
+            unit = __shfl_sync(0xffffffffu, unit, 0) * prm.unit_stride;
+            no_more = unit >= prm.n_units;
+        }
+        if (no_more && (!kCarry || (ring_count == 0 && !__any_sync(0xffffffffu, alive)))) break;     // no unit left and nothing carried over
+        const bool have_unit = !no_more;                       // (false: a last pass that only finishes the orphans)
+        if (have_unit) { ++units; decode_unit(prm, unit, tile, s0, s1); }
+        if (!kCarry) { pix = 0; ring_head = 0; ring_count = 0; alive = false; }
         const int tx = tile % prm.tiles_x, ty = tile / prm.tiles_x;
         const int tw = min(8, prm.width - tx * 8), th = min(4, prm.height - ty * 4), npix = tw * th;     // ragged edge tiles
-        const int n_items = prm.max_depth >= 1 ? npix * (s1 - s0) : 0;
+        const int n_items = (have_unit && prm.max_depth >= 1) ? npix * (s1 - s0) : 0;
         acc[warp][lane] = 0.f; acc[warp][lane + 32] = 0.f; acc[warp][lane + 64] = 0.f;
+#if RTW_CARRY
+        int* const tl_scr = kCarry ? tl_scratch[warp] : reinterpret_cast<int*>(ring[warp][0]);
+#else
+        int* const tl_scr = reinterpret_cast<int*>(ring[warp][0]);
+#endif
         // every primitive a primary ray of this tile can touch (-1: too many, traverse instead)
-        const int list_n = prm.no_tile_cull ? -1
-                           : W ? build_tile_list_wide(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], reinterpret_cast<int*>(ring[warp][0]), lane)
-                               : build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], reinterpret_cast<int*>(ring[warp][0]), lane);
+        const int list_n = (prm.no_tile_cull || !have_unit) ? -1
+                           : W ? build_tile_list_wide(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], tl_scr, lane)
+                               : build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], tl_scr, lane);
         __syncwarp();
-        if (lane == 0) { if (list_n >= 0) atomicAdd(stats + 2, (unsigned long long)list_n); else atomicAdd(stats + 3, 1ull); }
-        int next = 0, pix = 0;
-        int ring_head = 0, ring_count = 0;                     // warp-uniform
-        bool alive = false;
+        if (lane == 0 && have_unit) { if (list_n >= 0) atomicAdd(stats + 2, (unsigned long long)list_n); else atomicAdd(stats + 3, 1ull); }
+        int next = 0;
         // Each iteration of this loop is EITHER a primary batch or a secondary step; both run the SAME copy of the
         // closest-hit and shading code (two inlined copies doubled the kernel to 145 KB and cost 40 % in i-cache misses).
         //  primary batch : taken when the ring cannot serve the lanes that need a path.  All 32 lanes queue their
@@ -121,6 +151,24 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
             const unsigned mask = __ballot_sync(0xffffffffu, need);
             const int n_need = __popc(mask);
             const bool primary = ring_count < n_need && next < n_items;      // warp-uniform
+#if RTW_CARRY
+            if (kCarry && ring_count < n_need && !primary && have_unit) {
+                // Nothing left to start in this unit and the ring cannot fill the idle lanes: hand what is still in flight
+                // over to the next unit (unless an older generation of orphans is still alive: then drain as usual).
+                const int live = (32 - n_need) + ring_count;
+                const int older = __shfl_sync(0xffffffffu, carry_s[warp][0], 0);      // (one lane's view: the decision is warp-uniform)
+                if (live > 0 && older == 0) {
+                    if (alive) pix |= 32;
+                    for (int k = lane; k < ring_count; k += 32) {
+                        float* rg = ring[warp][0] + ((ring_head + k) & 63);
+                        rg[704] = __int_as_float(__float_as_int(rg[704]) | 32);
+                    }
+                    if (lane == 0) { carry_s[warp][0] = live; carry_s[warp][1] = tx; carry_s[warp][2] = ty; }
+                    __syncwarp();
+                    break;
+                }
+            }
+#endif
             bool work = false;
             int wpix = 0;
             if (primary) {
@@ -133,7 +181,7 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
                     rg[192] = ps.ray.d.x; rg[256] = ps.ray.d.y; rg[320] = ps.ray.d.z; rg[384] = ps.ray.time;
                     rg[448] = ps.T.x; rg[512] = ps.T.y; rg[576] = ps.T.z;
                     rg[640] = __int_as_float(ps.last_prim);
-                    rg[704] = __int_as_float(pix | (ps.segment << 5) | ((int)ps.rng.sample << 11));
+                    rg[704] = __int_as_float(pix | (ps.segment << 6) | ((int)ps.rng.sample << 12));      // pixel(5) orphan(1) segment(6) sample(20)
                     alive = false;
                 }
                 ring_count += __popc(ma);
@@ -156,9 +204,14 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
                         ps.T = mk(rg[448], rg[512], rg[576]);
                         ps.last_prim = __float_as_int(rg[640]);
                         const int meta = __float_as_int(rg[704]);
-                        pix = meta & 31;
-                        ps.rng.start((uint32_t)((ty * 4 + (pix >> 3)) * prm.width + tx * 8 + (pix & 7)), (uint32_t)meta >> 11);
-                        ps.segment = (meta >> 5) & 63;
+                        pix = meta & 63;
+#if RTW_CARRY
+                        const int rtx = (kCarry && (pix & 32)) ? carry_s[warp][1] : tx, rty = (kCarry && (pix & 32)) ? carry_s[warp][2] : ty;     // an orphan belongs to the previous unit's tile
+#else
+                        const int rtx = tx, rty = ty;
+#endif
+                        ps.rng.start((uint32_t)((rty * 4 + ((pix >> 3) & 3)) * prm.width + rtx * 8 + (pix & 7)), (uint32_t)meta >> 12);
+                        ps.segment = (meta >> 6) & 63;
                         alive = true;
                     }
                 }
@@ -166,8 +219,12 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
                 ring_head = (ring_head + taken) & 63; ring_count -= taken;
                 if (!__any_sync(0xffffffffu, alive)) break;     // ring empty, nothing in flight, no items left
                 if (alive) {
-                    if (ps.segment >= prm.max_depth) alive = false;                          // main.rs:21-23
-                    else { ps.segment++; ps.rng.set_bounce((uint32_t)ps.segment); work = true; wpix = pix; }
+                    if (ps.segment >= prm.max_depth) {                                       // main.rs:21-23
+                        alive = false;
+#if RTW_CARRY
+                        if (kCarry && (pix & 32)) atomicSub(&carry_s[warp][0], 1);
+#endif
+                    } else { ps.segment++; ps.rng.set_bounce((uint32_t)ps.segment); work = true; wpix = pix; }
                 }
             }
 #ifdef RTW_INSTRUMENT
@@ -204,9 +261,20 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
             if (work) {
                 ++rays;
                 if (add.x != 0.f || add.y != 0.f || add.z != 0.f) {          // miss / emitter: T*background, T*emitted
-                    atomicAdd(&acc[warp][wpix * 3 + 0], add.x);
-                    atomicAdd(&acc[warp][wpix * 3 + 1], add.y);
-                    atomicAdd(&acc[warp][wpix * 3 + 2], add.z);
+#if RTW_CARRY
+                    if (kCarry && (wpix & 32)) {                             // orphan of the previous unit: its tile was flushed, add to the image itself
+                        const int ox = carry_s[warp][1] * 8 + (wpix & 7), oy = carry_s[warp][2] * 4 + ((wpix >> 3) & 3);
+                        float* dst = fb + ((size_t)(prm.height - 1 - oy) * prm.width + ox) * 3;
+                        if (add.x != 0.f) atomicAdd_system(dst, add.x);
+                        if (add.y != 0.f) atomicAdd_system(dst + 1, add.y);
+                        if (add.z != 0.f) atomicAdd_system(dst + 2, add.z);
+                    } else
+#endif
+                    {
+                        atomicAdd(&acc[warp][wpix * 3 + 0], add.x);
+                        atomicAdd(&acc[warp][wpix * 3 + 1], add.y);
+                        atomicAdd(&acc[warp][wpix * 3 + 2], add.z);
+                    }
                 }
             }
 #ifdef RTW_INSTRUMENT
@@ -233,15 +301,20 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
                     rg[192] = ps.ray.d.x; rg[256] = ps.ray.d.y; rg[320] = ps.ray.d.z; rg[384] = ps.ray.time;
                     rg[448] = ps.T.x; rg[512] = ps.T.y; rg[576] = ps.T.z;
                     rg[640] = __int_as_float(ps.last_prim);
-                    rg[704] = __int_as_float(wpix | (ps.segment << 5) | ((int)ps.rng.sample << 11));
+                    rg[704] = __int_as_float(wpix | (ps.segment << 6) | ((int)ps.rng.sample << 12));
                 }
                 ring_count += __popc(mc);
                 next += min(32, n_items - next);
                 __syncwarp();
-            } else if (work) alive = cont;
+            } else if (work) {
+                alive = cont;
+#if RTW_CARRY
+                if (kCarry && !cont && (pix & 32)) atomicSub(&carry_s[warp][0], 1);
+#endif
+            }
         }
         __syncwarp();
-        flush_tile(prm, fb, acc[warp], tx, ty, tw, lane);
+        if (have_unit) flush_tile(prm, fb, acc[warp], tx, ty, tw, lane);
         __syncwarp();
     }
     // ray statistics: one atomic per warp
@@ -601,7 +674,7 @@ DCamera to_dcamera(const rtw_camera& c) {
 
 int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     if (p.width < 2 || p.height < 2 || p.spp < 1 || p.max_depth < 0) return fail(RTW_ERR_INVALID_ARG, "bad render params");
-    // a queued ray packs pixel(5) | segment(6) | sample(21) into one word (the pool kernel: sample(17), checked at launch)
+    // a queued ray packs pixel(5) | orphan(1) | segment(6) | sample(20) into one word (the pool kernel: sample(17), checked at launch)
     if (p.spp > (1 << 20) || p.max_depth > 63) return fail(RTW_ERR_INVALID_ARG, "spp <= 1048576 and max_depth <= 63");
     if (!fin_all(p.background[0], p.background[1], p.background[2], p.t_min)) return fail(RTW_ERR_INVALID_ARG, "non-finite background / t_min");
     std::memset(&d, 0, sizeof(d));
@@ -625,7 +698,7 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
         static const char* bspp = getenv("RTW_B_SPP");          // tuning (tools/ab_env.sh): phase-B unit size, share in %, phase-A minimum
         static const char* bshare = getenv("RTW_B_SHARE");
         static const char* amin = getenv("RTW_A_MIN");
-        const int spp_b = (p.spp >= 160 && !one_phase) ? (int)((long long)p.spp * (bshare ? atoi(bshare) : 20) / 100) : 0;
+        int spp_b = (p.spp >= 160 && !one_phase) ? (int)((long long)p.spp * (bshare ? atoi(bshare) : 20) / 100) : 0;
         d.spp_a = p.spp - spp_b;
         long long want_units = (wu ? atoll(wu) : 24LL) * total_warps;
         if (const char* e = getenv("RTW_EMULATE_RANKS")) want_units *= std::max(1, atoi(e));
@@ -633,7 +706,12 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
         if (chunks < 1) chunks = 1;
         chunk = (int)((d.spp_a + chunks - 1) / chunks);
         const int a_min = amin ? std::max(1, atoi(amin)) : 32;
-        if (chunk < a_min) chunk = a_min;
+        if (chunk < a_min) {
+            chunk = a_min;
+            // phase A at its floor = the many-GPU regime (a frame is ~14 ms): with the carry-over short units are cheap, and 30 %
+            // of the samples in them ends the frame 0.2 ms earlier than 20 % (emulated 8 ranks: 13.24 vs 13.47 ms, r2_ad_carry_units.log)
+            if (spp_b > 0 && !bshare) { spp_b = (int)((long long)p.spp * 30 / 100); d.spp_a = p.spp - spp_b; }
+        }
         if (spp_b > 0) {
             // (8 when phase A already sits at its floor — the 8-GPU regime: the frame then ends ~0.3 ms earlier, measured with
             // RTW_EMULATE_RANKS=8, profiles/r2_f_units.log; a warp needs ~1 ms of wall time per 32-sample unit at full residency)
@@ -1309,7 +1387,7 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     TRY(ensure_fb(s->local, r0.device, dev_out ? 1 : p->width, dev_out ? 1 : p->height));
     float* fb = dev_out ? out : s->local.fb();
     CUDA_TRY(cudaSetDevice(r0.device));
-    dp.accumulate = (n_rep > 1 || dp.chunks + dp.chunks_b > 1 || kernel_mode(s, p->flags) == 5) ? 1 : 0;   // (wavefront: finished paths are ADDED)
+    dp.accumulate = (RTW_CARRY || n_rep > 1 || dp.chunks + dp.chunks_b > 1 || kernel_mode(s, p->flags) == 5) ? 1 : 0;   // (wavefront, orphans of a carried unit: finished paths are ADDED)
     CUDA_TRY(cudaMemsetAsync(s->local.counter(), 0, 256, r0.stream));
     if (dp.accumulate) CUDA_TRY(cudaMemsetAsync(fb, 0, fb_bytes, r0.stream));
     if (n_rep > 1) CUDA_TRY(cudaStreamSynchronize(r0.stream));   // peers must see the zeroed buffers
