@@ -1058,3 +1058,28 @@ def test_box_as_one_leaf_equals_six_rects(pkg, gpu, monkeypatch, name, width):
     # the render kernel traced what trace_paths traced (tile lists, ring, self-intersection rule with face indices)
     ref = ra.reshape(H, W, spp, 3).sum(2)[::-1]
     assert np.abs(ia - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("name", ["random_scene", "cornell_box", "two_perlin_spheres", "final_scene"])
+def test_tiny_work_units_carry_their_last_rays_over(pkg, gpu, name):
+    """Work units of ONE or TWO samples per tile: every unit ends with most of its paths still in flight, so the megakernel
+    constantly carries the last rays of a unit (lanes + ring) into the next one as orphans of the old tile (csrc/rtw_api.cu
+    render_kernel, RTW_CARRY; the variants with media code drain the old way).  Scheduling must not show in the result: the
+    same paths as with one unit per tile — equal ray counts, images equal up to f32 summation order — and the image is the
+    per-pixel sum of trace_paths' paths (the reference's accumulation, src/main.rs:519-520, :542-547)."""
+    sc, spec = pkg.scenes.build(gpu, name)
+    sc.commit(1, 0)
+    W, H, spp = 203, 117, 12                                 # ragged tiles on both axes
+    cam = spec.camera(gpu, W, H)
+    F = pkg.api.RTW_FLAG_KERNEL_MEGA
+    one, s1 = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=21, samples_per_unit=spp, flags=F))
+    for spu in (1, 2, 5):
+        img, st = sc.render(cam, pkg.make_params(W, H, spp, background=spec.background, seed=21, samples_per_unit=spu, flags=F))
+        assert st["rays"] == s1["rays"] and st["paths"] == W * H * spp, (name, spu)
+        assert np.isfinite(img).all()
+        assert np.abs(img - one).max() <= 2e-4 * max(1.0, np.abs(one).max()), (name, spu)
+    p = pkg.make_params(W, H, spp, background=spec.background, seed=21, flags=F)
+    ys, xs, ss = np.meshgrid(np.arange(H), np.arange(W), np.arange(spp), indexing="ij")
+    rgb, _ = sc.trace_paths(cam, p, xs.ravel(), ys.ravel(), ss.ravel())
+    ref = rgb.reshape(H, W, spp, 3).sum(2)[::-1]
+    assert np.abs(one - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
