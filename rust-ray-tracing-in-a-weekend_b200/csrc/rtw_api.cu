@@ -710,7 +710,10 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
             chunk = a_min;
             // phase A at its floor = the many-GPU regime (a frame is ~14 ms): with the carry-over short units are cheap, and 30 %
             // of the samples in them ends the frame 0.2 ms earlier than 20 % (emulated 8 ranks: 13.24 vs 13.47 ms, r2_ad_carry_units.log)
-            if (spp_b > 0 && !bshare) { spp_b = (int)((long long)p.spp * 30 / 100); d.spp_a = p.spp - spp_b; }
+            // (only when several GPUs share the frame: a SMALL frame on one GPU reaches the floor too, and there the extra short
+            // units cost — two_perlin_spheres 800x450x200 on one GPU 12.6 -> 13.8 ms)
+            const bool many = p.n_gpus > 1 || getenv("RTW_EMULATE_RANKS") != nullptr;
+            if (spp_b > 0 && !bshare && many) { spp_b = (int)((long long)p.spp * 30 / 100); d.spp_a = p.spp - spp_b; }
         }
         if (spp_b > 0) {
             // (8 when phase A already sits at its floor — the 8-GPU regime: the frame then ends ~0.3 ms earlier, measured with
@@ -1379,7 +1382,8 @@ int rtw_render(rtw_scene* s, const rtw_camera* cam, const rtw_render_params* p, 
     if (n_rep > (int)s->reps.size()) return fail(RTW_ERR_INVALID_ARG, "n_gpus exceeds the committed replicas");
     int total_warps = 0;
     for (int i = 0; i < n_rep; ++i) total_warps += s->reps[i].grid * RTW_WARPS;
-    DParams dp; TRY(make_params(*p, total_warps, dp));
+    rtw_render_params pu = *p; pu.n_gpus = n_rep;             // (the unit sizing wants to know how many GPUs share the frame)
+    DParams dp; TRY(make_params(pu, total_warps, dp));
     if (st) { std::memset(st, 0, sizeof(*st)); fill_scene_stats(s, st); }
     Replica& r0 = s->reps[0];
     const bool dev_out = (p->flags & RTW_FLAG_DEVICE_OUT) != 0;
