@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out; L=gpurun_out/af_check.log; : > $L
+for i in 1 2; do RTW_TAG=af timeout 600 python tools/exp_time2.py 2>&1 | tee -a $L; done
+timeout 300 python tools/profile_one.py random_scene 500 2>&1 | tail -2 | tee -a $L
+RTW_EMULATE_RANKS=8 timeout 300 python tools/profile_one.py random_scene 500 2>&1 | tail -3 | tee -a $L
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -3 | tee -a $L
