@@ -71,8 +71,9 @@ __global__ void wf_reserve_kernel(WfPool pool, unsigned long long* __restrict__ 
     pool.ctr[1] = 0ull; pool.ctr[2] = 0ull;          // per-iteration counters: active slots, trace cursor
 }
 
+// (spheres-only variant: 64 registers without spills = 4 CTAs per SM instead of 3: sweep 1 M / 4 M +0.7 % / +1.1 %, profiles/r2_ag_logic.log)
 template <int F>
-__global__ void __launch_bounds__(RTW_WF_BLOCK)
+__global__ void __launch_bounds__(RTW_WF_BLOCK, F == 0 ? 4 : 1)
 wf_logic_kernel(const __grid_constant__ DScene sc, const __grid_constant__ DCamera cam, const __grid_constant__ DParams prm, WfPool pool,
                 unsigned long long total_paths, float* __restrict__ fb) {
     __shared__ unsigned s_need[RTW_WF_BLOCK / 32];
