@@ -77,7 +77,10 @@ __device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; 
 #define RTW_COOP 1          // unit-ball samples drawn by the whole warp (coop_unit_sphere); 0 = every lane loops on its own
 #endif
 
-template <int F, int W>
+// S = 1: the variant for scenes of a handful of primitives (DParams::list_max): every ray scans ALL primitives instead of
+// walking the BVH — no traversal code in the kernel at all.  S = 0: everything else (no scan overhead: C1 pays 0.55 % for a
+// run-time switch, profiles/r2_ak_c1_scan_ab.log).
+template <int F, int W, int S>
 __global__ void __launch_bounds__(RTW_BLOCK, RTW_MIN_BLOCKS)
 render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsigned int* __restrict__ unit_counter, float* __restrict__ fb,
               unsigned long long* __restrict__ stats /* [0] rays, [1] units */) {
@@ -132,6 +135,8 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
         int* const tl_scr = reinterpret_cast<int*>(ring[warp][0]);
 #endif
         // every primitive a primary ray of this tile can touch (-1: too many, traverse instead)
+        // (the small-scene kernels keep their tile lists: without them two_spheres -4.5 % but simple_light +3.8 %, two_perlin_spheres
+        // +5.7 %, cornell_box +0.8 %: profiles/r2_al_small_notile.log)
         const int list_n = (prm.no_tile_cull || !have_unit) ? -1
                            : W ? build_tile_list_wide(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], tl_scr, lane)
                                : build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], tl_scr, lane);
@@ -234,12 +239,20 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
             TRay tr; float t_best = CUDART_INF_F; int prim_best = -1;
             if (work) {
                 tr = make_tray(ps.ray);
-                if (primary && list_n >= 0) {
+                // Candidate scan instead of a BVH walk: primary rays over their tile's list; in the small-scene kernels (S = 1) EVERY
+                // ray over all primitives (cornell_box: 8 leaves — the same trip count in every lane against ~6 divergent node visits
+                // + 2-3 leaf tests).  One copy of the loop serves both.  Measured (profiles/r2_ah_list_scan.log): cornell_box 145.7 ->
+                // 121.2 ms, two_spheres / earth -7 %, the other small scenes -3 %.
+                constexpr bool kScan = S != 0;
+                const bool use_tile = primary && list_n >= 0;
+                if (use_tile || kScan) {
+                    const int n_scan = (!kScan || use_tile) ? list_n : sc.n_bvh_prims;
+                    const int skip = (!kScan || primary) ? -1 : ps.last_prim;
 #pragma unroll 1
-                    for (int i = 0; i < list_n; ++i) {
-                        const int pi = tlist[warp][i];
+                    for (int i = 0; i < n_scan; ++i) {
+                        const int pi = (!kScan || use_tile) ? tlist[warp][i] : i;
                         int hp;
-                        const float t = prim_root<F>(sc, pi, tr, prm.t_min, t_best, -1, hp);
+                        const float t = prim_root<F>(sc, pi, tr, prm.t_min, t_best, skip, hp);
                         if (t == t) { t_best = t; prim_best = hp; }
                     }
                 } else {
@@ -731,6 +744,8 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     d.n_units = (uint32_t)n_units;
     d.accumulate = 1;
     d.no_tile_cull = (p.flags & RTW_FLAG_NO_TILE_CULL) ? 1 : 0;
+    d.list_max = 8;                                                  // measured: profiles/r2_ah_list_scan.log
+    if (const char* e = getenv("RTW_LIST_MAX")) d.list_max = std::max(0, atoi(e));
     d.unit_stride = 1;
     if (const char* e = getenv("RTW_EMULATE_RANKS")) d.unit_stride = (uint32_t)std::max(1, atoi(e));   // tuning aid: image incomplete
     return 0;
@@ -992,9 +1007,11 @@ int launch_all(rtw_scene* s, int n_rep, const rtw_camera* cam, const DParams& dp
         default: {
             // smallest kernel variant that covers the scene's features (code size = instruction-cache pressure)
             const int f = s->flat.features;
+            const bool small = !s->flat.wide && s->flat.n_bvh_prims <= dp.list_max;       // a handful of primitives: scan, no BVH walk
 #define RTW_TRY_VARIANT(V) if ((f & ~(V)) == 0) { \
-                if (s->flat.wide) render_kernel<V, 1><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); \
-                else render_kernel<V, 0><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); \
+                if (s->flat.wide) render_kernel<V, 1, 0><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); \
+                else if (small) render_kernel<V, 0, 1><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); \
+                else render_kernel<V, 0, 0><<<r.grid, RTW_BLOCK, 0, r.stream>>>(r.ds, dc, dp, counter, fb, r.stats); \
                 break; }
             RTW_TRY_VARIANT(0)                                         // spheres, solid / checker         (C1, two_spheres)
             RTW_TRY_VARIANT(FEAT_NOISE)                                // + Perlin                         (two_perlin_spheres)
@@ -1307,7 +1324,7 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
             CUDA_TRY(cudaMalloc(&r.stats, 32));
             int sms = 0, per_sm = 0;
             CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r.device));
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FEAT_ALL, 0>, RTW_BLOCK, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<FEAT_ALL, 0, 0>, RTW_BLOCK, 0));
             if (per_sm < 1) per_sm = 1;
             r.grid = sms * per_sm; r.sms = sms;
             for (int k = 0; k < 8; ++k) r.pool_grid[k] = 0;

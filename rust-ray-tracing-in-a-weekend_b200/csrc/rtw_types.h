@@ -139,6 +139,7 @@ struct DParams {
     int32_t first_sample;              // sample index of this launch's sample 0 (progressive passes / resume)
     uint32_t philox_rk[20];            // Philox4x32-10 key schedule of `seed` (round r: key + r * Weyl constants)
     uint32_t unit_stride;              // 1; RTW_EMULATE_RANKS=k: this GPU takes every k-th unit only (tuning the k-GPU unit sizes on one GPU)
+    int32_t list_max;                  // scenes of at most this many BVH primitives: secondary rays scan ALL primitives (no BVH walk)
 };
 
 #endif
