@@ -744,7 +744,7 @@ int make_params(const rtw_render_params& p, int total_warps, DParams& d) {
     d.n_units = (uint32_t)n_units;
     d.accumulate = 1;
     d.no_tile_cull = (p.flags & RTW_FLAG_NO_TILE_CULL) ? 1 : 0;
-    d.list_max = 8;                                                  // measured: profiles/r2_ah_list_scan.log
+    d.list_max = 8;      // measured: cornell_box (8 leaves, closed room) -17 % (r2_ah_list_scan.log); sparse spheres break even at 6-8, lose 8 % at 12 (r2_am_listmax_crossover.log)
     if (const char* e = getenv("RTW_LIST_MAX")) d.list_max = std::max(0, atoi(e));
     d.unit_stride = 1;
     if (const char* e = getenv("RTW_EMULATE_RANKS")) d.unit_stride = (uint32_t)std::max(1, atoi(e));   // tuning aid: image incomplete
