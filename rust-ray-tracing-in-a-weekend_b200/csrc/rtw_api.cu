@@ -931,8 +931,11 @@ int wf_render_replica(rtw_scene* s, Replica& r, const DCamera& dc, const DParams
     const size_t n_floats = (size_t)dp.width * dp.height * 3;
     {
         cudaPointerAttributes at{};
-        const bool remote = cudaPointerGetAttributes(&at, fb) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != r.device;
+        bool remote = cudaPointerGetAttributes(&at, fb) == cudaSuccess && at.type == cudaMemoryTypeDevice && at.device != r.device;
         cudaGetLastError();
+        // (a framebuffer opened through CUDA IPC reports the IMPORTING device: one process per GPU is told apart by the mapping itself)
+        const uint8_t* fbb = reinterpret_cast<const uint8_t*>(fb);
+        if (s->shared.ipc_mapped && s->shared.base && fbb >= s->shared.base && fbb < s->shared.base + s->shared.bytes) remote = true;
         if (remote) {
             if (r.wf_fb_floats < n_floats) {
                 if (r.wf_fb) { CUDA_TRY(cudaFree(r.wf_fb)); r.wf_fb = nullptr; }
@@ -948,9 +951,15 @@ int wf_render_replica(rtw_scene* s, Replica& r, const DCamera& dc, const DParams
     if (s->flat.wide) rc = plain ? wf_run<0, 1>(s, r, dc, dp, path_counter, total, target) : wf_run<FEAT_ALL, 1>(s, r, dc, dp, path_counter, total, target);
     else rc = plain ? wf_run<0, 0>(s, r, dc, dp, path_counter, total, target) : wf_run<FEAT_ALL, 0>(s, r, dc, dp, path_counter, total, target);
     if (rc < 0) { if (target != fb) cudaMemsetAsync(target, 0, n_floats * sizeof(float), r.stream); return rc; }     // (the local framebuffer is always left zeroed)
-    if (target != fb) { wf_merge_kernel<<<r.sms * 8, 256, 0, r.stream>>>(target, fb, n_floats); CUDA_TRY(cudaGetLastError()); }
+    const double t_merge0 = now_ms();
+    if (target != fb) {
+        if (getenv("RTW_TIMING")) CUDA_TRY(cudaStreamSynchronize(r.stream));
+        wf_merge_kernel<<<r.sms * 8, 256, 0, r.stream>>>(target, fb, n_floats);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaEventRecord(r.ev1, r.stream));
     CUDA_TRY(cudaStreamSynchronize(r.stream));
+    if (target != fb && getenv("RTW_TIMING")) fprintf(stderr, "[wavefront] merge of the local framebuffer: %.2f ms\n", now_ms() - t_merge0);
     float e = 0; CUDA_TRY(cudaEventElapsedTime(&e, r.ev0, r.ev1));
     ms = e; rays = 0; paths = 0;
     for (int k = 0; k < r.wf_pools; ++k) {
