@@ -831,7 +831,20 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
     // A boundary made of ONE sphere (final_scene's two media): its second crossing comes out of the same discriminant
     // — the first probe returns the near root, the second probe can only return the far one — so one test serves both.
     const bool one_sphere = md.y == 1 && __ldg(reinterpret_cast<const int*>(sc.prims + md.x) + 12) <= PRIM_MOVING_SPHERE;
-    float t1 = 0.f, t2 = 0.f, lo = -inf, far_root = CUDART_NAN_F;
+    float t1 = 0.f, t2 = 0.f, lo = -inf;
+    if (one_sphere) {
+        // straight-line path (final_scene: both media, every segment of every path): one sphere test, no scan loops, no root cache
+        const DPrim* pp = sc.prims + md.x;
+        const int4 meta = __ldg(reinterpret_cast<const int4*>(pp) + 3);
+        float far_root = CUDART_NAN_F;
+        t1 = sphere_root(pp, meta.x, __int_as_float(meta.w), r, -inf, inf, false, &far_root);       // the near crossing, over (-inf, inf)
+        if (!(t1 == t1)) return false;
+        // in f32 the +0.0001 vanishes once |t1| > 2048 (r = 5000 fog sphere): keep the probe strictly beyond t1
+        lo = t1 + 0.0001f;
+        if (!(lo > t1)) lo = nextafterf(t1, inf);
+        if (!(far_root >= lo)) return false;
+        t2 = far_root;
+    } else {
     XfCache xc; xc.xf = -1; xc.o = r.o; xc.d = r.d;        // 6 faces x 2 probes of a rotated Box: one transform instead of 12
     // Small boundaries (a Box: 6 faces) are intersected ONCE: the first scan keeps every face's root, the second scan
     // (same faces, range [t1 + 0.0001, inf)) re-reads them — the same values hit_hittables would compute again.
@@ -851,18 +864,16 @@ RTW_DEV bool medium_hit(const DScene& sc, int mi, const TRay& r, float t_min, fl
                 int hp;                                              // (a Box boundary is ONE record: its slab test yields both crossings)
                 t = prim_root(sc, md.x + i, r, keep ? -inf : lo, keep ? inf : hi, -1, hp, &fr, &xc);
                 if (keep) { ts[i] = t; tfar[i] = fr; }
-                if (one_sphere) far_root = fr;
             }
             if (t >= lo && t <= hi) { hi = t; found = t; }          // closest-so-far (hit_hittables :43-55); NaN fails
         }
         if (!(found == found)) return false;
         if (pass == 0) {
             t1 = found;
-            // in f32 the +0.0001 vanishes once |t1| > 2048 (r = 5000 fog sphere): keep the probe strictly beyond t1
             lo = t1 + 0.0001f;
             if (!(lo > t1)) lo = nextafterf(t1, inf);
-            if (one_sphere) { if (!(far_root >= lo)) return false; t2 = far_root; break; }
         } else t2 = found;
+    }
     }
     if (t1 < t_min) t1 = t_min;
     if (t2 > t_max) t2 = t_max;
