@@ -21,8 +21,13 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <cfloat>
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bvh_build.hpp"
@@ -238,9 +243,94 @@ __global__ void single_leaf_root_kernel(const float* __restrict__ boxes, DWNode*
     nodes[0] = w; leaf_order[0] = 0;
 }
 
-struct Buf {            // scratch allocation freed on scope exit
+// ---- staged upload (SURVEY 8f-2 "commit overlap") ------------------------------------------------------------------
+// The spheres of a big scene live in pageable host memory (the caller's constructors filled a std::vector).  One
+// cudaMemcpyAsync from pageable memory is staged by the driver through one pinned buffer on the calling thread: 16 M
+// spheres = 640 MB took 60-190 ms, most of the commit.  Here a few host threads each copy their chunks into their own
+// pinned buffers (allocated once per process) and hand them to their own stream, so the host-side copy of one chunk
+// overlaps the DMA of the others and several cores share the host-side copy.  Returns with the data on the device.
+constexpr int kStageThreads = 4, kStageSlots = 2;
+constexpr size_t kStageChunk = (size_t)8 << 20;
+struct StagePool { std::mutex mu; bool tried = false, ok = false; void* buf[kStageThreads][kStageSlots] = {}; };
+StagePool g_stage;
+
+cudaError_t staged_upload(cudaStream_t st, void* dst, const void* src, size_t bytes) {
+    const char* sw = getenv("RTW_STAGED_UPLOAD");
+    std::unique_lock<std::mutex> lk(g_stage.mu, std::try_to_lock);      // a second concurrent commit takes the plain copy
+    bool staged = bytes >= 4 * kStageChunk && lk.owns_lock() && !(sw && sw[0] == '0');
+    if (staged && !g_stage.tried) {
+        g_stage.tried = true; g_stage.ok = true;
+        for (int t = 0; t < kStageThreads && g_stage.ok; ++t)
+            for (int k = 0; k < kStageSlots && g_stage.ok; ++k)
+                if (cudaHostAlloc(&g_stage.buf[t][k], kStageChunk, cudaHostAllocPortable) != cudaSuccess) { g_stage.ok = false; cudaGetLastError(); }
+    }
+    if (!staged || !g_stage.ok) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+    int dev = 0;
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) return e0;
+    const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+    cudaError_t errs[kStageThreads];
+    std::thread th[kStageThreads];
+    for (int t = 0; t < kStageThreads; ++t) th[t] = std::thread([&, t] {
+        cudaError_t e = cudaSetDevice(dev);
+        cudaStream_t s = nullptr; cudaEvent_t ev[kStageSlots] = {};
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        for (int k = 0; k < kStageSlots && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+        size_t use = 0;
+        for (size_t c = t; c < n_chunks && e == cudaSuccess; c += kStageThreads, ++use) {
+            const int k = (int)(use % kStageSlots);
+            if (use >= (size_t)kStageSlots) e = cudaEventSynchronize(ev[k]);      // the buffer's previous chunk has left
+            if (e != cudaSuccess) break;
+            const size_t off = c * kStageChunk, len = bytes - off < kStageChunk ? bytes - off : kStageChunk;
+            memcpy(g_stage.buf[t][k], (const char*)src + off, len);
+            e = cudaMemcpyAsync((char*)dst + off, g_stage.buf[t][k], len, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[k], s);
+        }
+        if (s) { const cudaError_t e2 = cudaStreamSynchronize(s); if (e == cudaSuccess) e = e2; }
+        for (int k = 0; k < kStageSlots; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
+        if (s) cudaStreamDestroy(s);
+        errs[t] = e;
+    });
+    for (int t = 0; t < kStageThreads; ++t) th[t].join();
+    (void)st;                                                           // dst was cudaMalloc'ed by the caller; kernels launched from here on see the data
+    for (int t = 0; t < kStageThreads; ++t) if (errs[t] != cudaSuccess) return errs[t];
+    return cudaSuccess;
+}
+
+// ---- scratch pool ------------------------------------------------------------------------------------------------
+// The builder's scratch (16 M spheres: 26 buffers, 4.2 GB) comes from a stream-ordered memory pool of its own, kept across
+// commits and trimmed when a scene is freed (trim_scratch): measured on the 16 M-sphere commit, cudaFree of that scratch
+// took 100 ms and cudaMalloc 10-60 ms of a 200-ms commit (profiles/r2_au2_commit_phases.log).  RTW_SCRATCH_POOL=0: plain
+// cudaMalloc / cudaFree (also the fallback when the pool cannot be created).
+constexpr int kMaxDev = 32;
+struct ScratchPools { std::mutex mu; cudaMemPool_t pool[kMaxDev] = {}; bool tried[kMaxDev] = {}; };
+ScratchPools g_pools;
+
+cudaMemPool_t scratch_pool(int dev) {
+    if (dev < 0 || dev >= kMaxDev) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pools.mu);
+    if (!g_pools.tried[dev]) {
+        g_pools.tried[dev] = true;
+        const char* sw = getenv("RTW_SCRATCH_POOL");
+        if (!(sw && sw[0] == '0')) {
+            cudaMemPoolProps pr; memset(&pr, 0, sizeof(pr));
+            pr.allocType = cudaMemAllocationTypePinned; pr.handleTypes = cudaMemHandleTypeNone;
+            pr.location.type = cudaMemLocationTypeDevice; pr.location.id = dev;
+            cudaMemPool_t mp = nullptr;
+            if (cudaMemPoolCreate(&mp, &pr) == cudaSuccess) {
+                unsigned long long keep = ~0ull;            // nothing goes back to the driver before trim_scratch
+                cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep);
+                g_pools.pool[dev] = mp;
+            } else cudaGetLastError();
+        }
+    }
+    return g_pools.pool[dev];
+}
+
+struct Buf {            // scratch allocation freed on scope exit (stream-ordered when it came from the pool)
     void* p = nullptr;
-    ~Buf() { if (p) cudaFree(p); }
+    cudaStream_t st = nullptr; bool pooled = false;
+    ~Buf() { if (p) { if (pooled) cudaFreeAsync(p, st); else cudaFree(p); } }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
@@ -253,17 +343,38 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
     const int n_inner = n - 1;
     const bool timing = getenv("RTW_TIMING") != nullptr;
     cudaEvent_t ev[8]; int n_ev = 0;
+    const auto host_t0 = std::chrono::steady_clock::now();
+    double malloc_ms = 0;                                       // host time inside cudaMalloc (RTW_TIMING)
+    auto dmalloc = [&](auto** p, size_t bytes) {
+        if (!timing) return cudaMalloc(p, bytes);
+        const auto a = std::chrono::steady_clock::now();
+        const cudaError_t e = cudaMalloc(p, bytes);
+        malloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+        return e;
+    };
+    int dev = 0;
+    BCUDA(cudaGetDevice(&dev));
+    cudaMemPool_t mpool = scratch_pool(dev);
+    auto salloc = [&](Buf& b, size_t bytes) {                   // scratch: from the pool, in stream order on `st`
+        if (!mpool) return dmalloc(&b.p, bytes);
+        const auto a = std::chrono::steady_clock::now();
+        const cudaError_t e = cudaMallocFromPoolAsync(&b.p, bytes ? bytes : 16, mpool, st);
+        if (timing) malloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count();
+        if (e == cudaSuccess) { b.st = st; b.pooled = true; }
+        return e;
+    };
     auto mark = [&]() { if (timing && n_ev < 8) { cudaEventCreate(&ev[n_ev]); cudaEventRecord(ev[n_ev], st); ++n_ev; } };
     mark();
     // ---- inputs
     Buf d_bulk, d_hprims, d_hboxes;
     if (in.n_bulk) {
-        BCUDA(cudaMalloc(&d_bulk.p, (size_t)in.n_bulk * sizeof(BulkSphereD)));
-        BCUDA(cudaMemcpyAsync(d_bulk.p, in.bulk, (size_t)in.n_bulk * sizeof(BulkSphereD), cudaMemcpyHostToDevice, st));
+        BCUDA(salloc(d_bulk, (size_t)in.n_bulk * sizeof(BulkSphereD)));
+        if (d_bulk.pooled) BCUDA(cudaStreamSynchronize(st));     // the upload's own streams may touch the buffer from here on
+        BCUDA(staged_upload(st, d_bulk.p, in.bulk, (size_t)in.n_bulk * sizeof(BulkSphereD)));
     }
     if (in.n_host) {
-        BCUDA(cudaMalloc(&d_hprims.p, (size_t)in.n_host * sizeof(DPrim)));
-        BCUDA(cudaMalloc(&d_hboxes.p, (size_t)in.n_host * 24));
+        BCUDA(salloc(d_hprims, (size_t)in.n_host * sizeof(DPrim)));
+        BCUDA(salloc(d_hboxes, (size_t)in.n_host * 24));
         BCUDA(cudaMemcpyAsync(d_hprims.p, in.host_prims, (size_t)in.n_host * sizeof(DPrim), cudaMemcpyHostToDevice, st));
         BCUDA(cudaMemcpyAsync(d_hboxes.p, in.host_boxes, (size_t)in.n_host * 24, cudaMemcpyHostToDevice, st));
     }
@@ -271,8 +382,8 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
     mark();
     // ---- boxes, Morton codes, sort
     Buf d_boxes, d_bounds, d_keys, d_vals, d_keys2, d_vals2, d_tmp;
-    BCUDA(cudaMalloc(&d_boxes.p, (size_t)n * 24));
-    BCUDA(cudaMalloc(&d_bounds.p, 64));
+    BCUDA(salloc(d_boxes, (size_t)n * 24));
+    BCUDA(salloc(d_bounds, 64));
     {
         unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
         BCUDA(cudaMemcpyAsync(d_bounds.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
@@ -281,14 +392,14 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
     prim_boxes_kernel<<<G, T, 0, st>>>(n, in.n_host, d_hboxes.as<float>(), d_bulk.as<BulkSphereD>(), d_boxes.as<float>(), d_bounds.as<unsigned>());
     BCUDA(cudaGetLastError());
     Buf d_wnodes_scratch, d_order, d_q0, d_q1, d_counters, d_left, d_right, d_parent, d_box2, d_flags, d_count;
-    BCUDA(cudaMalloc(&d_order.p, (size_t)n * 4));
-    BCUDA(cudaMalloc(&d_counters.p, 64));
+    BCUDA(salloc(d_order, (size_t)n * 4));
+    BCUDA(salloc(d_counters, 64));
     DWNode* wn = nullptr;
     int n_wide = 0, depth = 0;
     DNode* bn = nullptr; int n_bin = 0;
     Buf d_bnodes;
     if (n == 1 && in.width == 2) {          // one primitive: a root whose two slots point at it (like the host flattener)
-        BCUDA(cudaMalloc(&d_bnodes.p, sizeof(DNode)));
+        BCUDA(salloc(d_bnodes, sizeof(DNode)));
         float hb[6];
         BCUDA(cudaMemcpyAsync(hb, d_boxes.p, 24, cudaMemcpyDeviceToHost, st));
         BCUDA(cudaStreamSynchronize(st));
@@ -298,45 +409,45 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
         BCUDA(cudaMemcpyAsync(d_bnodes.p, &d, sizeof(d), cudaMemcpyHostToDevice, st));
         BCUDA(cudaStreamSynchronize(st));
         bn = d_bnodes.as<DNode>(); n_bin = 1; depth = 1;
-        BCUDA(cudaMalloc(&d_vals.p, 4));
+        BCUDA(salloc(d_vals, 4));
         BCUDA(cudaMemsetAsync(d_vals.p, 0, 4, st));
         BCUDA(cudaMemsetAsync(d_order.p, 0, 4, st));
     } else if (n == 1) {
-        BCUDA(cudaMalloc(&d_wnodes_scratch.p, sizeof(DWNode)));
+        BCUDA(salloc(d_wnodes_scratch, sizeof(DWNode)));
         wn = d_wnodes_scratch.as<DWNode>();
         single_leaf_root_kernel<<<1, 1, 0, st>>>(d_boxes.as<float>(), wn, d_order.as<int>());
         BCUDA(cudaGetLastError());
-        BCUDA(cudaMalloc(&d_vals.p, 4));
+        BCUDA(salloc(d_vals, 4));
         BCUDA(cudaMemsetAsync(d_vals.p, 0, 4, st));
         n_wide = 1; depth = 1;
     } else {
-        BCUDA(cudaMalloc(&d_keys.p, (size_t)n * 8)); BCUDA(cudaMalloc(&d_vals.p, (size_t)n * 4));
-        BCUDA(cudaMalloc(&d_keys2.p, (size_t)n * 8)); BCUDA(cudaMalloc(&d_vals2.p, (size_t)n * 4));
+        BCUDA(salloc(d_keys, (size_t)n * 8)); BCUDA(salloc(d_vals, (size_t)n * 4));
+        BCUDA(salloc(d_keys2, (size_t)n * 8)); BCUDA(salloc(d_vals2, (size_t)n * 4));
         morton_kernel<<<G, T, 0, st>>>(n, d_boxes.as<float>(), d_bounds.as<unsigned>(), d_keys.as<unsigned long long>(), d_vals.as<unsigned>());
         BCUDA(cudaGetLastError());
         cub::DoubleBuffer<unsigned long long> kb(d_keys.as<unsigned long long>(), d_keys2.as<unsigned long long>());
         cub::DoubleBuffer<unsigned> vb(d_vals.as<unsigned>(), d_vals2.as<unsigned>());
         size_t tmp_bytes = 0;
         BCUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, kb, vb, n, 0, 63, st));
-        BCUDA(cudaMalloc(&d_tmp.p, tmp_bytes ? tmp_bytes : 16));
+        BCUDA(salloc(d_tmp, tmp_bytes ? tmp_bytes : 16));
         BCUDA(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, kb, vb, n, 0, 63, st));
         const unsigned long long* keys = kb.Current();
         const unsigned* sorted_idx = vb.Current();
         mark();
         // ---- binary radix tree + refit
-        BCUDA(cudaMalloc(&d_left.p, (size_t)n_inner * 4)); BCUDA(cudaMalloc(&d_right.p, (size_t)n_inner * 4));
-        BCUDA(cudaMalloc(&d_parent.p, (size_t)(n_inner + n) * 4));
-        BCUDA(cudaMalloc(&d_box2.p, (size_t)(n_inner + n) * 24));
-        BCUDA(cudaMalloc(&d_flags.p, (size_t)n_inner * 4));
+        BCUDA(salloc(d_left, (size_t)n_inner * 4)); BCUDA(salloc(d_right, (size_t)n_inner * 4));
+        BCUDA(salloc(d_parent, (size_t)(n_inner + n) * 4));
+        BCUDA(salloc(d_box2, (size_t)(n_inner + n) * 24));
+        BCUDA(salloc(d_flags, (size_t)n_inner * 4));
         BCUDA(cudaMemsetAsync(d_flags.p, 0, (size_t)n_inner * 4, st));
-        BCUDA(cudaMalloc(&d_count.p, (size_t)n_inner * 4));
+        BCUDA(salloc(d_count, (size_t)n_inner * 4));
         karras_kernel<<<(n_inner + T - 1) / T, T, 0, st>>>(n, keys, d_left.as<int>(), d_right.as<int>(), d_parent.as<int>());
         BCUDA(cudaGetLastError());
         refit_kernel<<<G, T, 0, st>>>(n, sorted_idx, d_boxes.as<float>(), d_left.as<int>(), d_right.as<int>(), d_parent.as<int>(), d_box2.as<float>(), d_flags.as<int>(), d_count.as<int>());
         BCUDA(cudaGetLastError());
         mark();
         if (in.width == 2) {
-            BCUDA(cudaMalloc(&d_bnodes.p, (size_t)n_inner * sizeof(DNode)));
+            BCUDA(salloc(d_bnodes, (size_t)n_inner * sizeof(DNode)));
             bn = d_bnodes.as<DNode>(); n_bin = n_inner;
             emit_binary_kernel<<<(n_inner + T - 1) / T, T, 0, st>>>(n_inner, d_left.as<int>(), d_right.as<int>(), d_box2.as<float>(), bn);
             BCUDA(cudaGetLastError());
@@ -351,9 +462,9 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
             if (sorted_idx != d_vals.as<unsigned>()) std::swap(d_vals.p, d_vals2.p);
         } else {
         // ---- collapse, level by level (every wide node consumes at least one binary inner node: n_inner bounds everything)
-        BCUDA(cudaMalloc(&d_wnodes_scratch.p, (size_t)n_inner * sizeof(DWNode)));
-        BCUDA(cudaMalloc(&d_q0.p, (size_t)n_inner * sizeof(rtww::WideItem)));
-        BCUDA(cudaMalloc(&d_q1.p, (size_t)n_inner * sizeof(rtww::WideItem)));
+        BCUDA(salloc(d_wnodes_scratch, (size_t)n_inner * sizeof(DWNode)));
+        BCUDA(salloc(d_q0, (size_t)n_inner * sizeof(rtww::WideItem)));
+        BCUDA(salloc(d_q1, (size_t)n_inner * sizeof(rtww::WideItem)));
         wn = d_wnodes_scratch.as<DWNode>();
         {
             int init[4] = {1, 0, 0, 0};
@@ -385,13 +496,13 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
     if (in.width == 2 ? depth > 60 : depth > RTW_WIDE_STACK) { err = "device-built BVH deeper than the traversal stack (degenerate primitive distribution)"; return -2; }
     // ---- outputs: compact node array + primitive records in leaf order (+ room for the medium boundary records)
     if (in.width == 2) {
-        BCUDA(cudaMalloc(&out.nodes, (size_t)n_bin * sizeof(DNode)));
+        BCUDA(dmalloc(&out.nodes, (size_t)n_bin * sizeof(DNode)));
         BCUDA(cudaMemcpyAsync(out.nodes, bn, (size_t)n_bin * sizeof(DNode), cudaMemcpyDeviceToDevice, st));
     } else {
-        BCUDA(cudaMalloc(&out.wnodes, (size_t)n_wide * sizeof(DWNode)));
+        BCUDA(dmalloc(&out.wnodes, (size_t)n_wide * sizeof(DWNode)));
         BCUDA(cudaMemcpyAsync(out.wnodes, wn, (size_t)n_wide * sizeof(DWNode), cudaMemcpyDeviceToDevice, st));
     }
-    BCUDA(cudaMalloc(&out.prims, (size_t)(n + in.n_boundary) * sizeof(DPrim)));
+    BCUDA(dmalloc(&out.prims, (size_t)(n + in.n_boundary) * sizeof(DPrim)));
     emit_prims_kernel<<<G, T, 0, st>>>(n, in.n_host, d_order.as<int>(), d_vals.as<unsigned>(), d_hprims.as<DPrim>(), d_bulk.as<BulkSphereD>(), out.prims);
     BCUDA(cudaGetLastError());
     if (in.n_boundary)
@@ -403,10 +514,17 @@ int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std
     if (timing && n_ev >= 2) {
         const char* names[] = {"upload", "boxes+morton+sort", "radix tree+refit", "collapse", "emit"};
         for (int i = 1; i < n_ev; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, "[device build] %s %.2f ms\n", names[i - 1], ms); }
-        fprintf(stderr, "[device build] %d prims -> %d wide nodes, depth %d\n", n, n_wide, depth);
+        fprintf(stderr, "[device build] %d prims -> %d wide nodes, depth %d; host: %.2f ms in all, %.2f ms of it inside cudaMalloc (scratch is freed after this line)\n", n, n_wide, depth,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(), malloc_ms);
     }
     for (int i = 0; i < n_ev; ++i) cudaEventDestroy(ev[i]);
     return 0;
+}
+
+void trim_scratch(int dev) {
+    if (dev < 0 || dev >= kMaxDev) return;
+    std::lock_guard<std::mutex> lk(g_pools.mu);
+    if (g_pools.pool[dev]) cudaMemPoolTrimTo(g_pools.pool[dev], 0);
 }
 
 void free_output(BuildOutput& o) {

@@ -37,6 +37,8 @@ struct BuildOutput {                       // device allocations owned by the ca
 // Builds on the current device, on stream `st`; returns 0 or a negative rtw_status (-2 nesting / depth, -3 CUDA, -4 OOM).
 int build_on_device(cudaStream_t st, const BuildInput& in, BuildOutput& out, std::string& err);
 void free_output(BuildOutput& out);
+// The builder's scratch pool of device `dev` gives its unused memory back to the driver (called when a scene is freed).
+void trim_scratch(int dev);
 
 }  // namespace rtwb
 #endif

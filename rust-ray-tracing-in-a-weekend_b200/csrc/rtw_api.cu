@@ -595,6 +595,7 @@ void free_replicas(rtw_scene* s) {
     for (Replica& r : s->reps) {
         cudaSetDevice(r.device);
         if (r.blob) cudaFree(r.blob);
+        if (r.built.prims) rtwb::trim_scratch(r.device);        // (the device builder's scratch pool, bvh_build.cu)
         rtwb::free_output(r.built);
         if (r.wf_mem) cudaFree(r.wf_mem);
         if (r.wf_fb) cudaFree(r.wf_fb);
@@ -1311,6 +1312,7 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     }
     int rc = rtw::flatten(s->g, s->g.world, s->flat, err, fo);
     if (rc) return fail(rc, err);
+    const double t_flat = now_ms();
     if (s->flat.emit_only && s->flat.n_bvh_prims == 0) {         // nothing to build: the plain path handles the empty world
         fo.emit_only = false;
         rc = rtw::flatten(s->g, s->g.world, s->flat, err, fo);
@@ -1397,6 +1399,7 @@ static int commit_impl(rtw_scene* s, int32_t n_gpus, int32_t first_device) {
     for (Replica& r : s->reps) { CUDA_TRY(cudaSetDevice(r.device)); CUDA_TRY(cudaStreamSynchronize(r.stream)); }
     s->committed = true;
     s->ms_commit = now_ms() - t0;
+    if (getenv("RTW_TIMING")) fprintf(stderr, "[commit] flatten %.2f ms, device build (rank-0 replica, with its scratch frees) %.2f ms, all %.2f ms\n", t_flat - t0, s->flat.emit_only ? s->ms_build_dev : 0.0, s->ms_commit);
     return RTW_OK;
 }
 

@@ -648,7 +648,16 @@ int flatten(const SceneGraph& g, const std::vector<int>& roots, FlatScene& out, 
         pack_materials(g, out);
         for (const DPrim& p : fl.bvh_prims) if (p.mat < 0 || p.mat >= (int)out.mats.size()) { err = "material handle out of range"; return RTW_ERR_INVALID_ARG; }
         for (const DMedium& m : out.media) if (m.mat < 0 || m.mat >= (int)out.mats.size()) { err = "phase material handle out of range"; return RTW_ERR_INVALID_ARG; }
-        if (with_bulk) for (const BulkSphere& b : g.bulk) if (b.mat < 1 || b.mat > (int)out.mats.size()) { err = "material handle out of range"; return RTW_ERR_INVALID_ARG; }
+        if (with_bulk) {                                   // (16 M spheres: 640 MB to read — 58 ms on one thread, most of this flatten)
+            std::atomic<int> bad{0};
+            const int n_mats = (int)out.mats.size();
+            parallel_chunks(g.bulk.size(), 1 << 16, [&](int, size_t i0, size_t i1) {
+                int b = 0;
+                for (size_t i = i0; i < i1; ++i) b |= (g.bulk[i].mat < 1 || g.bulk[i].mat > n_mats) ? 1 : 0;
+                if (b) bad.store(1, std::memory_order_relaxed);
+            });
+            if (bad.load()) { err = "material handle out of range"; return RTW_ERR_INVALID_ARG; }
+        }
         const long long n_all = (long long)fl.bvh_prims.size() + (with_bulk ? (long long)g.bulk.size() : 0);
         if (n_all >= (1 << 28)) { err = "too many primitives"; return RTW_ERR_INVALID_ARG; }
         out.emit_only = true;
