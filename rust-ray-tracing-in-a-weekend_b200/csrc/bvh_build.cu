@@ -271,7 +271,8 @@ cudaError_t staged_upload(cudaStream_t st, void* dst, const void* src, size_t by
     const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
     cudaError_t errs[kStageThreads];
     std::thread th[kStageThreads];
-    for (int t = 0; t < kStageThreads; ++t) th[t] = std::thread([&, t] {
+    for (int t = 0; t < kStageThreads; ++t) errs[t] = cudaSuccess;
+    auto work = [&](int t) {
         cudaError_t e = cudaSetDevice(dev);
         cudaStream_t s = nullptr; cudaEvent_t ev[kStageSlots] = {};
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
@@ -290,9 +291,13 @@ cudaError_t staged_upload(cudaStream_t st, void* dst, const void* src, size_t by
         for (int k = 0; k < kStageSlots; ++k) if (ev[k]) cudaEventDestroy(ev[k]);
         if (s) cudaStreamDestroy(s);
         errs[t] = e;
-    });
-    for (int t = 0; t < kStageThreads; ++t) th[t].join();
-    (void)st;                                                           // dst was cudaMalloc'ed by the caller; kernels launched from here on see the data
+    };
+    for (int t = 1; t < kStageThreads; ++t) {
+        try { th[t] = std::thread(work, t); } catch (...) { work(t); }     // (no thread to be had: this one does the share; nothing unwinds across the C ABI)
+    }
+    work(0);
+    for (int t = 1; t < kStageThreads; ++t) if (th[t].joinable()) th[t].join();
+    (void)st;                                                           // every chunk has arrived: kernels launched from here on see the data
     for (int t = 0; t < kStageThreads; ++t) if (errs[t] != cudaSuccess) return errs[t];
     return cudaSuccess;
 }
