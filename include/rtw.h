@@ -140,7 +140,10 @@ int rtw_camera_new(const double look_from[3], const double look_at[3], const dou
                    double time0, double time1, rtw_camera* out);
 
 /* Flatten (SoA + linearised BVH), upload one replica per device.  n_gpus <= rtw_device_count();
- * first_device lets one-process-per-GPU launchers pin a rank to its LOCAL_RANK. */
+ * first_device lets one-process-per-GPU launchers pin a rank to its LOCAL_RANK.
+ * Scenes of >= 256 Ki primitives are built on the device: the spheres travel through 64 MiB of pinned staging
+ * buffers that the library allocates once per process, and the builder's scratch comes from a memory pool that is
+ * kept across commits (a re-commit of 16 M spheres: 0.05 s) and returned to the driver by rtw_scene_free. */
 int rtw_scene_commit(rtw_scene*, int32_t n_gpus, int32_t first_device);
 
 /* The hot path: replaces src/main.rs:497-589.  out_rgb_sum = per-pixel SUM of radiance over spp,
