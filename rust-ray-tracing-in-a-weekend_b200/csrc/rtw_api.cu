@@ -61,6 +61,9 @@ __device__ __forceinline__ unsigned long long dbg_now() { unsigned long long t; 
 #endif
 // 7 CTAs = 28 warps per SM at 72 registers: measured best of 6 / 7 / 8 on every config once the kernel had been shrunk
 // (8 CTAs = 64 registers spill ~30 words per thread; 6 CTAs lose more latency hiding than the registers buy)
+#ifndef RTW_NOTILE_MEDIA
+#define RTW_NOTILE_MEDIA 1
+#endif
 #ifndef RTW_MIN_BLOCKS
 #define RTW_MIN_BLOCKS 7
 #endif
@@ -137,7 +140,11 @@ render_kernel(DScene sc, DCamera cam, const __grid_constant__ DParams prm, unsig
         // every primitive a primary ray of this tile can touch (-1: too many, traverse instead)
         // (the small-scene kernels keep their tile lists: without them two_spheres -4.5 % but simple_light +3.8 %, two_perlin_spheres
         // +5.7 %, cornell_box +0.8 %: profiles/r2_al_small_notile.log)
-        const int list_n = (prm.no_tile_cull || !have_unit) ? -1
+        // (not in the big variants that carry the media code — final_scene: their 69 KB are past the reach of the instruction caches,
+        // DESIGN 10-3; without the list code the variant is 736 instructions shorter and final_scene renders in 436.6 instead of
+        // 448.3 ms, profiles/r2_ax_final_scene_code_size.log; primary rays then walk the BVH like every other ray)
+        constexpr bool kNoTile = RTW_NOTILE_MEDIA != 0 && (F & FEAT_MEDIA) && S == 0;
+        const int list_n = (kNoTile || prm.no_tile_cull || !have_unit) ? -1
                            : W ? build_tile_list_wide(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], tl_scr, lane)
                                : build_tile_list(sc, tile_ray_bounds(cam, prm, tx * 8, ty * 4, tw, th), prm.t_min, tlist[warp], tl_scr, lane);
         __syncwarp();
