@@ -9,5 +9,9 @@ for rep in range(2):
         spec = m.scenes.sweep_scene(sc, n)
         t0 = time.time(); sc.commit(1, 0); t1 = time.time()
         print(f"[seq] rep {rep} {n} spheres: commit {1e3 * (t1 - t0):.1f} ms", flush=True)
+        if os.environ.get("SEQ_RENDER"):             # a 4K wavefront render in between, like the bench
+            spp = int(os.environ["SEQ_RENDER"])
+            img, st = sc.render(spec.camera(rtw, 3840, 2160), m.make_params(3840, 2160, spp, background=spec.background, seed=1))
+            print(f"[seq] rep {rep} {n} spheres: render {st['ms_render']:.1f} ms", flush=True)
         t0 = time.time(); sc.close(); t1 = time.time()
         print(f"[seq] rep {rep} {n} spheres: close {1e3 * (t1 - t0):.1f} ms", flush=True)
